@@ -1,0 +1,127 @@
+"""Generate the golden fixtures in tests/golden/ by running the UNMODIFIED reference.
+
+Run in the build container only (it imports /root/reference/models.py, which does not exist
+on the GPU box):
+
+    python tests/golden/make_golden.py
+
+Weights come from melgan_multi_b200.synth (seeded numpy MT19937), loaded into the reference
+modules through load_state_dict, so the fixtures hold inputs' seeds and the reference's
+OUTPUTS only.  Everything is computed by the reference's own forward() on CPU in fp32.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+warnings.filterwarnings("ignore")
+
+import models as ref_models  # noqa: E402  (the reference)
+from melgan_multi_b200 import synth  # noqa: E402
+sys.path.insert(0, HERE)
+import cases  # noqa: E402
+
+
+def load_state(module, state):
+    module.load_state_dict({k: torch.from_numpy(v) for k, v in state.items()}, strict=True)
+    return module.eval()
+
+
+def generator_stage_outputs(gen, x):
+    """Re-run Generator.forward step by step with the reference's own submodules to tap the
+    per-stage activations (same calls as models.py:61-71)."""
+    import torch.nn.functional as F
+    taps = []
+    h = gen.conv_pre(x); taps.append(h)
+    for i in range(4):
+        h = F.leaky_relu(h)
+        h = gen.ups[i](h)
+        h = gen.resblocks[i](h)
+        taps.append(h)
+    h = F.leaky_relu(h)
+    h = gen.conv_post(h); taps.append(h)
+    return [t.detach().numpy() for t in taps], torch.tanh(h).detach().numpy()
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count())
+    out = {}
+
+    # ---------------- generator ----------------
+    gstate = synth.generator_state(1234)
+    gen = load_state(ref_models.Generator(), gstate)
+    with torch.no_grad():
+        for (B, T, seed, realistic) in cases.GEN_CASES:
+            x = synth.mel_input(B, T, seed, realistic)
+            y = gen(torch.from_numpy(x)).numpy()
+            out[cases.gen_key(B, T, seed, realistic)] = y
+        # per-stage taps on a tiny case
+        x = synth.mel_input(1, 3, 5)
+        taps, y = generator_stage_outputs(gen, torch.from_numpy(x))
+        y_direct = gen(torch.from_numpy(x)).numpy()
+        assert np.array_equal(y, y_direct)
+        for i, t in enumerate(taps):
+            out["gen_taps_T3_s5_%d" % i] = t
+        out["gen_taps_T3_s5_audio"] = y
+        # long utterance (config 5): keep three windows and block sums
+        x = synth.mel_input(1, 1000, 0)
+        y = gen(torch.from_numpy(x)).numpy().reshape(-1)
+        out["gen_T1000_head"] = y[:4096].copy()
+        out["gen_T1000_mid"] = y[128000 - 2048:128000 + 2048].copy()
+        out["gen_T1000_tail"] = y[-4096:].copy()
+        out["gen_T1000_blocksum"] = y.astype(np.float64).reshape(250, 1024).sum(axis=1)
+        # weight-norm fold as the reference modules apply it (pre-forward hook output)
+        out["fold_conv_pre"] = gen.conv_pre.weight.detach().numpy()
+        out["fold_ups3"] = gen.ups[3].weight.detach().numpy()
+        out["fold_res2_c1_1"] = gen.resblocks[2].convs1[1].weight.detach().numpy()
+
+    # ---------------- discriminator ----------------
+    dstate = synth.discriminator_state(4321)
+    msd = load_state(ref_models.MultiScaleDiscriminator(), dstate)
+    with torch.no_grad():
+        for (B, L, seed) in cases.MSD_CASES:
+            y = synth.audio_input(B, L, seed)
+            y_hat = synth.audio_input(B, L, seed + 7)
+            rs, gs, frs, fgs = msd(torch.from_numpy(y), torch.from_numpy(y_hat))
+            tag = "msd_B%d_L%d_s%d" % (B, L, seed)
+            for i in range(3):
+                out["%s_logit_r%d" % (tag, i)] = rs[i].numpy()
+                out["%s_logit_g%d" % (tag, i)] = gs[i].numpy()
+                for j in range(7):
+                    for nm, fm in (("r", frs[i][j]), ("g", fgs[i][j])):
+                        a = fm.numpy()
+                        out["%s_fmap_%s%d_%d_shape" % (tag, nm, i, j)] = np.array(a.shape)
+                        out["%s_fmap_%s%d_%d_sum" % (tag, nm, i, j)] = np.array(
+                            [a.astype(np.float64).sum(), np.abs(a.astype(np.float64)).sum()])
+                        out["%s_fmap_%s%d_%d_head" % (tag, nm, i, j)] = a[:, :4, :48].copy()
+            out[tag + "_feature_loss"] = np.array(ref_models.feature_loss(frs, fgs).item())
+            out[tag + "_generator_loss"] = np.array(ref_models.generator_loss(gs).item())
+            dl, rl, gl = ref_models.discriminator_loss(rs, gs)
+            out[tag + "_discriminator_loss"] = np.array([dl.item()] + rl + gl)
+
+    # ---------------- primitive ops (edge cases) ----------------
+    import torch.nn.functional as F
+    for key, kind, prm, x, w, b in cases.op_inputs():
+        tx = torch.from_numpy(x)
+        if kind == "conv":
+            y = F.conv1d(tx, torch.from_numpy(w), torch.from_numpy(b), *prm)
+        elif kind == "convT":
+            y = F.conv_transpose1d(tx, torch.from_numpy(w), torch.from_numpy(b), *prm)
+        else:
+            y = torch.nn.AvgPool1d(prm[0], prm[1], padding=prm[2])(tx)
+        out[key] = y.numpy()
+
+    path = os.path.join(HERE, "reference_outputs.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, "%.2f MB" % (os.path.getsize(path) / 1e6), len(out), "arrays")
+
+
+if __name__ == "__main__":
+    main()

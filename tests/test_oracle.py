@@ -1,0 +1,98 @@
+"""The C oracle (oracle/melgan_oracle.c) against the reference's own outputs (tests/golden)."""
+import numpy as np
+import pytest
+
+import cases
+from conftest import rel_errors
+from melgan_multi_b200 import synth
+from oracle import cport
+
+TOL = 2e-5  # fp32 reference (oneDNN summation order) vs double-accumulating oracle
+
+
+@pytest.fixture(scope="module")
+def gen_folded():
+    return cport.fold_generator(synth.generator_state(1234))
+
+
+@pytest.fixture(scope="module")
+def msd_folded():
+    return cport.fold_discriminators(synth.discriminator_state(4321))
+
+
+def test_primitive_ops_match_reference(golden):
+    for key, kind, prm, x, w, b in cases.op_inputs():
+        if kind == "conv":
+            y = cport.conv1d(x, w, b, *prm)
+        elif kind == "convT":
+            y = cport.conv_transpose1d(x, w, b, *prm)
+        else:
+            y = cport.avgpool1d(x, *prm)
+        ref = golden[key]
+        assert y.shape == ref.shape, key
+        m, l2 = rel_errors(y, ref)
+        assert m < 1e-5 and l2 < 1e-5, (key, m, l2)
+
+
+def test_weight_norm_fold_matches_reference_hook(golden):
+    st = synth.generator_state(1234)
+    for key, name in (("fold_conv_pre", "conv_pre"), ("fold_ups3", "ups.3"),
+                      ("fold_res2_c1_1", "resblocks.2.convs1.1")):
+        w = cport.fold_weight_norm(st[name + ".weight_g"], st[name + ".weight_v"])
+        np.testing.assert_allclose(w, golden[key], rtol=2e-6, atol=1e-8)
+        np.testing.assert_allclose(synth.fold_weight_norm(st[name + ".weight_g"], st[name + ".weight_v"]),
+                                   golden[key], rtol=2e-6, atol=1e-8)
+
+
+@pytest.mark.parametrize("case", cases.GEN_CASES)
+def test_generator_matches_reference(golden, gen_folded, case):
+    B, T, seed, realistic = case
+    ws, bs = gen_folded
+    y = cport.generator_forward(ws, bs, synth.mel_input(B, T, seed, realistic))
+    ref = golden[cases.gen_key(*case)]
+    assert y.shape == ref.shape == (B, 1, 256 * T)
+    m, l2 = rel_errors(y, ref)
+    assert m < TOL and l2 < TOL, (case, m, l2)
+
+
+def test_generator_stage_taps_match_reference(golden, gen_folded):
+    ws, bs = gen_folded
+    y, stages = cport.generator_forward(ws, bs, synth.mel_input(1, 3, 5), want_stages=True)
+    for i, s in enumerate(stages):
+        m, l2 = rel_errors(s, golden["gen_taps_T3_s5_%d" % i])
+        assert m < TOL and l2 < TOL, (i, m, l2)
+    assert rel_errors(y, golden["gen_taps_T3_s5_audio"])[0] < TOL
+
+
+def test_generator_long_utterance_matches_reference(golden, gen_folded):
+    ws, bs = gen_folded
+    y = cport.generator_forward(ws, bs, synth.mel_input(1, 1000, 0)).reshape(-1)
+    scale = np.abs(golden["gen_T1000_mid"]).max()
+    assert np.abs(y[:4096] - golden["gen_T1000_head"]).max() < TOL * scale
+    assert np.abs(y[128000 - 2048:128000 + 2048] - golden["gen_T1000_mid"]).max() < TOL * scale
+    assert np.abs(y[-4096:] - golden["gen_T1000_tail"]).max() < TOL * scale
+    bs_ = y.astype(np.float64).reshape(250, 1024).sum(axis=1)
+    assert np.abs(bs_ - golden["gen_T1000_blocksum"]).max() < 1024 * TOL * scale
+
+
+@pytest.mark.parametrize("case", cases.MSD_CASES)
+def test_msd_matches_reference(golden, msd_folded, case):
+    B, L, seed = case
+    y = synth.audio_input(B, L, seed)
+    y_hat = synth.audio_input(B, L, seed + 7)
+    rs, gs, frs, fgs = cport.msd_forward(msd_folded, y, y_hat)
+    tag = "msd_B%d_L%d_s%d" % (B, L, seed)
+    for i in range(3):
+        for nm, lg, fm in (("r", rs, frs), ("g", gs, fgs)):
+            ref = golden["%s_logit_%s%d" % (tag, nm, i)]
+            assert lg[i].shape == ref.shape
+            m, l2 = rel_errors(lg[i], ref)
+            assert m < 5e-5 and l2 < 5e-5, (i, nm, m, l2)
+            for j in range(7):
+                a = fm[i][j]
+                assert tuple(golden["%s_fmap_%s%d_%d_shape" % (tag, nm, i, j)]) == a.shape
+                head = golden["%s_fmap_%s%d_%d_head" % (tag, nm, i, j)]
+                m, _ = rel_errors(a[:, :4, :48], head)
+                assert m < 5e-5, (i, j, nm, m)
+                s = golden["%s_fmap_%s%d_%d_sum" % (tag, nm, i, j)]
+                assert abs(np.abs(a.astype(np.float64)).sum() - s[1]) < 1e-5 * s[1]
