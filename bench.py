@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json metric: audio frames/sec (22.05 kHz) of the generator forward.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is one generator forward over one synthetic batch of config 2 (B=64 mel segments of
+80 x 32 frames -> 64 x 8192 audio frames) per GPU.  1 audio frame = 1 PCM sample; 1 mel frame = 256
+audio frames.  Weights are seeded random-init (melgan_multi_b200.synth), data synthetic.
+
+  value      device-resident throughput: mel already in HBM, CUDA events around the C-ABI
+             device-pointer call (mg_gen_forward), L2 flushed between steps, max over ranks.
+  e2e        the same metric through the host-buffer C ABI (mg_gen_engine_forward): pinned host mel
+             in, H2D copy, kernels, D2H copy of the audio out, every step, wall clock, max over ranks.
+  roofline   dominant kernel (stage 1: ConvT 256->128 + 128-channel ResBlock, 44% of the FLOPs),
+             per-kernel CUDA events from mg_gen_forward_timed in a second pass of K steps.
+  cpu_baseline  oracle/torch_port.py (the reference's arithmetic on PyTorch-CPU/oneDNN, all host
+             threads) on a bounded sample, rank 0 at N=1 only.
+  --impl reference   times that same CPU port as the reference arm (the reference is pure Python and
+             /root/reference does not exist on the GPU box).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+B_PER_GPU, T_FRAMES = 64, 32
+METRIC = "generator_fwd_audio_frames_per_sec"
+UNIT = "audio_frames/s"
+WORKLOAD = "configs[1]: Generator forward, batch=64, 80x32 mel -> 64x8192 samples, fp32"
+
+
+def flops_per_mel_frame():
+    pre = 2 * 80 * 512 * 7
+    stages = []
+    for i, (cin, cout, s) in enumerate([(512, 256, 8), (256, 128, 8), (128, 64, 2), (64, 32, 2)]):
+        up = [8, 64, 128, 256][i]
+        stages.append(up * (2 * 2 * cin * cout) + up * 6 * (2 * cout * cout * 3))
+    post = 2 * 32 * 7 * 256
+    return pre, stages, post
+
+
+ALG_BYTES_PER_FRAME = 152896  # per-stage-fused design, fp32 activations in/out of each kernel
+STAGE_BYTES_PER_FRAME = [320 * 1 + 2048, 2048 + 8192, 8192 + 32768, 32768 + 32768, 32768 + 1024]
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained"), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            if len(r) < 8:
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[4:8]):
+                if v.strip() == "Active":
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # "under load": samples in the upper half of the observed range
+        hi = [c for c in sm if c >= 0.5 * max(sm)]
+        return {"sm_mhz": statistics.median(hi), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_port_throughput(sample_B, budget_s, min_iters=2):
+    """Times oracle/torch_port.py on all host threads.  Returns (audio_frames/s, cores, iters, per-iter s)."""
+    import torch
+    from melgan_multi_b200 import synth
+    from oracle import torch_port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ws, bs = torch_port.fold_state(synth.generator_state(1234))
+    x = torch.from_numpy(synth.mel_input(sample_B, T_FRAMES, 0))
+    torch_port.generator_forward(ws, bs, x)  # warm-up
+    times, t_all = [], time.perf_counter()
+    while len(times) < min_iters or (time.perf_counter() - t_all) < budget_s:
+        t0 = time.perf_counter()
+        torch_port.generator_forward(ws, bs, x)
+        times.append(time.perf_counter() - t0)
+        if len(times) >= 50:
+            break
+    med = statistics.median(times)
+    return sample_B * T_FRAMES * 256 / med, cores, len(times), med
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU implementation (PyTorch-CPU port of models.py:61-71)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from melgan_multi_b200 import synth
+    from oracle import torch_port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample_B = 16
+    ws, bs = torch_port.fold_state(synth.generator_state(1234))
+    x = torch.from_numpy(synth.mel_input(sample_B, T_FRAMES, 0))
+    for _ in range(max(1, min(args.warmup, 3))):
+        torch_port.generator_forward(ws, bs, x)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        torch_port.generator_forward(ws, bs, x)
+    dt = time.perf_counter() - t0
+    val = args.steps * sample_B * T_FRAMES * 256 / dt
+    sample = "B=%d of the 64 x 80x32 mel segments per step, PyTorch-CPU (oneDNN) port of the reference forward, %d threads" % (
+        sample_B, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU-baseline timing")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from melgan_multi_b200 import engine, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    K, W, B, T = args.steps, args.warmup, B_PER_GPU, T_FRAMES
+    peaks = load_peaks()
+    state = synth.generator_state(1234)
+
+    # ---- device-resident path -----------------------------------------------------------
+    gd = engine.GeneratorDevice(dev)
+    order = [n for n, *_ in synth.GENERATOR_LAYERS]
+    to = lambda a: torch.from_numpy(a).to(dev)
+    gd.pack([to(state[n + ".weight_v"]) for n in order], [to(state[n + ".weight_g"]) for n in order],
+            [to(state[n + ".bias"]) for n in order])
+    mels = [to(synth.mel_input(B, T, 10 * rank + i)) for i in range(4)]
+    out = torch.empty((B, 1, 256 * T), dtype=torch.float32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    sampler = ClockSampler(local_rank)
+    for i in range(W):
+        flush.zero_()
+        gd.forward(mels[i % 4], out)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier()
+    for k in range(K):
+        flush.zero_()
+        ev[k][0].record()
+        gd.forward(mels[k % 4], out)
+        ev[k][1].record()
+    barrier()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = max_over_ranks(sum(step_ms))
+    frames_per_step = B * T * 256 * world
+    value = K * frames_per_step / (total_ms * 1e-3)
+
+    # ---- per-kernel pass (roofline) -------------------------------------------------------
+    kms = np.zeros(5)
+    for k in range(K):
+        flush.zero_()
+        kms += np.array(gd.forward_timed(mels[k % 4], out))
+    kms /= K
+    clocks = sampler.stop()
+    pre_f, stage_f, post_f = flops_per_mel_frame()
+    frames = B * T
+    k_flops = [pre_f * frames] + [f * frames for f in stage_f]
+    k_flops[4] += post_f * frames
+    dom = 2  # kernel index of stage 1
+    dom_tflops = k_flops[dom] / (kms[dom] * 1e-3) / 1e12
+    fwd_flops = sum(k_flops)
+    packed_bytes = engine.lib().mg_gen_packed_bytes()
+    fwd_bytes = ALG_BYTES_PER_FRAME * frames + packed_bytes
+    fwd_ms = total_ms / K
+    roofline = {
+        "kernel": "gen_stage_kernel<stage 1: lrelu+ConvT(256->128,k16,s8)+ResBlock(128)>",
+        "bound": "tensor", "achieved": dom_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+        "frac": dom_tflops / peaks["bf16_tflops"], "traffic": None,
+        "peak_source": "%s bf16 dense burst (MEASURED_PEAKS.json)" % peaks["source"],
+        "algorithmic_flops_per_launch": k_flops[dom], "avg_launch_ms": float(kms[dom]),
+        "math": "fp32 FFMA (SIMT), 1 pass; tensor pipe not used yet",
+        "kernel_ms": {n: float(v) for n, v in zip(["conv_pre", "stage0", "stage1", "stage2", "stage3+post"], kms)},
+        "kernel_tflops": {n: k_flops[i] / (kms[i] * 1e-3) / 1e12 for i, n in
+                          enumerate(["conv_pre", "stage0", "stage1", "stage2", "stage3+post"])},
+        "hbm": {"achieved": fwd_bytes / (fwd_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": fwd_bytes / (fwd_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                "algorithmic_bytes_per_forward": fwd_bytes,
+                "note": "whole forward; the fused generator is 683 FLOP/B, i.e. math-bound (SURVEY 8d)"},
+        "forward_tflops": fwd_flops / (fwd_ms * 1e-3) / 1e12,
+    }
+
+    # ---- end to end through the host-buffer C ABI -----------------------------------------
+    host = engine.GeneratorHost(B, T)
+    host.load_state(state)
+    pin_in = [torch.from_numpy(synth.mel_input(B, T, 10 * rank + i)).pin_memory() for i in range(4)]
+    pin_out = torch.empty((B, 1, 256 * T), dtype=torch.float32).pin_memory()
+    for i in range(W):
+        host.forward_ptr(pin_in[i % 4].data_ptr(), pin_out.data_ptr(), B, T)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(K):
+        host.forward_ptr(pin_in[k % 4].data_ptr(), pin_out.data_ptr(), B, T)
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    checksum = float(pin_out.double().abs().sum())
+    e2e_s = max_over_ranks(e2e_s)
+    e2e_value = K * frames_per_step / e2e_s
+    host.close()
+
+    cpu = None
+    if rank == 0 and world == 1:
+        v, cores, iters, med = cpu_port_throughput(4, args.cpu_budget)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "B=4 of the 64 segments (80x32 mel each), %d iterations, median %.3f s; "
+                         "oracle/torch_port.py = the reference forward on PyTorch-CPU/oneDNN, all threads" % (iters, med)}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "mel_frames": T, "global_batch": B * world,
+                       "parallelism": "dp%d (independent batches, no collective)" % world,
+                       "l2": "flushed between steps (256 MiB memset)", "weights": "seeded random init"},
+            "mel_frames_per_s": value / 256, "realtime_factor": value / 22050.0,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 80 * T * 4 * world,
+                    "d2h_bytes_per_step": B * 256 * T * 4 * world, "ms_per_step": 1e3 * e2e_s / K,
+                    "api": "mg_gen_engine_forward (host buffers, pinned)", "output_abs_sum": checksum},
+            "gpu_launches": K * world * engine.lib().mg_gen_forward_launches(),
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

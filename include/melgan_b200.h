@@ -1,0 +1,117 @@
+/*
+ * melgan_b200.h -- C ABI of the B200-native MelGAN engine (libmelgan_b200.so).
+ *
+ * The reference (diver-j/melgan-multi) has no FFI or operator registry: its boundary for the
+ * hot path is the torch.nn.Module protocol of models.py, imported by name at train.py:13
+ * (`from models import Generator, MultiScaleDiscriminator, ...`).  This library sits directly
+ * underneath a drop-in `models` module (melgan_multi_b200/models.py); each entry point below
+ * names the reference code it replaces.  Plain pointers and sizes only, no torch types.
+ *
+ * Conventions
+ *   - Every function returns 0 on success or a negative MG_ERR_* code; the message for the
+ *     calling thread is available from mg_last_error_string().  Nothing throws or exits.
+ *   - "device pointer" arguments are CUDA device addresses owned by the caller (PyTorch
+ *     storage in practice); the library never frees or retains them past the call.
+ *   - Tensors are fp32, contiguous, NCL ([batch][channel][length]) exactly like the
+ *     reference's (models.py:61-71 takes [B,80,T], returns [B,1,256*T]).
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued asynchronously on it and
+ *     the library never synchronises the device in the device-pointer entry points.
+ *   - Re-entrant: no mutable global state except the thread-local error string.
+ */
+#ifndef MELGAN_B200_H_
+#define MELGAN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MG_OK 0
+#define MG_ERR_INVALID_ARGUMENT (-1)
+#define MG_ERR_CUDA (-2)
+#define MG_ERR_UNSUPPORTED_DEVICE (-3)
+#define MG_ERR_WORKSPACE_TOO_SMALL (-4)
+#define MG_ERR_OUT_OF_MEMORY (-5)
+
+#define MG_GEN_NUM_LAYERS 30 /* conv_pre, ups[0..3], 4 x (convs1[0..2], convs2[0..2]), conv_post */
+
+/* ABI version of this header (bumped on any signature change). */
+int mg_abi_version(void);
+
+/* Message describing the last failure on the calling thread ("" if none). */
+const char *mg_last_error_string(void);
+
+/* 0 if the current CUDA device can run the sm_100a kernels, MG_ERR_UNSUPPORTED_DEVICE /
+ * MG_ERR_CUDA otherwise.  There is no CPU fallback anywhere in this library. */
+int mg_device_check(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Weight-norm fold + packing.   Replaces: the weight_norm pre-forward hooks that recompute
+ * w = g * v / ||v|| on every forward of every layer (models.py:16-28,46-59; 30 launches of
+ * aten::_weight_norm_interface per Generator.forward) with ONE launch that folds
+ * all 30 layers and writes them in the layouts the fused kernels stream from.
+ *
+ * v, g, bias: HOST arrays of MG_GEN_NUM_LAYERS DEVICE pointers in reference registration
+ * order (conv_pre, ups.0-3, resblocks.0.convs1.0-2, resblocks.0.convs2.0-2, ..., conv_post);
+ * shapes as in the reference state_dict (Conv1d weight_v [Cout,Cin,K], weight_g [Cout,1,1];
+ * ConvTranspose1d weight_v [Cin,Cout,K], weight_g [Cin,1,1] -- the norm is per dim 0).
+ * packed: device buffer of mg_gen_packed_bytes() bytes, 256-byte aligned.
+ */
+size_t mg_gen_packed_bytes(void);
+int mg_gen_pack(const float *const *v, const float *const *g, const float *const *bias,
+                void *packed, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Generator forward.   Replaces: models.Generator.forward (models.py:61-71): conv_pre, four
+ * fused (LeakyReLU -> ConvTranspose1d -> ResBlock) stages (ResBlock.forward, models.py:32-40),
+ * LeakyReLU -> conv_post -> tanh fused into the last stage.
+ *
+ * mel   [B, 80, T]     device, fp32
+ * audio [B, 1, 256*T]  device, fp32
+ * workspace: device scratch of at least mg_gen_workspace_bytes(B, T) bytes, 256-byte aligned.
+ * Any B >= 1, T >= 1 (train.py:157 feeds whole utterances).
+ */
+size_t mg_gen_workspace_bytes(int B, int T);
+int mg_gen_forward(const void *packed, const float *mel, float *audio, int B, int T,
+                   void *workspace, size_t workspace_bytes, void *stream);
+
+/* Same as mg_gen_forward, but brackets each of the mg_gen_forward_launches() kernels with CUDA
+ * events on `stream`, waits for the last one and returns the per-kernel device times in
+ * kernel_ms[0..4] (conv_pre, stage 0..3).  Used by bench.py for the per-kernel roofline. */
+int mg_gen_forward_timed(const void *packed, const float *mel, float *audio, int B, int T,
+                         void *workspace, size_t workspace_bytes, void *stream, float *kernel_ms);
+
+/* Debug/parity tap: copies the activation after stage `which` (0 = conv_pre output [B,512,T],
+ * 1..3 = ResBlock 0..2 output [B,C,L]; the last stage is fused with conv_post and has no tap) of the LAST mg_gen_forward that used `workspace` into
+ * `out` (device, NCL).  Only valid immediately after that call on the same stream. */
+int mg_gen_stage_output(const void *workspace, int which, float *out, int B, int T, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Host-buffer engine.   The call a non-PyTorch host makes: owns its device buffers, takes and
+ * returns HOST memory, and performs the host<->device copies itself (this is the path
+ * bench.py times as "e2e").  One engine per host thread / CUDA stream.
+ */
+typedef struct mg_gen_engine mg_gen_engine;
+
+/* Creates an engine able to run up to max_B x max_T (it grows on demand if exceeded). */
+int mg_gen_engine_create(mg_gen_engine **out, int max_B, int max_T);
+/* v/g/bias: HOST arrays of 30 HOST pointers (state_dict tensors, reference order). */
+int mg_gen_engine_load_state(mg_gen_engine *e, const float *const *v, const float *const *g,
+                             const float *const *bias);
+/* mel_host [B,80,T] -> audio_host [B,1,256T]; synchronous (returns when audio_host is filled).
+ * Pinned host memory is used as given; pageable memory is staged through an internal pinned
+ * buffer. */
+int mg_gen_engine_forward(mg_gen_engine *e, const float *mel_host, float *audio_host, int B, int T);
+/* Device time of the kernels of the last forward, in milliseconds (CUDA events). */
+int mg_gen_engine_last_kernel_ms(mg_gen_engine *e, float *ms);
+void mg_gen_engine_destroy(mg_gen_engine *e);
+
+/* Number of kernel launches one mg_gen_forward enqueues (for bench.py's gpu_launches). */
+int mg_gen_forward_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MELGAN_B200_H_ */

@@ -1,0 +1,218 @@
+// C ABI of libmelgan_b200.so (see include/melgan_b200.h for the contract of every entry point).
+#include <new>
+#include <string.h>
+
+#include "mg_common.cuh"
+
+namespace mg {
+
+static thread_local char g_error[512] = "";
+
+char *error_buffer() { return g_error; }
+
+int set_error(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+static int check_shape(const char *fn, int B, int T) {
+    if (B < 1 || T < 1) return set_error(MG_ERR_INVALID_ARGUMENT, "%s: need B >= 1 and T >= 1 (got B=%d, T=%d)", fn, B, T);
+    if ((long long)B * T > (1ll << 24)) return set_error(MG_ERR_INVALID_ARGUMENT, "%s: B*T = %lld too large", fn, (long long)B * T);
+    return MG_OK;
+}
+
+}  // namespace mg
+
+using namespace mg;
+
+extern "C" {
+
+int mg_abi_version(void) { return 1; }
+
+const char *mg_last_error_string(void) { return error_buffer(); }
+
+int mg_device_check(void) {
+    int dev = 0;
+    MG_CUDA_TRY(cudaGetDevice(&dev));
+    cudaDeviceProp p;
+    MG_CUDA_TRY(cudaGetDeviceProperties(&p, dev));
+    if (p.major != 10)
+        return set_error(MG_ERR_UNSUPPORTED_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                         dev, p.major, p.minor);
+    return MG_OK;
+}
+
+size_t mg_gen_packed_bytes(void) { return packed_float_count() * sizeof(float); }
+
+int mg_gen_pack(const float *const *v, const float *const *g, const float *const *bias, void *packed, void *stream) {
+    if (!v || !g || !bias || !packed) return set_error(MG_ERR_INVALID_ARGUMENT, "mg_gen_pack: null argument");
+    if ((uintptr_t)packed % 16) return set_error(MG_ERR_INVALID_ARGUMENT, "mg_gen_pack: packed must be 16-byte aligned");
+    return launch_pack(v, g, bias, (float *)packed, (cudaStream_t)stream);
+}
+
+size_t mg_gen_workspace_bytes(int B, int T) {
+    if (B < 1 || T < 1) return 0;
+    return ws_offset(4, (size_t)B, (size_t)T) * sizeof(float);
+}
+
+int mg_gen_forward(const void *packed, const float *mel, float *audio, int B, int T, void *workspace,
+                   size_t workspace_bytes, void *stream) {
+    int rc = check_shape("mg_gen_forward", B, T);
+    if (rc) return rc;
+    if (!packed || !mel || !audio || !workspace) return set_error(MG_ERR_INVALID_ARGUMENT, "mg_gen_forward: null argument");
+    if (workspace_bytes < mg_gen_workspace_bytes(B, T))
+        return set_error(MG_ERR_WORKSPACE_TOO_SMALL, "mg_gen_forward: workspace %zu < %zu bytes", workspace_bytes,
+                         mg_gen_workspace_bytes(B, T));
+    if ((uintptr_t)packed % 16 || (uintptr_t)workspace % 16)
+        return set_error(MG_ERR_INVALID_ARGUMENT, "mg_gen_forward: packed/workspace must be 16-byte aligned");
+    return launch_generator_simt((const float *)packed, mel, audio, B, T, (float *)workspace, (cudaStream_t)stream);
+}
+
+int mg_gen_forward_timed(const void *packed, const float *mel, float *audio, int B, int T, void *workspace,
+                         size_t workspace_bytes, void *stream, float *kernel_ms) {
+    int rc = check_shape("mg_gen_forward_timed", B, T);
+    if (rc) return rc;
+    if (!packed || !mel || !audio || !workspace || !kernel_ms)
+        return set_error(MG_ERR_INVALID_ARGUMENT, "mg_gen_forward_timed: null argument");
+    if (workspace_bytes < mg_gen_workspace_bytes(B, T))
+        return set_error(MG_ERR_WORKSPACE_TOO_SMALL, "mg_gen_forward_timed: workspace too small");
+    cudaEvent_t ev[6];
+    for (int i = 0; i < 6; ++i) MG_CUDA_TRY(cudaEventCreate(&ev[i]));
+    rc = launch_generator_simt((const float *)packed, mel, audio, B, T, (float *)workspace, (cudaStream_t)stream, ev);
+    if (rc == MG_OK) {
+        cudaError_t e = cudaEventSynchronize(ev[5]);
+        if (e != cudaSuccess) rc = set_error(MG_ERR_CUDA, "mg_gen_forward_timed: %s", cudaGetErrorString(e));
+        for (int i = 0; i < 5 && rc == MG_OK; ++i)
+            if (cudaEventElapsedTime(&kernel_ms[i], ev[i], ev[i + 1]) != cudaSuccess)
+                rc = set_error(MG_ERR_CUDA, "mg_gen_forward_timed: cudaEventElapsedTime failed");
+    }
+    for (int i = 0; i < 6; ++i) cudaEventDestroy(ev[i]);
+    return rc;
+}
+
+int mg_gen_stage_output(const void *workspace, int which, float *out, int B, int T, void *stream) {
+    int rc = check_shape("mg_gen_stage_output", B, T);
+    if (rc) return rc;
+    if (which < 0 || which > 3 || !workspace || !out)
+        return set_error(MG_ERR_INVALID_ARGUMENT, "mg_gen_stage_output: which must be 0..3 (the last stage is fused with conv_post)");
+    const size_t off = ws_offset(which, B, T), n = ws_offset(which + 1, B, T) - off;
+    MG_CUDA_TRY(cudaMemcpyAsync(out, (const float *)workspace + off, n * sizeof(float), cudaMemcpyDeviceToDevice,
+                                (cudaStream_t)stream));
+    return MG_OK;
+}
+
+int mg_gen_forward_launches(void) { return generator_simt_num_launches(); }
+
+/* ------------------------------- host-buffer engine ------------------------------------- */
+
+struct mg_gen_engine {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float *packed = nullptr;
+    float *raw = nullptr;  // device staging for raw v/g/bias
+    float *mel = nullptr, *audio = nullptr, *ws = nullptr;
+    float *pin_in = nullptr, *pin_out = nullptr;
+    size_t cap_frames = 0;  // B*T capacity
+    bool loaded = false;
+    float last_ms = 0.f;
+};
+
+static void engine_free_io(mg_gen_engine *e) {
+    cudaFree(e->mel); cudaFree(e->audio); cudaFree(e->ws);
+    cudaFreeHost(e->pin_in); cudaFreeHost(e->pin_out);
+    e->mel = e->audio = e->ws = e->pin_in = e->pin_out = nullptr;
+    e->cap_frames = 0;
+}
+
+static int engine_reserve(mg_gen_engine *e, size_t frames) {
+    if (frames <= e->cap_frames) return MG_OK;
+    engine_free_io(e);
+    MG_CUDA_TRY(cudaMalloc(&e->mel, frames * kMelBins * sizeof(float)));
+    MG_CUDA_TRY(cudaMalloc(&e->audio, frames * 256 * sizeof(float)));
+    MG_CUDA_TRY(cudaMalloc(&e->ws, ws_offset(4, 1, frames) * sizeof(float)));
+    MG_CUDA_TRY(cudaMallocHost(&e->pin_in, frames * kMelBins * sizeof(float)));
+    MG_CUDA_TRY(cudaMallocHost(&e->pin_out, frames * 256 * sizeof(float)));
+    e->cap_frames = frames;
+    return MG_OK;
+}
+
+int mg_gen_engine_create(mg_gen_engine **out, int max_B, int max_T) {
+    if (!out) return set_error(MG_ERR_INVALID_ARGUMENT, "mg_gen_engine_create: null out");
+    int rc = check_shape("mg_gen_engine_create", max_B, max_T);
+    if (rc) return rc;
+    if ((rc = mg_device_check())) return rc;
+    mg_gen_engine *e = new (std::nothrow) mg_gen_engine();
+    if (!e) return set_error(MG_ERR_OUT_OF_MEMORY, "mg_gen_engine_create: host allocation failed");
+    *out = e;
+    MG_CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    MG_CUDA_TRY(cudaEventCreate(&e->ev0));
+    MG_CUDA_TRY(cudaEventCreate(&e->ev1));
+    MG_CUDA_TRY(cudaMalloc(&e->packed, mg_gen_packed_bytes()));
+    MG_CUDA_TRY(cudaMalloc(&e->raw, (packed_float_count() + 4353) * sizeof(float)));
+    return engine_reserve(e, (size_t)max_B * max_T);
+}
+
+int mg_gen_engine_load_state(mg_gen_engine *e, const float *const *v, const float *const *g, const float *const *bias) {
+    if (!e || !v || !g || !bias) return set_error(MG_ERR_INVALID_ARGUMENT, "mg_gen_engine_load_state: null argument");
+    const float *dv[kNumLayers], *dg[kNumLayers], *db[kNumLayers];
+    float *p = e->raw;
+    for (int l = 0; l < kNumLayers; ++l) {
+        if (!v[l] || !g[l] || !bias[l]) return set_error(MG_ERR_INVALID_ARGUMENT, "mg_gen_engine_load_state: null tensor, layer %d", l);
+        const size_t nv = layer_weight_count(l), ng = layer_norm_rows(l), nb = layer_shape(l).cout;
+        MG_CUDA_TRY(cudaMemcpyAsync(p, v[l], nv * sizeof(float), cudaMemcpyHostToDevice, e->stream)); dv[l] = p; p += nv;
+        MG_CUDA_TRY(cudaMemcpyAsync(p, g[l], ng * sizeof(float), cudaMemcpyHostToDevice, e->stream)); dg[l] = p; p += ng;
+        MG_CUDA_TRY(cudaMemcpyAsync(p, bias[l], nb * sizeof(float), cudaMemcpyHostToDevice, e->stream)); db[l] = p; p += nb;
+    }
+    int rc = launch_pack(dv, dg, db, e->packed, e->stream);
+    if (rc) return rc;
+    MG_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    e->loaded = true;
+    return MG_OK;
+}
+
+int mg_gen_engine_forward(mg_gen_engine *e, const float *mel_host, float *audio_host, int B, int T) {
+    if (!e || !mel_host || !audio_host) return set_error(MG_ERR_INVALID_ARGUMENT, "mg_gen_engine_forward: null argument");
+    int rc = check_shape("mg_gen_engine_forward", B, T);
+    if (rc) return rc;
+    if (!e->loaded) return set_error(MG_ERR_INVALID_ARGUMENT, "mg_gen_engine_forward: no weights loaded");
+    const size_t frames = (size_t)B * T;
+    if ((rc = engine_reserve(e, frames))) return rc;
+    const size_t nin = frames * kMelBins * sizeof(float), nout = frames * 256 * sizeof(float);
+    cudaPointerAttributes at;
+    const bool in_pinned = cudaPointerGetAttributes(&at, mel_host) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    const bool out_pinned = cudaPointerGetAttributes(&at, audio_host) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();  // clear "invalid value" some drivers raise for pageable pointers
+    const float *src = mel_host;
+    if (!in_pinned) { memcpy(e->pin_in, mel_host, nin); src = e->pin_in; }
+    MG_CUDA_TRY(cudaMemcpyAsync(e->mel, src, nin, cudaMemcpyHostToDevice, e->stream));
+    MG_CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
+    rc = launch_generator_simt(e->packed, e->mel, e->audio, B, T, e->ws, e->stream);
+    if (rc) return rc;
+    MG_CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
+    MG_CUDA_TRY(cudaMemcpyAsync(out_pinned ? audio_host : e->pin_out, e->audio, nout, cudaMemcpyDeviceToHost, e->stream));
+    MG_CUDA_TRY(cudaStreamSynchronize(e->stream));
+    if (!out_pinned) memcpy(audio_host, e->pin_out, nout);
+    MG_CUDA_TRY(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
+    return MG_OK;
+}
+
+int mg_gen_engine_last_kernel_ms(mg_gen_engine *e, float *ms) {
+    if (!e || !ms) return set_error(MG_ERR_INVALID_ARGUMENT, "mg_gen_engine_last_kernel_ms: null argument");
+    *ms = e->last_ms;
+    return MG_OK;
+}
+
+void mg_gen_engine_destroy(mg_gen_engine *e) {
+    if (!e) return;
+    engine_free_io(e);
+    cudaFree(e->packed); cudaFree(e->raw);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+}  // extern "C"

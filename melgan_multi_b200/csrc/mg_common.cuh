@@ -1,0 +1,45 @@
+// Shared helpers: error plumbing for the C ABI, cp.async wrappers, activation.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/melgan_b200.h"
+#include "mg_layout.h"
+
+namespace mg {
+
+// thread-local error string (the only mutable global state of the library)
+char *error_buffer();
+int set_error(int code, const char *fmt, ...);
+
+#define MG_CUDA_TRY(expr)                                                                     \
+    do {                                                                                      \
+        cudaError_t err__ = (expr);                                                           \
+        if (err__ != cudaSuccess)                                                             \
+            return ::mg::set_error(MG_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,               \
+                                   cudaGetErrorString(err__), __FILE__, __LINE__);            \
+    } while (0)
+
+__device__ __forceinline__ float lrelu(float x) { return fmaxf(x, x * kSlope); }
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// ---- launches implemented in the .cu files ------------------------------------------------
+int launch_pack(const float *const *v, const float *const *g, const float *const *bias, float *packed,
+                cudaStream_t s);
+// ev: nullptr, or 6 events recorded before each of the 5 launches and after the last one
+int launch_generator_simt(const float *packed, const float *mel, float *audio, int B, int T, float *ws,
+                          cudaStream_t s, cudaEvent_t *ev = nullptr);
+int generator_simt_num_launches();
+
+}  // namespace mg

@@ -1,0 +1,87 @@
+// Generator layer table and the packed-weight layout (host + device).
+//
+// Layer order is the reference's registration order (models.py:46-59):
+//   0 conv_pre | 1..4 ups[0..3] | 5+6i+j resblocks[i].convs1[j] | 5+6i+3+j resblocks[i].convs2[j] | 29 conv_post
+//
+// Packed layouts (what the kernels stream; all fp32, folded w = g*v/||v||):
+//   Conv1d  [Cout][Cin][K]  ->  [Cin][K][Cout]      (Cout contiguous: a chunk of input channels is
+//                                                    one contiguous block, co-vectors are float4-loadable)
+//   ConvT1d [Cin][Cout][K]  ->  [Cin][Cout][S][2]   (K = 2S; the two taps (phase, phase+S) that reach one
+//                                                    output phase sit side by side)
+//   conv_post [1][32][7]    ->  [32][7]             (same as raw; Cout = 1)
+//   biases: concatenated in layer order after the weights.
+#pragma once
+#include <stddef.h>
+
+#ifndef MG_HD
+#ifdef __CUDACC__
+#define MG_HD __host__ __device__
+#else
+#define MG_HD
+#endif
+#endif
+
+namespace mg {
+
+constexpr int kNumLayers = 30;
+constexpr int kMelBins = 80;
+constexpr int kPreCout = 512;
+constexpr int kPreK = 7;
+constexpr int kPostK = 7;
+constexpr float kSlope = 0.01f;  // F.leaky_relu default (models.py:35,37,64,67)
+
+struct LayerShape {
+    int kind;  // 0 = Conv1d, 1 = ConvTranspose1d
+    int cin, cout, k;
+    int stride;  // ConvT only
+};
+
+MG_HD constexpr int stage_cin(int i) { return 512 >> i; }
+MG_HD constexpr int stage_cout(int i) { return 256 >> i; }
+MG_HD constexpr int stage_stride(int i) { return i < 2 ? 8 : 2; }
+MG_HD constexpr int stage_kup(int i) { return i < 2 ? 16 : 4; }
+MG_HD constexpr int stage_pad(int i) { return i < 2 ? 4 : 1; }
+// cumulative upsampling factor after stage i: 8, 64, 128, 256
+MG_HD constexpr int stage_upfactor(int i) { return i == 0 ? 8 : i == 1 ? 64 : i == 2 ? 128 : 256; }
+
+MG_HD constexpr LayerShape layer_shape(int l) {
+    if (l == 0) return {0, kMelBins, kPreCout, kPreK, 1};
+    if (l <= 4) return {1, stage_cin(l - 1), stage_cout(l - 1), stage_kup(l - 1), stage_stride(l - 1)};
+    if (l <= 28) return {0, stage_cout((l - 5) / 6), stage_cout((l - 5) / 6), 3, 1};
+    return {0, 32, 1, kPostK, 1};
+}
+MG_HD constexpr int layer_dilation(int l) {  // only meaningful for resblock convs
+    return (l >= 5 && l <= 28 && ((l - 5) % 6) < 3) ? (((l - 5) % 6) == 0 ? 1 : ((l - 5) % 6) == 1 ? 3 : 9) : 1;
+}
+MG_HD constexpr size_t layer_weight_count(int l) {
+    return (size_t)layer_shape(l).cin * layer_shape(l).cout * layer_shape(l).k;
+}
+// rows of the weight-norm (dim 0 of weight_v): Cout for Conv1d, Cin for ConvTranspose1d
+MG_HD constexpr int layer_norm_rows(int l) { return layer_shape(l).kind == 0 ? layer_shape(l).cout : layer_shape(l).cin; }
+
+MG_HD constexpr size_t weight_offset(int l) {  // in floats
+    size_t o = 0;
+    for (int i = 0; i < l; ++i) o += layer_weight_count(i);
+    return o;
+}
+MG_HD constexpr size_t total_weight_count() { return weight_offset(kNumLayers); }
+MG_HD constexpr size_t bias_offset(int l) {  // in floats, from the start of the blob
+    size_t o = total_weight_count();
+    for (int i = 0; i < l; ++i) o += (size_t)layer_shape(i).cout;
+    return o;
+}
+MG_HD constexpr size_t packed_float_count() { return bias_offset(kNumLayers); }
+
+static_assert(packed_float_count() == 4524290 - 4353, "packed blob = all G params minus the weight_g scalars");
+
+// Activation workspace (floats per batch item per mel frame): conv_pre out, stage 0..2 outs.
+MG_HD constexpr size_t ws_offset(int which, size_t B, size_t T) {  // which: 0 pre, 1..3 stage 0..2
+    size_t o = 0;
+    if (which >= 1) o += B * 512 * T;
+    if (which >= 2) o += B * 256 * 8 * T;
+    if (which >= 3) o += B * 128 * 64 * T;
+    if (which >= 4) o += B * 64 * 128 * T;
+    return o;
+}
+
+}  // namespace mg

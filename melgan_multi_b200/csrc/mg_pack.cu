@@ -1,0 +1,83 @@
+// Weight-norm fold + packing of all 30 generator layers in ONE launch.
+//
+// Replaces the per-layer weight_norm pre-forward hook of the reference (w = g * v / ||v||,
+// norm over every axis but 0; models.py:16-28,46-59).  One CTA per norm row (4353 rows):
+// the CTA reduces ||v_row||^2, then scatters g/||v|| * v into the packed layout of mg_layout.h.
+#include "mg_common.cuh"
+
+namespace mg {
+
+struct PackArgs {
+    const float *v[kNumLayers];
+    const float *g[kNumLayers];
+    const float *bias[kNumLayers];
+};
+
+struct RowTable {
+    int first_row[kNumLayers + 1];
+};
+
+static RowTable make_row_table() {
+    RowTable t;
+    int r = 0;
+    for (int l = 0; l < kNumLayers; ++l) {
+        t.first_row[l] = r;
+        r += layer_norm_rows(l);
+    }
+    t.first_row[kNumLayers] = r;
+    return t;
+}
+
+__global__ void __launch_bounds__(128) pack_kernel(PackArgs a, RowTable rt, float *__restrict__ packed) {
+    const int grow = blockIdx.x;
+    int l = 0;
+#pragma unroll 1
+    while (grow >= rt.first_row[l + 1]) ++l;
+    const int row = grow - rt.first_row[l];
+    const LayerShape sh = layer_shape(l);
+    const int inner = (sh.kind == 0 ? sh.cin : sh.cout) * sh.k;
+    const float *__restrict__ vr = a.v[l] + (size_t)row * inner;
+
+    float ss = 0.f;
+    for (int j = threadIdx.x; j < inner; j += blockDim.x) {
+        float e = vr[j];
+        ss = fmaf(e, e, ss);
+    }
+    __shared__ float red[4];
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    const float total = red[0] + red[1] + red[2] + red[3];
+    const float scale = a.g[l][row] / sqrtf(total);
+
+    float *__restrict__ wp = packed + weight_offset(l);
+    if (sh.kind == 0) {
+        // v[co=row][ci][k] -> wp[(ci*K + k)*Cout + co]
+        for (int j = threadIdx.x; j < inner; j += blockDim.x) wp[(size_t)j * sh.cout + row] = scale * vr[j];
+    } else {
+        // v[ci=row][co][k] -> wp[((ci*Cout + co)*S + k%S)*2 + k/S]
+        const int S = sh.stride;
+        for (int j = threadIdx.x; j < inner; j += blockDim.x) {
+            const int co = j / sh.k, k = j - co * sh.k;
+            wp[(((size_t)row * sh.cout + co) * S + (k % S)) * 2 + (k / S)] = scale * vr[j];
+        }
+    }
+    if (threadIdx.x == 0 && row < sh.cout) packed[bias_offset(l) + row] = a.bias[l][row];
+}
+
+int launch_pack(const float *const *v, const float *const *g, const float *const *bias, float *packed,
+                cudaStream_t s) {
+    PackArgs a;
+    for (int l = 0; l < kNumLayers; ++l) {
+        if (!v[l] || !g[l] || !bias[l]) return set_error(MG_ERR_INVALID_ARGUMENT, "mg_gen_pack: null tensor for layer %d", l);
+        a.v[l] = v[l];
+        a.g[l] = g[l];
+        a.bias[l] = bias[l];
+    }
+    static const RowTable rt = make_row_table();
+    pack_kernel<<<rt.first_row[kNumLayers], 128, 0, s>>>(a, rt, packed);
+    MG_CUDA_TRY(cudaGetLastError());
+    return MG_OK;
+}
+
+}  // namespace mg

@@ -1,0 +1,210 @@
+"""ctypes binding of libmelgan_b200.so (the C ABI in include/melgan_b200.h).
+
+PyTorch is plumbing here: it owns device memory and streams; every kernel that runs on the hot
+path lives in the shared library.  There is no CPU or eager-PyTorch fallback: if the library
+is missing, or the device is not sm_100, calls raise.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmelgan_b200.so")
+NUM_LAYERS = 30
+
+_f32p = ctypes.POINTER(ctypes.c_float)
+_lib = None
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def lib():
+    """Loads the shared library (once).  Raises if it has not been built: the product path never
+    degrades to a fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise EngineError(
+                "libmelgan_b200.so is not built (%s). Run `python -m melgan_multi_b200.build` "
+                "(needs nvcc); there is no CPU/PyTorch fallback for the hot path." % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        L.mg_abi_version.restype = ctypes.c_int
+        L.mg_last_error_string.restype = ctypes.c_char_p
+        L.mg_device_check.restype = ctypes.c_int
+        L.mg_gen_packed_bytes.restype = ctypes.c_size_t
+        L.mg_gen_pack.restype = ctypes.c_int
+        L.mg_gen_pack.argtypes = [ctypes.c_void_p] * 5
+        L.mg_gen_workspace_bytes.restype = ctypes.c_size_t
+        L.mg_gen_workspace_bytes.argtypes = [ctypes.c_int, ctypes.c_int]
+        L.mg_gen_forward.restype = ctypes.c_int
+        L.mg_gen_forward.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                     ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+        L.mg_gen_forward_timed.restype = ctypes.c_int
+        L.mg_gen_forward_timed.argtypes = L.mg_gen_forward.argtypes + [ctypes.POINTER(ctypes.c_float)]
+        L.mg_gen_stage_output.restype = ctypes.c_int
+        L.mg_gen_stage_output.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                          ctypes.c_int, ctypes.c_void_p]
+        L.mg_gen_forward_launches.restype = ctypes.c_int
+        L.mg_gen_engine_create.restype = ctypes.c_int
+        L.mg_gen_engine_create.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int]
+        L.mg_gen_engine_load_state.restype = ctypes.c_int
+        L.mg_gen_engine_load_state.argtypes = [ctypes.c_void_p] * 4
+        L.mg_gen_engine_forward.restype = ctypes.c_int
+        L.mg_gen_engine_forward.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                            ctypes.c_int]
+        L.mg_gen_engine_last_kernel_ms.restype = ctypes.c_int
+        L.mg_gen_engine_last_kernel_ms.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]
+        L.mg_gen_engine_destroy.restype = None
+        L.mg_gen_engine_destroy.argtypes = [ctypes.c_void_p]
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise EngineError("melgan_b200 error %d: %s" % (rc, lib().mg_last_error_string().decode()))
+
+
+def _ptr_array(ptrs):
+    return (ctypes.c_void_p * len(ptrs))(*ptrs)
+
+
+# ------------------------------------------------------------------------------------------
+# Device-pointer path (what models.Generator.forward uses with torch tensors)
+# ------------------------------------------------------------------------------------------
+class GeneratorDevice:
+    """Packed weights + workspace cache on one CUDA device, driven with torch tensors."""
+
+    def __init__(self, device):
+        import torch
+        self.torch = torch
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise EngineError("the B200 engine runs on CUDA devices only (got %s)" % (device,))
+        with torch.cuda.device(self.device):
+            check(lib().mg_device_check())
+        self.packed = torch.empty(lib().mg_gen_packed_bytes() // 4, dtype=torch.float32, device=self.device)
+        self._ws = None
+        self._ws_key = None
+
+    def pack(self, vs, gs, bs):
+        """vs/gs/bs: 30 contiguous fp32 CUDA tensors each (weight_v, weight_g, bias; reference order)."""
+        torch = self.torch
+        keep = []
+        def ptrs(ts):
+            out = []
+            for t in ts:
+                t = t.detach()
+                if t.device != self.device or t.dtype != torch.float32:
+                    raise EngineError("generator parameters must be fp32 tensors on %s" % (self.device,))
+                t = t.contiguous()
+                keep.append(t)
+                out.append(t.data_ptr())
+            return _ptr_array(out)
+        if not (len(vs) == len(gs) == len(bs) == NUM_LAYERS):
+            raise EngineError("expected %d layers" % NUM_LAYERS)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            check(lib().mg_gen_pack(ptrs(vs), ptrs(gs), ptrs(bs), self.packed.data_ptr(), stream))
+        del keep
+
+    def workspace(self, B, T):
+        need = lib().mg_gen_workspace_bytes(B, T)
+        if self._ws is None or self._ws.numel() * 4 < need:
+            self._ws = self.torch.empty((need + 3) // 4, dtype=self.torch.float32, device=self.device)
+        return self._ws
+
+    def forward(self, mel, out=None):
+        torch = self.torch
+        if mel.dim() != 3 or mel.shape[1] != 80:
+            raise EngineError("mel must be [B, 80, T], got %s" % (tuple(mel.shape),))
+        if mel.device != self.device or mel.dtype != torch.float32:
+            raise EngineError("mel must be an fp32 tensor on %s" % (self.device,))
+        mel = mel.contiguous()
+        B, _, T = mel.shape
+        if out is None:
+            out = torch.empty((B, 1, 256 * T), dtype=torch.float32, device=self.device)
+        ws = self.workspace(B, T)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            check(lib().mg_gen_forward(self.packed.data_ptr(), mel.data_ptr(), out.data_ptr(), B, T,
+                                       ws.data_ptr(), ws.numel() * 4, stream))
+        return out
+
+    def forward_timed(self, mel, out):
+        """Like forward, returns the 5 per-kernel device times in ms (conv_pre, stage 0..3)."""
+        torch = self.torch
+        mel = mel.contiguous()
+        B, _, T = mel.shape
+        ws = self.workspace(B, T)
+        ms = (ctypes.c_float * 5)()
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            check(lib().mg_gen_forward_timed(self.packed.data_ptr(), mel.data_ptr(), out.data_ptr(), B, T,
+                                             ws.data_ptr(), ws.numel() * 4, stream, ms))
+        return list(ms)
+
+    def stage_output(self, which, B, T):
+        """Activation after conv_pre (0) or stage 0..2 (1..3) of the last forward, NCL."""
+        torch = self.torch
+        shapes = [(B, 512, T), (B, 256, 8 * T), (B, 128, 64 * T), (B, 64, 128 * T)]
+        out = torch.empty(shapes[which], dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            check(lib().mg_gen_stage_output(self._ws.data_ptr(), which, out.data_ptr(), B, T, stream))
+        return out
+
+
+# ------------------------------------------------------------------------------------------
+# Host-buffer path (no torch needed): numpy in, numpy out, copies inside the call
+# ------------------------------------------------------------------------------------------
+class GeneratorHost:
+    """mg_gen_engine_* wrapper: the call a non-PyTorch host makes (host buffers in and out)."""
+
+    def __init__(self, max_B=1, max_T=32):
+        self._h = ctypes.c_void_p()
+        check(lib().mg_gen_engine_create(ctypes.byref(self._h), max_B, max_T))
+
+    def load_state(self, state):
+        """state: mapping name -> float32 ndarray with the reference's state_dict keys."""
+        from .synth import GENERATOR_LAYERS
+        keep, vs, gs, bs = [], [], [], []
+        for name, *_ in GENERATOR_LAYERS:
+            for lst, suffix in ((vs, ".weight_v"), (gs, ".weight_g"), (bs, ".bias")):
+                a = np.ascontiguousarray(state[name + suffix], dtype=np.float32)
+                keep.append(a)
+                lst.append(a.ctypes.data)
+        check(lib().mg_gen_engine_load_state(self._h, _ptr_array(vs), _ptr_array(gs), _ptr_array(bs)))
+
+    def forward(self, mel, out=None):
+        mel = np.ascontiguousarray(mel, dtype=np.float32)
+        B, C, T = mel.shape
+        if C != 80:
+            raise EngineError("mel must be [B, 80, T]")
+        if out is None:
+            out = np.empty((B, 1, 256 * T), np.float32)
+        check(lib().mg_gen_engine_forward(self._h, mel.ctypes.data, out.ctypes.data, B, T))
+        return out
+
+    def forward_ptr(self, mel_ptr, out_ptr, B, T):
+        """Raw host pointers (e.g. pinned torch tensors' data_ptr())."""
+        check(lib().mg_gen_engine_forward(self._h, mel_ptr, out_ptr, B, T))
+
+    def last_kernel_ms(self):
+        ms = ctypes.c_float()
+        check(lib().mg_gen_engine_last_kernel_ms(self._h, ctypes.byref(ms)))
+        return ms.value
+
+    def close(self):
+        if self._h:
+            lib().mg_gen_engine_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,228 @@
+"""Drop-in replacement for the reference's ``models`` module (/root/reference/models.py).
+
+``train.py:13`` does ``from models import Generator, MultiScaleDiscriminator, feature_loss,
+generator_loss, discriminator_loss``; this module exports the same five names with the same
+constructor and ``forward`` signatures, the same ``state_dict`` keys, shapes and parameter
+registration order (so reference checkpoints and Adam state load), and leaves
+``weight_g`` / ``weight_v`` / ``bias`` as ordinary leaf parameters so the reference's gradient
+all-reduce wrapper (distributed.py:90-142) hooks them unchanged.
+
+What runs where
+  * ``Generator.forward`` (models.py:61-71 in the reference): five hand-written sm_100a kernels in
+    libmelgan_b200.so -- conv_pre, then one fused kernel per (LeakyReLU -> ConvTranspose1d ->
+    ResBlock) stage, the last one also doing LeakyReLU -> conv_post -> tanh -- plus one launch
+    that folds weight-norm for all 30 layers whenever the parameters changed.  CUDA only; a CPU
+    tensor raises (the reference's CPU path lives in oracle/ as test infrastructure).
+  * Backward of the generator, and the discriminators (forward and backward), are NOT native yet:
+    they run as stock PyTorch ops so that train.py keeps working.  They are listed as open rows
+    in DESIGN.md and are never part of a benchmark or parity claim.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.nn import AvgPool1d, Conv1d, ConvTranspose1d
+from torch.nn.utils import weight_norm
+
+from . import engine as _engine
+from .synth import DISCRIMINATOR_LAYERS, GENERATOR_LAYERS
+
+_RES_DILATIONS = (1, 3, 9)
+
+
+def get_padding(kernel_size, dilation=1):
+    """'same' padding for an odd kernel (reference models.py:8-9)."""
+    return (kernel_size * dilation - dilation) // 2
+
+
+def _wn_conv(cin, cout, k, **kw):
+    return weight_norm(Conv1d(cin, cout, k, **kw))
+
+
+class ResBlock(nn.Module):
+    """Parameter container with the reference's layout (models.py:12-30).  ``forward`` is the stock
+    PyTorch restatement used only by the autograd (backward) path."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.convs1 = nn.ModuleList(
+            [_wn_conv(in_channels, out_channels, 3, dilation=d, padding=get_padding(3, d)) for d in _RES_DILATIONS])
+        self.convs2 = nn.ModuleList(
+            [_wn_conv(in_channels, out_channels, 3, dilation=1, padding=get_padding(3, 1)) for _ in _RES_DILATIONS])
+
+    def forward(self, x):
+        for first, second in zip(self.convs1, self.convs2):
+            x = second(F.leaky_relu(first(F.leaky_relu(x)))) + x
+        return x
+
+
+def _layer_modules(gen):
+    """The 30 weight-normed modules of a Generator in reference registration order."""
+    mods = [gen.conv_pre] + list(gen.ups)
+    for rb in gen.resblocks:
+        mods += list(rb.convs1) + list(rb.convs2)
+    mods.append(gen.conv_post)
+    return mods
+
+
+class _GeneratorFunction(torch.autograd.Function):
+    """Forward on the fused sm_100a kernels; backward by recomputation through stock PyTorch ops
+    (open row: native backward).  Inputs: mel, then 30 x (weight_v, weight_g, bias)."""
+
+    @staticmethod
+    def forward(ctx, gen, mel, *params):
+        ctx.gen = gen
+        ctx.save_for_backward(mel, *params)
+        return gen._engine_forward(mel)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        gen = ctx.gen
+        mel, *params = ctx.saved_tensors
+        with torch.enable_grad():
+            mel_ = mel.detach().requires_grad_(ctx.needs_input_grad[1])
+            leaves = [p.detach().requires_grad_(True) for p in params]
+            y = gen._torch_forward(mel_, leaves)
+            wanted = ([mel_] if ctx.needs_input_grad[1] else []) + leaves
+            grads = torch.autograd.grad(y, wanted, grad_out, allow_unused=True)
+        grads = list(grads)
+        gmel = grads.pop(0) if ctx.needs_input_grad[1] else None
+        return (None, gmel, *grads)
+
+
+class Generator(nn.Module):
+    """mel [B, 80, T] fp32 CUDA -> audio [B, 1, 256*T] (reference models.py:43-71)."""
+
+    def __init__(self):
+        super().__init__()
+        self.conv_pre = _wn_conv(80, 512, 7, padding=3)
+        self.ups = nn.ModuleList([
+            weight_norm(ConvTranspose1d(cin, cout, k, k // 2, padding=k // 4))
+            for _n, kind, cin, cout, k in GENERATOR_LAYERS if kind == "convT"])
+        self.resblocks = nn.ModuleList([ResBlock(c, c) for c in (256, 128, 64, 32)])
+        self.conv_post = _wn_conv(32, 1, 7, padding=3)
+        self._dev = None          # engine.GeneratorDevice, created lazily on the parameters' device
+        self._packed_key = None   # (data_ptr, _version) of every parameter at the last pack
+
+    # -- parameter plumbing -----------------------------------------------------------------
+    def _param_triplets(self):
+        mods = _layer_modules(self)
+        return [m.weight_v for m in mods], [m.weight_g for m in mods], [m.bias for m in mods]
+
+    def _ensure_packed(self):
+        vs, gs, bs = self._param_triplets()
+        dev = vs[0].device
+        if dev.type != "cuda":
+            raise _engine.EngineError(
+                "melgan_multi_b200.Generator runs on CUDA (sm_100a) only; move the module with .to('cuda'). "
+                "There is deliberately no CPU fallback.")
+        if self._dev is None or self._dev.device != dev:
+            self._dev = _engine.GeneratorDevice(dev)
+            self._packed_key = None
+        key = tuple((t.data_ptr(), t._version) for t in vs + gs + bs)
+        if key != self._packed_key:
+            self._dev.pack(vs, gs, bs)
+            self._packed_key = key
+        return self._dev
+
+    def _engine_forward(self, mel):
+        return self._ensure_packed().forward(mel)
+
+    # -- stock-PyTorch restatement, used ONLY to differentiate (backward) ---------------------
+    def _torch_forward(self, x, leaves):
+        ws = [torch._weight_norm(leaves[3 * i], leaves[3 * i + 1], 0) for i in range(30)]
+        bs = [leaves[3 * i + 2] for i in range(30)]
+        x = F.conv1d(x, ws[0], bs[0], padding=3)
+        for i in range(4):
+            k = ws[1 + i].shape[2]
+            x = F.conv_transpose1d(F.leaky_relu(x), ws[1 + i], bs[1 + i], stride=k // 2, padding=k // 4)
+            for j, d in enumerate(_RES_DILATIONS):
+                a, b = 5 + 6 * i + j, 5 + 6 * i + 3 + j
+                h = F.conv1d(F.leaky_relu(x), ws[a], bs[a], padding=d, dilation=d)
+                x = F.conv1d(F.leaky_relu(h), ws[b], bs[b], padding=1) + x
+        return torch.tanh(F.conv1d(F.leaky_relu(x), ws[29], bs[29], padding=3))
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise _engine.EngineError("melgan_multi_b200.Generator.forward needs a CUDA tensor (no CPU fallback)")
+        if x.dtype != torch.float32:
+            x = x.float()
+        vs, gs, bs = self._param_triplets()
+        needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in vs + gs + bs))
+        if not needs_grad:
+            return self._engine_forward(x)
+        flat = []
+        for v, g, b in zip(vs, gs, bs):
+            flat += [v, g, b]
+        return _GeneratorFunction.apply(self, x, *flat)
+
+
+class Discriminator(nn.Module):
+    """Reference models.py:74-103.  Stock PyTorch ops for now (open row in DESIGN.md)."""
+
+    def __init__(self):
+        super().__init__()
+        spec = {n: (cin, cout, k, s, g, p) for n, cin, cout, k, s, g, p in DISCRIMINATOR_LAYERS}
+        def mk(n):
+            cin, cout, k, s, g, p = spec[n]
+            return weight_norm(Conv1d(cin, cout, k, s, groups=g, padding=p))
+        self.conv_pre = mk("conv_pre")
+        self.grouped_convs = nn.ModuleList([mk("grouped_convs.%d" % i) for i in range(4)])
+        self.conv_post1 = mk("conv_post1")
+        self.conv_post2 = mk("conv_post2")
+
+    def forward(self, x):
+        fmap = []
+        for layer in [self.conv_pre] + list(self.grouped_convs) + [self.conv_post1]:
+            x = F.leaky_relu(layer(x))
+            fmap.append(x)
+        x = self.conv_post2(x)
+        fmap.append(x)
+        return torch.flatten(x, 1, -1), fmap
+
+
+class MultiScaleDiscriminator(nn.Module):
+    """Reference models.py:106-135: three Discriminators on y, pool(y), pool(pool(y))."""
+
+    def __init__(self):
+        super().__init__()
+        self.discriminators = nn.ModuleList([Discriminator() for _ in range(3)])
+        self.meanpools = nn.ModuleList([AvgPool1d(4, 2, padding=2), AvgPool1d(4, 4, padding=2)])
+
+    def forward(self, y, y_hat):
+        y_d_rs, y_d_gs, fmap_rs, fmap_gs = [], [], [], []
+        for i, d in enumerate(self.discriminators):
+            if i > 0:
+                y, y_hat = self.meanpools[i - 1](y), self.meanpools[i - 1](y_hat)
+            r, fr = d(y)
+            g, fg = d(y_hat)
+            y_d_rs.append(r); fmap_rs.append(fr); y_d_gs.append(g); fmap_gs.append(fg)
+        return y_d_rs, y_d_gs, fmap_rs, fmap_gs
+
+
+def feature_loss(fmap_r, fmap_g):
+    """10 * sum over the 21 feature-map pairs of mean |r - g| (reference models.py:138-144)."""
+    total = 0
+    for maps_r, maps_g in zip(fmap_r, fmap_g):
+        for r, g in zip(maps_r, maps_g):
+            total = total + (r - g).abs().mean()
+    return total * 10
+
+
+def discriminator_loss(disc_real_outputs, disc_generated_outputs):
+    """LSGAN discriminator loss; returns (loss, real terms, generated terms) like models.py:147-159."""
+    total, r_losses, g_losses = 0, [], []
+    for dr, dg in zip(disc_real_outputs, disc_generated_outputs):
+        r_term = ((1 - dr) ** 2).mean()
+        g_term = (dg ** 2).mean()
+        total = total + r_term + g_term
+        r_losses.append(r_term.item())
+        g_losses.append(g_term.item())
+    return total, r_losses, g_losses
+
+
+def generator_loss(disc_generated_outputs):
+    """LSGAN generator loss (reference models.py:162-167)."""
+    total = 0
+    for dg in disc_generated_outputs:
+        total = total + ((1 - dg) ** 2).mean()
+    return total

@@ -118,6 +118,15 @@ def main():
             y = torch.nn.AvgPool1d(prm[0], prm[1], padding=prm[2])(tx)
         out[key] = y.numpy()
 
+    # ---------------- module ABI: state_dict keys / shapes / parameter order ----------------
+    import json
+    abi = {}
+    for nm, mod in (("Generator", ref_models.Generator()), ("MultiScaleDiscriminator", ref_models.MultiScaleDiscriminator())):
+        abi[nm] = {"state_dict": [[k, list(v.shape)] for k, v in mod.state_dict().items()],
+                   "parameters": [n for n, _ in mod.named_parameters()]}
+    with open(os.path.join(HERE, "module_abi.json"), "w") as f:
+        json.dump(abi, f, indent=0)
+
     path = os.path.join(HERE, "reference_outputs.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, "%.2f MB" % (os.path.getsize(path) / 1e6), len(out), "arrays")

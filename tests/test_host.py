@@ -1,0 +1,110 @@
+"""CPU-only checks: module ABI vs the reference, C-ABI symbols, loud failure without a GPU."""
+import ctypes
+import json
+import os
+import re
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from melgan_multi_b200 import engine, synth
+
+warnings.filterwarnings("ignore")
+
+
+@pytest.fixture(scope="module")
+def abi():
+    with open(os.path.join(ROOT, "tests", "golden", "module_abi.json")) as f:
+        return json.load(f)
+
+
+def test_generator_module_abi_matches_reference(abi):
+    from melgan_multi_b200 import models
+    g = models.Generator()
+    got = [[k, list(v.shape)] for k, v in g.state_dict().items()]
+    assert got == abi["Generator"]["state_dict"]
+    assert [n for n, _ in g.named_parameters()] == abi["Generator"]["parameters"]
+    assert sum(p.numel() for p in g.parameters()) == 4524290
+
+
+def test_msd_module_abi_matches_reference(abi):
+    from melgan_multi_b200 import models
+    d = models.MultiScaleDiscriminator()
+    got = [[k, list(v.shape)] for k, v in d.state_dict().items()]
+    assert got == abi["MultiScaleDiscriminator"]["state_dict"]
+    assert [n for n, _ in d.named_parameters()] == abi["MultiScaleDiscriminator"]["parameters"]
+    assert sum(p.numel() for p in d.parameters()) == 16924086
+
+
+def test_synth_state_matches_module_abi(abi):
+    gs = synth.generator_state(1)
+    assert [[k, list(v.shape)] for k, v in gs.items()] == abi["Generator"]["state_dict"]
+    ds = synth.discriminator_state(1)
+    assert [[k, list(v.shape)] for k, v in ds.items()] == abi["MultiScaleDiscriminator"]["state_dict"]
+    # seeded and reproducible
+    assert np.array_equal(gs["ups.2.weight_v"], synth.generator_state(1)["ups.2.weight_v"])
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    """Every function declared in include/melgan_b200.h must be exported by the built library."""
+    hdr = open(os.path.join(ROOT, "include", "melgan_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = re.findall(r"\b(mg_[a-z0-9_]+)\s*\(", hdr)
+    assert len(set(names)) >= 14
+    lib = ctypes.CDLL(engine.LIB_PATH)
+    for n in set(names):
+        assert hasattr(lib, n), "missing export %s" % n
+    assert engine.lib().mg_abi_version() == 1
+    assert engine.lib().mg_gen_packed_bytes() == (4524290 - 4353) * 4
+    assert engine.lib().mg_gen_workspace_bytes(64, 32) == 64 * 32 * 18944 * 4
+    assert engine.lib().mg_gen_workspace_bytes(0, 32) == 0
+
+
+def test_generator_refuses_cpu_tensors():
+    from melgan_multi_b200 import models
+    g = models.Generator()
+    with pytest.raises(engine.EngineError):
+        g(torch.zeros(1, 80, 4))
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_engine_fails_loudly_without_gpu():
+    with pytest.raises(engine.EngineError):
+        engine.GeneratorHost(1, 4)
+    assert "CUDA" in engine.lib().mg_last_error_string().decode() or "cuda" in engine.lib().mg_last_error_string().decode()
+
+
+def test_torch_restatement_used_for_backward_matches_golden(golden):
+    """Generator._torch_forward (the stock-op graph autograd differentiates) == reference output."""
+    import cases
+    from melgan_multi_b200 import models
+    g = models.Generator()
+    g.load_state_dict({k: torch.from_numpy(v) for k, v in synth.generator_state(1234).items()})
+    vs, gs_, bs = g._param_triplets()
+    leaves = []
+    for v, gg, b in zip(vs, gs_, bs):
+        leaves += [v, gg, b]
+    case = cases.GEN_CASES[1]
+    with torch.no_grad():
+        y = g._torch_forward(torch.from_numpy(synth.mel_input(*case)), leaves).numpy()
+    ref = golden[cases.gen_key(*case)]
+    assert np.abs(y - ref).max() <= 2e-5 * np.abs(ref).max()
+
+
+def test_losses_match_reference_values(golden):
+    import cases
+    from melgan_multi_b200 import models
+    B, L, seed = cases.MSD_CASES[1]
+    d = models.MultiScaleDiscriminator()
+    d.load_state_dict({k: torch.from_numpy(v) for k, v in synth.discriminator_state(4321).items()})
+    with torch.no_grad():
+        rs, gs, frs, fgs = d(torch.from_numpy(synth.audio_input(B, L, seed)),
+                             torch.from_numpy(synth.audio_input(B, L, seed + 7)))
+    tag = "msd_B%d_L%d_s%d" % (B, L, seed)
+    assert abs(models.feature_loss(frs, fgs).item() - float(golden[tag + "_feature_loss"])) < 1e-4
+    assert abs(models.generator_loss(gs).item() - float(golden[tag + "_generator_loss"])) < 1e-5
+    dl, rl, gl = models.discriminator_loss(rs, gs)
+    np.testing.assert_allclose([dl.item()] + rl + gl, golden[tag + "_discriminator_loss"], rtol=1e-4, atol=1e-6)

@@ -96,3 +96,14 @@ def test_msd_matches_reference(golden, msd_folded, case):
                 assert m < 5e-5, (i, j, nm, m)
                 s = golden["%s_fmap_%s%d_%d_sum" % (tag, nm, i, j)]
                 assert abs(np.abs(a.astype(np.float64)).sum() - s[1]) < 1e-5 * s[1]
+
+
+def test_torch_cpu_port_matches_reference(golden):
+    """oracle/torch_port.py (bench.py's CPU baseline) against the reference's outputs."""
+    import torch
+    from oracle import torch_port
+    ws, bs = torch_port.fold_state(synth.generator_state(1234))
+    for case in (cases.GEN_CASES[1], cases.GEN_CASES[4]):
+        y = torch_port.generator_forward(ws, bs, torch.from_numpy(synth.mel_input(*case))).numpy()
+        m, l2 = rel_errors(y, golden[cases.gen_key(*case)])
+        assert m < TOL and l2 < TOL, (case, m, l2)
