@@ -106,12 +106,26 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def usable_cpus():
+    """Host threads this process may really use: min(affinity mask, cgroup v2 cpu.max quota).  os.cpu_count()
+    alone reports the machine (128 on the GPU boxes) while the container is capped (16), and oneDNN with 128
+    threads on a 16-CPU quota runs ~500x slower."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        pass
+    return max(1, n)
+
+
 def cpu_port_throughput(sample_B, budget_s, min_iters=2):
     """Times oracle/torch_port.py on all host threads.  Returns (audio_frames/s, cores, iters, per-iter s)."""
     import torch
     from melgan_multi_b200 import synth
     from oracle import torch_port
-    cores = os.cpu_count() or 1
+    cores = usable_cpus()
     torch.set_num_threads(cores)
     ws, bs = torch_port.fold_state(synth.generator_state(1234))
     x = torch.from_numpy(synth.mel_input(sample_B, T_FRAMES, 0))
@@ -135,7 +149,7 @@ def run_reference(args):
     import torch
     from melgan_multi_b200 import synth
     from oracle import torch_port
-    cores = os.cpu_count() or 1
+    cores = usable_cpus()
     torch.set_num_threads(cores)
     sample_B = 16
     ws, bs = torch_port.fold_state(synth.generator_state(1234))
@@ -251,7 +265,9 @@ def main():
         "frac": dom_tflops / peaks["bf16_tflops"], "traffic": None,
         "peak_source": "%s bf16 dense burst (MEASURED_PEAKS.json)" % peaks["source"],
         "algorithmic_flops_per_launch": k_flops[dom], "avg_launch_ms": float(kms[dom]),
-        "math": "fp32 FFMA (SIMT), 1 pass; tensor pipe not used yet",
+        "math": ("split-bf16 tcgen05 (3 MMA passes per product) in the ResBlocks; ConvT/pre/post fp32 SIMT"
+                 if os.environ.get("MG_GEN_PATH") == "tc" else "fp32 FFMA (SIMT), 1 pass; tensor pipe not used"),
+        "path": os.environ.get("MG_GEN_PATH", "simt"),
         "kernel_ms": {n: float(v) for n, v in zip(["conv_pre", "stage0", "stage1", "stage2", "stage3+post"], kms)},
         "kernel_tflops": {n: k_flops[i] / (kms[i] * 1e-3) / 1e12 for i, n in
                           enumerate(["conv_pre", "stage0", "stage1", "stage2", "stage3+post"])},
@@ -282,9 +298,9 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1:
-        v, cores, iters, med = cpu_port_throughput(4, args.cpu_budget)
+        v, cores, iters, med = cpu_port_throughput(16, args.cpu_budget)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "B=4 of the 64 segments (80x32 mel each), %d iterations, median %.3f s; "
+               "sample": "B=16 of the 64 segments (80x32 mel each), %d iterations, median %.3f s; "
                          "oracle/torch_port.py = the reference forward on PyTorch-CPU/oneDNN, all threads" % (iters, med)}
 
     if rank == 0:

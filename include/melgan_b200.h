@@ -83,6 +83,15 @@ int mg_gen_forward(const void *packed, const float *mel, float *audio, int B, in
 int mg_gen_forward_timed(const void *packed, const float *mel, float *audio, int B, int T,
                          void *workspace, size_t workspace_bytes, void *stream, float *kernel_ms);
 
+/* Waits for `stream` and reports whether the tensor-core pipeline of the last forward on `workspace`
+ * completed (its producer/consumer waits are bounded so a logic error returns MG_ERR_CUDA here instead
+ * of hanging the device). */
+int mg_gen_check_status(const void *workspace, int B, int T, void *stream);
+
+/* One ResBlock (models.py:32-40) of stage `stage` (C = 256 >> stage channels) on the tensor-core path:
+ * x, y [B, C, L] device fp32, x != y.  Synchronous; parity-test entry point for the tcgen05 kernel. */
+int mg_gen_resblock(const void *packed, int stage, const float *x, float *y, int B, int L, void *stream);
+
 /* Debug/parity tap: copies the activation after stage `which` (0 = conv_pre output [B,512,T],
  * 1..3 = ResBlock 0..2 output [B,C,L]; the last stage is fused with conv_post and has no tap) of the LAST mg_gen_forward that used `workspace` into
  * `out` (device, NCL).  Only valid immediately after that call on the same stream. */

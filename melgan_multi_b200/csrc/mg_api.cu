@@ -1,5 +1,6 @@
 // C ABI of libmelgan_b200.so (see include/melgan_b200.h for the contract of every entry point).
 #include <new>
+#include <stdlib.h>
 #include <string.h>
 
 #include "mg_common.cuh"
@@ -16,6 +17,24 @@ int set_error(int code, const char *fmt, ...) {
     vsnprintf(g_error, sizeof(g_error), fmt, ap);
     va_end(ap);
     return code;
+}
+
+// Development switch between the two generator pipelines: MG_GEN_PATH=simt (default) | tc
+static bool use_tc() {
+    const char *e = getenv("MG_GEN_PATH");
+    return e && strcmp(e, "tc") == 0;
+}
+
+static int *status_ptr(void *workspace, int B, int T) {
+    return reinterpret_cast<int *>(reinterpret_cast<float *>(workspace) + ws_offset(6, (size_t)B, (size_t)T));
+}
+
+static int run_generator(const float *packed, const float *mel, float *audio, int B, int T, float *ws, cudaStream_t s,
+                         cudaEvent_t *ev) {
+    if (!use_tc()) return launch_generator_simt(packed, mel, audio, B, T, ws, s, ev);
+    int *st = status_ptr(ws, B, T);
+    MG_CUDA_TRY(cudaMemsetAsync(st, 0, sizeof(int), s));
+    return launch_generator_tc(packed, mel, audio, B, T, ws, st, s, ev);
 }
 
 static int check_shape(const char *fn, int B, int T) {
@@ -45,7 +64,7 @@ int mg_device_check(void) {
     return MG_OK;
 }
 
-size_t mg_gen_packed_bytes(void) { return packed_float_count() * sizeof(float); }
+size_t mg_gen_packed_bytes(void) { return packed_total_bytes(); }
 
 int mg_gen_pack(const float *const *v, const float *const *g, const float *const *bias, void *packed, void *stream) {
     if (!v || !g || !bias || !packed) return set_error(MG_ERR_INVALID_ARGUMENT, "mg_gen_pack: null argument");
@@ -55,7 +74,7 @@ int mg_gen_pack(const float *const *v, const float *const *g, const float *const
 
 size_t mg_gen_workspace_bytes(int B, int T) {
     if (B < 1 || T < 1) return 0;
-    return ws_offset(4, (size_t)B, (size_t)T) * sizeof(float);
+    return ws_offset(6, (size_t)B, (size_t)T) * sizeof(float) + 256;  // + pipeline status word
 }
 
 int mg_gen_forward(const void *packed, const float *mel, float *audio, int B, int T, void *workspace,
@@ -68,7 +87,7 @@ int mg_gen_forward(const void *packed, const float *mel, float *audio, int B, in
                          mg_gen_workspace_bytes(B, T));
     if ((uintptr_t)packed % 16 || (uintptr_t)workspace % 16)
         return set_error(MG_ERR_INVALID_ARGUMENT, "mg_gen_forward: packed/workspace must be 16-byte aligned");
-    return launch_generator_simt((const float *)packed, mel, audio, B, T, (float *)workspace, (cudaStream_t)stream);
+    return run_generator((const float *)packed, mel, audio, B, T, (float *)workspace, (cudaStream_t)stream, nullptr);
 }
 
 int mg_gen_forward_timed(const void *packed, const float *mel, float *audio, int B, int T, void *workspace,
@@ -81,7 +100,7 @@ int mg_gen_forward_timed(const void *packed, const float *mel, float *audio, int
         return set_error(MG_ERR_WORKSPACE_TOO_SMALL, "mg_gen_forward_timed: workspace too small");
     cudaEvent_t ev[6];
     for (int i = 0; i < 6; ++i) MG_CUDA_TRY(cudaEventCreate(&ev[i]));
-    rc = launch_generator_simt((const float *)packed, mel, audio, B, T, (float *)workspace, (cudaStream_t)stream, ev);
+    rc = run_generator((const float *)packed, mel, audio, B, T, (float *)workspace, (cudaStream_t)stream, ev);
     if (rc == MG_OK) {
         cudaError_t e = cudaEventSynchronize(ev[5]);
         if (e != cudaSuccess) rc = set_error(MG_ERR_CUDA, "mg_gen_forward_timed: %s", cudaGetErrorString(e));
@@ -104,7 +123,37 @@ int mg_gen_stage_output(const void *workspace, int which, float *out, int B, int
     return MG_OK;
 }
 
-int mg_gen_forward_launches(void) { return generator_simt_num_launches(); }
+int mg_gen_forward_launches(void) { return use_tc() ? generator_tc_num_launches() : generator_simt_num_launches(); }
+
+int mg_gen_check_status(const void *workspace, int B, int T, void *stream) {
+    int rc = check_shape("mg_gen_check_status", B, T);
+    if (rc) return rc;
+    if (!workspace) return set_error(MG_ERR_INVALID_ARGUMENT, "mg_gen_check_status: null workspace");
+    MG_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    if (!use_tc()) return MG_OK;
+    int st = 0;
+    MG_CUDA_TRY(cudaMemcpy(&st, status_ptr(const_cast<void *>(workspace), B, T), sizeof(int), cudaMemcpyDeviceToHost));
+    if (st) return set_error(MG_ERR_CUDA, "tensor-core pipeline wait timed out (role code %d)", st);
+    return MG_OK;
+}
+
+int mg_gen_resblock(const void *packed, int stage, const float *x, float *y, int B, int L, void *stream) {
+    if (!packed || !x || !y || x == y || stage < 0 || stage > 3 || B < 1 || L < 1)
+        return set_error(MG_ERR_INVALID_ARGUMENT, "mg_gen_resblock: bad argument");
+    int *st = nullptr;
+    MG_CUDA_TRY(cudaMalloc(&st, sizeof(int)));
+    cudaMemsetAsync(st, 0, sizeof(int), (cudaStream_t)stream);
+    int rc = launch_resblock_tc(x, y, (const float *)packed, stage, B, L, st, (cudaStream_t)stream);
+    int h = 0;
+    if (rc == MG_OK) {
+        cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+        if (e != cudaSuccess) rc = set_error(MG_ERR_CUDA, "mg_gen_resblock: %s", cudaGetErrorString(e));
+        else if (cudaMemcpy(&h, st, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess || h)
+            rc = set_error(MG_ERR_CUDA, "mg_gen_resblock: pipeline wait timed out (role code %d)", h);
+    }
+    cudaFree(st);
+    return rc;
+}
 
 /* ------------------------------- host-buffer engine ------------------------------------- */
 
@@ -132,7 +181,7 @@ static int engine_reserve(mg_gen_engine *e, size_t frames) {
     engine_free_io(e);
     MG_CUDA_TRY(cudaMalloc(&e->mel, frames * kMelBins * sizeof(float)));
     MG_CUDA_TRY(cudaMalloc(&e->audio, frames * 256 * sizeof(float)));
-    MG_CUDA_TRY(cudaMalloc(&e->ws, ws_offset(4, 1, frames) * sizeof(float)));
+    MG_CUDA_TRY(cudaMalloc(&e->ws, mg_gen_workspace_bytes(1, (int)frames)));
     MG_CUDA_TRY(cudaMallocHost(&e->pin_in, frames * kMelBins * sizeof(float)));
     MG_CUDA_TRY(cudaMallocHost(&e->pin_out, frames * 256 * sizeof(float)));
     e->cap_frames = frames;
@@ -150,7 +199,7 @@ int mg_gen_engine_create(mg_gen_engine **out, int max_B, int max_T) {
     MG_CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     MG_CUDA_TRY(cudaEventCreate(&e->ev0));
     MG_CUDA_TRY(cudaEventCreate(&e->ev1));
-    MG_CUDA_TRY(cudaMalloc(&e->packed, mg_gen_packed_bytes()));
+    MG_CUDA_TRY(cudaMalloc((void **)&e->packed, mg_gen_packed_bytes()));
     MG_CUDA_TRY(cudaMalloc(&e->raw, (packed_float_count() + 4353) * sizeof(float)));
     return engine_reserve(e, (size_t)max_B * max_T);
 }
@@ -189,12 +238,13 @@ int mg_gen_engine_forward(mg_gen_engine *e, const float *mel_host, float *audio_
     if (!in_pinned) { memcpy(e->pin_in, mel_host, nin); src = e->pin_in; }
     MG_CUDA_TRY(cudaMemcpyAsync(e->mel, src, nin, cudaMemcpyHostToDevice, e->stream));
     MG_CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
-    rc = launch_generator_simt(e->packed, e->mel, e->audio, B, T, e->ws, e->stream);
+    rc = run_generator(e->packed, e->mel, e->audio, B, T, e->ws, e->stream, nullptr);
     if (rc) return rc;
     MG_CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
     MG_CUDA_TRY(cudaMemcpyAsync(out_pinned ? audio_host : e->pin_out, e->audio, nout, cudaMemcpyDeviceToHost, e->stream));
     MG_CUDA_TRY(cudaStreamSynchronize(e->stream));
     if (!out_pinned) memcpy(audio_host, e->pin_out, nout);
+    if ((rc = mg_gen_check_status(e->ws, B, T, e->stream))) return rc;
     MG_CUDA_TRY(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
     return MG_OK;
 }

@@ -41,5 +41,9 @@ int launch_pack(const float *const *v, const float *const *g, const float *const
 int launch_generator_simt(const float *packed, const float *mel, float *audio, int B, int T, float *ws,
                           cudaStream_t s, cudaEvent_t *ev = nullptr);
 int generator_simt_num_launches();
+int generator_tc_num_launches();
+int launch_generator_tc(const float *packed, const float *mel, float *audio, int B, int T, float *ws, int *status,
+                        cudaStream_t s, cudaEvent_t *ev = nullptr);
+int launch_resblock_tc(const float *x, float *y, const float *packed, int stage, int B, int L, int *status, cudaStream_t s);
 
 }  // namespace mg

@@ -22,12 +22,12 @@
 
 namespace mg {
 
-template <int CIN_, int COUT_, int S_, int PTOT_, int WC_, int WP_, int WBUF_, bool POST_>
+template <int CIN_, int COUT_, int S_, int PTOT_, int WC_, int WP_, int WBUF_, bool POST_, bool RES_ = true>
 struct StageCfg {
     static constexpr int CIN = CIN_, COUT = COUT_, S = S_, PTOT = PTOT_, WC = WC_, WP = WP_, WBUF = WBUF_;
-    static constexpr bool POST = POST_;
+    static constexpr bool POST = POST_, RES = RES_;  // RES=false: ConvTranspose1d only (feeds the tensor-core ResBlock)
     static constexpr int PAD = S / 2;                   // ConvTranspose1d padding (4 for k16/s8, 1 for k4/s2)
-    static constexpr int HALO = 16 + (POST ? 3 : 0);    // ResBlock receptive field (+ conv_post k7)
+    static constexpr int HALO = RES ? 16 + (POST ? 3 : 0) : 0;  // ResBlock receptive field (+ conv_post k7)
     static constexpr int PVALID = PTOT - 2 * HALO;
     static constexpr int NT = 32 * WC * WP;
     static constexpr int COB = COUT / WC;               // output channels per thread
@@ -36,7 +36,7 @@ struct StageCfg {
     static constexpr int PADF = 16;                     // slack floats either side of R and U (dilation-9 taps)
     static constexpr int R_FLOATS = COUT * PTOT + 2 * PADF;
     static constexpr int IN_FLOATS = CIN * PIN;
-    static constexpr int U_FLOATS = R_FLOATS > IN_FLOATS ? R_FLOATS : IN_FLOATS;
+    static constexpr int U_FLOATS = (RES && R_FLOATS > IN_FLOATS) ? R_FLOATS : (IN_FLOATS + 3) / 4 * 4;
     static constexpr int CIC_UP = WBUF / (COUT * 2 * S);  // input channels per ConvT weight chunk
     static constexpr int cic_res() {
         int c = 1;
@@ -48,6 +48,7 @@ struct StageCfg {
     static_assert(COUT % WC == 0 && COB % 4 == 0, "COB must be a multiple of 4 (float4 weight loads)");
     static_assert(PTOT % (32 * WP) == 0 && PTOT % S == 0 && 32 % S == 0, "tile shape");
     static_assert(CIC_UP >= 1 && CIN % CIC_UP == 0, "ConvT chunking");
+    static_assert(RES || !POST, "conv_post fusion needs the ResBlock");
     static_assert(R_FLOATS % 4 == 0 && U_FLOATS % 4 == 0 && WBUF % 4 == 0, "16-byte alignment of smem regions");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
     static_assert(NT <= 1024, "block size");
@@ -223,6 +224,7 @@ gen_stage_kernel(const float *__restrict__ x, float *__restrict__ y, const float
         }
     }
     __syncthreads();
+    if (Cfg::RES) {
     if (tid < Cfg::PADF) {  // In is dead: give U its zero slack
         Ub[-Cfg::PADF + tid] = 0.f;
         Ub[COUT * PTOT + tid] = 0.f;
@@ -241,6 +243,7 @@ gen_stage_kernel(const float *__restrict__ x, float *__restrict__ y, const float
         MG_PAIR(1, 3)
         MG_PAIR(2, 9)
 #undef MG_PAIR
+    }
     }
 
     if (Cfg::POST) {
@@ -312,11 +315,42 @@ gen_pre_kernel(const float *__restrict__ mel, float *__restrict__ y, const float
         if (t0 + t < T) yr[t] = acc[t];
 }
 
+// LeakyReLU -> conv_post (32->1, k7) -> tanh (models.py:67-69) as its own kernel (tensor-core pipeline).
+constexpr int kPostTile = 256;
+__global__ void __launch_bounds__(256)
+gen_post_kernel(const float *__restrict__ x, float *__restrict__ audio, const float *__restrict__ packed, int L) {
+    __shared__ float xs[32][kPostTile + 8];
+    __shared__ float ws[32 * kPostK];
+    const int b = blockIdx.y, t0 = blockIdx.x * kPostTile;
+    for (int i = threadIdx.x; i < 32 * kPostK; i += 256) ws[i] = packed[weight_offset(29) + i];
+    for (int idx = threadIdx.x; idx < 32 * (kPostTile + 6); idx += 256) {
+        const int ci = idx / (kPostTile + 6), i = idx - ci * (kPostTile + 6);
+        const int t = t0 + i - 3;
+        xs[ci][i] = (t >= 0 && t < L) ? lrelu(x[((size_t)b * 32 + ci) * L + t]) : 0.f;
+    }
+    __syncthreads();
+    const float bias = packed[bias_offset(29)];
+    for (int i = threadIdx.x; i < kPostTile; i += 256) {
+        if (t0 + i >= L) break;
+        float acc = bias;
+#pragma unroll 4
+        for (int ci = 0; ci < 32; ++ci)
+#pragma unroll
+            for (int k = 0; k < kPostK; ++k) acc = fmaf(ws[ci * kPostK + k], xs[ci][i + k], acc);
+        audio[(size_t)b * L + t0 + i] = tanhf(acc);
+    }
+}
+
 //                     CIN  COUT S  PTOT WC WP WBUF  POST
 using Stage0 = StageCfg<512, 256, 8,  96, 16, 1, 4096, false>;
 using Stage1 = StageCfg<256, 128, 8, 192,  8, 2, 4096, false>;
 using Stage2 = StageCfg<128,  64, 2, 384,  8, 2, 2048, false>;
 using Stage3 = StageCfg< 64,  32, 2, 768,  4, 4, 2048, true>;
+// ConvTranspose1d-only variants (no halo, no U buffer)
+using Up0 = StageCfg<512, 256, 8,  96, 16, 1, 4096, false, false>;
+using Up1 = StageCfg<256, 128, 8, 192,  8, 2, 4096, false, false>;
+using Up2 = StageCfg<128,  64, 2, 384,  8, 2, 2048, false, false>;
+using Up3 = StageCfg< 64,  32, 2, 768,  4, 4, 2048, false, false>;
 
 template <class Cfg>
 static int launch_stage(const float *x, float *y, const float *packed, int stage, int B, int Lin, cudaStream_t s) {
@@ -334,6 +368,39 @@ static int launch_stage(const float *x, float *y, const float *packed, int stage
 }
 
 int generator_simt_num_launches() { return 5; }
+int generator_tc_num_launches() { return 10; }
+
+// Tensor-core pipeline (development stage): conv_pre (SIMT) -> 4 x [ConvT (SIMT) -> ResBlock (tcgen05)] -> post (SIMT)
+int launch_generator_tc(const float *packed, const float *mel, float *audio, int B, int T, float *ws, int *status,
+                        cudaStream_t s, cudaEvent_t *ev) {
+#define MG_MARK(i) do { if (ev) MG_CUDA_TRY(cudaEventRecord(ev[i], s)); } while (0)
+    float *a0 = ws + ws_offset(0, B, T);
+    float *a[4] = {ws + ws_offset(1, B, T), ws + ws_offset(2, B, T), ws + ws_offset(3, B, T), ws + ws_offset(4, B, T)};
+    float *u = ws + ws_offset(5, B, T);  // ConvT output of the current stage (largest: B*8192*T floats)
+    dim3 gpre((T + kPreTT - 1) / kPreTT, B);
+    MG_MARK(0);
+    gen_pre_kernel<<<gpre, 512, 0, s>>>(mel, a0, packed, T);
+    MG_CUDA_TRY(cudaGetLastError());
+    int rc;
+    MG_MARK(1);
+    if ((rc = launch_stage<Up0>(a0, u, packed, 0, B, T, s))) return rc;
+    if ((rc = launch_resblock_tc(u, a[0], packed, 0, B, 8 * T, status, s))) return rc;
+    MG_MARK(2);
+    if ((rc = launch_stage<Up1>(a[0], u, packed, 1, B, 8 * T, s))) return rc;
+    if ((rc = launch_resblock_tc(u, a[1], packed, 1, B, 64 * T, status, s))) return rc;
+    MG_MARK(3);
+    if ((rc = launch_stage<Up2>(a[1], u, packed, 2, B, 64 * T, s))) return rc;
+    if ((rc = launch_resblock_tc(u, a[2], packed, 2, B, 128 * T, status, s))) return rc;
+    MG_MARK(4);
+    if ((rc = launch_stage<Up3>(a[2], u, packed, 3, B, 128 * T, s))) return rc;
+    if ((rc = launch_resblock_tc(u, a[3], packed, 3, B, 256 * T, status, s))) return rc;
+    dim3 gpost((256 * T + kPostTile - 1) / kPostTile, B);
+    gen_post_kernel<<<gpost, 256, 0, s>>>(a[3], audio, packed, 256 * T);
+    MG_CUDA_TRY(cudaGetLastError());
+    MG_MARK(5);
+#undef MG_MARK
+    return MG_OK;
+}
 
 int launch_generator_simt(const float *packed, const float *mel, float *audio, int B, int T, float *ws,
                           cudaStream_t s, cudaEvent_t *ev) {

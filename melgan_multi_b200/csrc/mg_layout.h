@@ -74,6 +74,29 @@ MG_HD constexpr size_t packed_float_count() { return bias_offset(kNumLayers); }
 
 static_assert(packed_float_count() == 4524290 - 4353, "packed blob = all G params minus the weight_g scalars");
 
+// ---- tensor-core (split-bf16) blob for the 24 ResBlock convs -------------------------------------------
+// Appended to the fp32 blob.  Per conv (C channels, 3 taps): chunks of KC input channels in consumption order
+//   [tap][kslice = ci/KC][half: hi, lo][k-panel = (ci%KC)/8][co][ci%8]   (bf16)
+// so one (tap, kslice) chunk -- hi and lo halves back to back -- is one contiguous bulk copy, and inside a
+// half the layout is the "row-linear K-major" operand layout of mg_tc.cuh with rows = output channels.
+MG_HD constexpr int tc_kc(int C) { return C >= 128 ? 4096 / C : C; }          // 256:16, 128:32, 64:64, 32:32
+MG_HD constexpr int tc_chunk_bytes(int C) { return 4 * C * tc_kc(C); }          // hi + lo halves
+MG_HD constexpr int tc_chunks_per_conv(int C) { return 3 * C / tc_kc(C); }
+MG_HD constexpr size_t tc_conv_bytes(int C) { return (size_t)12 * C * C; }
+MG_HD constexpr size_t tc_res_offset(int l) {  // bytes from the start of the TC region, l in [5, 28]
+    size_t o = 0;
+    for (int i = 5; i < l; ++i) o += tc_conv_bytes(layer_shape(i).cout);
+    return o;
+}
+MG_HD constexpr size_t tc_region_bytes() { return tc_res_offset(29); }
+MG_HD constexpr size_t packed_total_bytes() { return ((packed_float_count() * 4 + 255) / 256) * 256 + tc_region_bytes(); }
+MG_HD constexpr size_t tc_region_start() { return ((packed_float_count() * 4 + 255) / 256) * 256; }  // bytes
+// element (bf16) index of w[co][ci][tap] (half h) inside its conv's TC block
+MG_HD constexpr size_t tc_weight_index(int C, int co, int ci, int tap, int h) {
+    const int KC = tc_kc(C);
+    return ((((size_t)(tap * (C / KC) + ci / KC) * 2 + h) * (KC / 8) + (ci % KC) / 8) * C + co) * 8 + (ci % 8);
+}
+
 // Activation workspace (floats per batch item per mel frame): conv_pre out, stage 0..2 outs.
 MG_HD constexpr size_t ws_offset(int which, size_t B, size_t T) {  // which: 0 pre, 1..3 stage 0..2
     size_t o = 0;
@@ -81,6 +104,8 @@ MG_HD constexpr size_t ws_offset(int which, size_t B, size_t T) {  // which: 0 p
     if (which >= 2) o += B * 256 * 8 * T;
     if (which >= 3) o += B * 128 * 64 * T;
     if (which >= 4) o += B * 64 * 128 * T;
+    if (which >= 5) o += B * 32 * 256 * T;   // stage 3 output (tensor-core pipeline only)
+    if (which >= 6) o += B * 32 * 256 * T;   // ConvT scratch (tensor-core pipeline only)
     return o;
 }
 

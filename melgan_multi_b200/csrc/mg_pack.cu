@@ -4,6 +4,7 @@
 // norm over every axis but 0; models.py:16-28,46-59).  One CTA per norm row (4353 rows):
 // the CTA reduces ||v_row||^2, then scatters g/||v|| * v into the packed layout of mg_layout.h.
 #include "mg_common.cuh"
+#include "mg_tc.cuh"
 
 namespace mg {
 
@@ -54,6 +55,18 @@ __global__ void __launch_bounds__(128) pack_kernel(PackArgs a, RowTable rt, floa
     if (sh.kind == 0) {
         // v[co=row][ci][k] -> wp[(ci*K + k)*Cout + co]
         for (int j = threadIdx.x; j < inner; j += blockDim.x) wp[(size_t)j * sh.cout + row] = scale * vr[j];
+        if (l >= 5 && l <= 28) {
+            // split-bf16 copy for the tensor-core ResBlock kernels (layout: mg_layout.h, tc_weight_index)
+            __nv_bfloat16 *tcw = reinterpret_cast<__nv_bfloat16 *>(reinterpret_cast<char *>(packed) + tc_region_start() +
+                                                                  tc_res_offset(l));
+            for (int j = threadIdx.x; j < inner; j += blockDim.x) {
+                const int ci = j / 3, tap = j - 3 * ci;
+                __nv_bfloat16 hi, lo;
+                tc::split_bf16(scale * vr[j], hi, lo);
+                tcw[tc_weight_index(sh.cout, row, ci, tap, 0)] = hi;
+                tcw[tc_weight_index(sh.cout, row, ci, tap, 1)] = lo;
+            }
+        }
     } else {
         // v[ci=row][co][k] -> wp[((ci*Cout + co)*S + k%S)*2 + k/S]
         const int S = sh.stride;

@@ -1,0 +1,281 @@
+// ResBlock on the 5th-gen tensor cores (tcgen05 + TMEM), split-bf16 (3 MMAs per product) for fp32-grade results.
+//
+// Reference semantics: ResBlock.forward, models.py:32-40 -- three times  x = c2(lrelu(c1(lrelu(x)))) + x  with
+// c1 dilations 1/3/9 and c2 dilation 1, all k=3 "same" convs on C channels.
+//
+// One CTA owns P = 128*NBLK consecutive positions of one batch item (16-position halo per side, recomputed by
+// the neighbours) and keeps the whole block on chip:
+//   TMEM   per 128-position block: R  [128 lanes x C cols] fp32  residual stream  (lane = position)
+//                                  D1 [128 lanes x C cols] fp32  c1 accumulator
+//   smem   X  = lrelu(current conv input) as split-bf16 (hi, lo), "row-linear K-major" (mg_tc.cuh): row = position,
+//               k-panels of 8 channels.  A conv tap at dilation d is the same buffer with the start address
+//               moved by 16*d bytes -- there is no im2col and no per-tap restaging.
+//   smem   ring of weight chunks (one (tap, K-slice) of [Cout x KC] hi+lo per chunk), filled by 1-D bulk TMA
+//               copies from the pre-packed blob (mg_layout.h), released by tcgen05.commit.
+// GEMM view of one conv: D[pos, co] (+)= sum_tap sum_pass X_pass[pos + (tap-1)*d, :] * W_pass[tap][co, :]^T with
+// M = 128 positions, N = C, K = 16 per instruction; passes (xh,wh), (xl,wh), (xh,wl).
+// c2 accumulates straight onto R, so the residual add costs nothing; conv biases are added when the accumulator
+// is read back (b2 is carried in `pend`).  Positions outside [0, L) are written as zeros into X after every conv,
+// which is the per-layer zero padding of the reference.
+//
+// Warp roles: NEPI/32 epilogue warps (TMEM -> registers -> bias/LeakyReLU/mask/split -> X), one TMA producer
+// warp, one MMA issuer warp (a single elected thread issues tcgen05.mma for the whole CTA).
+#include "mg_common.cuh"
+#include "mg_tc.cuh"
+
+namespace mg {
+using namespace tc;
+
+template <int C_>
+struct RbCfg {
+    static constexpr int C = C_;
+    static constexpr int NBLK = 256 / C;  // 128-position blocks per CTA: TMEM has 512 columns, a block needs 2C
+    static constexpr int P = 128 * NBLK;
+    static constexpr int SLACK = 16;      // zero rows either side of X (dilation-9 taps reach 9 rows out)
+    static constexpr int HALO = 16;       // 1+1+3+1+9+1
+    static constexpr int PVALID = P - 2 * HALO;
+    static constexpr int ROWS = P + 2 * SLACK;
+    static constexpr int XPITCH = ROWS * 16;  // bytes between k-panels
+    static constexpr int KP = C / 8;
+    static constexpr int XBYTES = KP * XPITCH;  // one of {hi, lo}
+    static constexpr int KC = tc_kc(C);
+    static constexpr int CHUNK = tc_chunk_bytes(C);
+    static constexpr int HALF = CHUNK / 2;
+    static constexpr int NCHUNK = tc_chunks_per_conv(C);
+    static constexpr int KSL = C / KC;
+    static constexpr int NSTAGE = 4;
+    static constexpr int NWG = NBLK >= 2 ? 2 : 1;
+    static constexpr int NEPI = 128 * NWG;
+    static constexpr int NT = NEPI + 64;
+    static constexpr int SMEM_BYTES = 2 * XBYTES + NSTAGE * CHUNK + C * 4 + (2 * NSTAGE + 1) * 8 + 16;
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+    static_assert(XPITCH / 16 < 16384, "LBO field");
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+// lrelu + mask + split 16 consecutive channels of one position and store them into the two k-panels they span
+__device__ __forceinline__ void store_x16(uint8_t *Xh, uint8_t *Xl, int xpitch, int c0, int xrow_bytes, const float (&f)[16]) {
+    uint32_t h[8], l[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) split2_bf16(f[2 * e], f[2 * e + 1], h[e], l[e]);
+    uint8_t *ph = Xh + (c0 >> 3) * xpitch + xrow_bytes;
+    uint8_t *pl = Xl + (c0 >> 3) * xpitch + xrow_bytes;
+    *reinterpret_cast<uint4 *>(ph) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4 *>(ph + xpitch) = make_uint4(h[4], h[5], h[6], h[7]);
+    *reinterpret_cast<uint4 *>(pl) = make_uint4(l[0], l[1], l[2], l[3]);
+    *reinterpret_cast<uint4 *>(pl + xpitch) = make_uint4(l[4], l[5], l[6], l[7]);
+}
+
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::NT, 1)
+resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const float *__restrict__ packed, int stage, int L,
+                   int *__restrict__ status) {
+    constexpr int C = Cfg::C, NBLK = Cfg::NBLK, P = Cfg::P, SLACK = Cfg::SLACK, HALO = Cfg::HALO;
+    constexpr int XPITCH = Cfg::XPITCH, XBYTES = Cfg::XBYTES, KC = Cfg::KC, CHUNK = Cfg::CHUNK, NSTAGE = Cfg::NSTAGE;
+    constexpr int NEPI = Cfg::NEPI, NWG = Cfg::NWG;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *Xh = smem, *Xl = smem + XBYTES, *ring = smem + 2 * XBYTES;
+    float *pend = reinterpret_cast<float *>(ring + NSTAGE * CHUNK);
+    uint64_t *full = reinterpret_cast<uint64_t *>(pend + C);
+    uint64_t *empty = full + NSTAGE;
+    uint64_t *done = empty + NSTAGE;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.y;
+    const int o = blockIdx.x * Cfg::PVALID - HALO;  // global position of tile-local p = 0
+    // consumption order of the six convs of ResBlock `stage`: c1[0], c2[0], c1[1], c2[1], c1[2], c2[2]
+    const int l0 = 5 + 6 * stage;
+    const uint8_t *tc_base = reinterpret_cast<const uint8_t *>(packed) + tc_region_start();
+
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    if (tid == 32) {
+        for (int s = 0; s < NSTAGE; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(done, 1);
+        fence_mbar_init();
+    }
+    for (int i = tid; i < 2 * Cfg::KP * 2 * SLACK; i += Cfg::NT) {  // zero the slack rows of Xh and Xl
+        const int r = i % (2 * SLACK), kp = (i / (2 * SLACK)) % Cfg::KP, hl = i / (2 * SLACK * Cfg::KP);
+        const int row = r < SLACK ? r : P + r;  // r in [SLACK, 2*SLACK) -> rows P+SLACK .. P+2*SLACK-1
+        *reinterpret_cast<uint4 *>((hl ? Xl : Xh) + kp * XPITCH + row * 16) = make_uint4(0, 0, 0, 0);
+    }
+    for (int i = tid; i < C; i += Cfg::NT) pend[i] = 0.f;
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == NEPI / 32) {
+        // ================= TMA producer: streams the 6 * NCHUNK weight chunks through the ring =================
+        if (lane == 0) {
+            int s = 0, ph = 0;
+            bool ok = true;
+            for (int conv = 0; conv < 6 && ok; ++conv) {
+                const int layer = l0 + (conv >> 1) + 3 * (conv & 1);
+                const uint8_t *src = tc_base + tc_res_offset(layer);
+                for (int ch = 0; ch < Cfg::NCHUNK; ++ch) {
+                    if (!mbar_wait(&empty[s], ph ^ 1)) { ok = false; break; }
+                    mbar_arrive_expect_tx(&full[s], CHUNK);
+                    bulk_g2s(ring + s * CHUNK, src + (size_t)ch * CHUNK, CHUNK, &full[s]);
+                    if (++s == NSTAGE) { s = 0; ph ^= 1; }
+                }
+            }
+            if (!ok) atomicExch(status, 2);
+        }
+    } else if (warp == NEPI / 32 + 1) {
+        // ================= MMA issuer =================
+        const uint32_t idesc = make_idesc_bf16(128, C);
+        int s = 0, ph = 0;
+        bool ok = true;
+        for (int conv = 0; conv < 6; ++conv) {
+            named_bar_sync(1, NEPI + 32);  // X for this conv is complete
+            tc_fence_after();
+            if (lane == 0 && ok) {
+                const int dil = (conv & 1) ? 1 : (conv == 0 ? 1 : conv == 2 ? 3 : 9);
+                const uint32_t dcol = (conv & 1) ? 0 : C;  // c1 -> D1, c2 -> R (accumulating onto the residual)
+                const bool fresh = !(conv & 1);
+                for (int ch = 0; ch < Cfg::NCHUNK && ok; ++ch) {
+                    const int tap = ch / Cfg::KSL, ks = ch % Cfg::KSL;
+                    if (!mbar_wait(&full[s], ph)) { ok = false; break; }
+                    tc_fence_after();
+                    const uint32_t wbase = smem_u32(ring + s * CHUNK);
+#pragma unroll
+                    for (int pass = 0; pass < 3; ++pass) {
+                        const uint32_t xa = smem_u32(pass == 1 ? Xl : Xh);
+                        const uint32_t wb = wbase + (pass == 2 ? Cfg::HALF : 0);
+#pragma unroll
+                        for (int k16 = 0; k16 < KC / 16; ++k16) {
+                            const uint64_t bdesc = make_desc(wb + 2 * k16 * (C * 16), C * 16, 128);
+#pragma unroll
+                            for (int blk = 0; blk < NBLK; ++blk) {
+                                const uint32_t a_addr = xa + (ks * (KC / 8) + 2 * k16) * XPITCH +
+                                                        (blk * 128 + SLACK + (tap - 1) * dil) * 16;
+                                const bool acc = !(fresh && ch == 0 && pass == 0 && k16 == 0);
+                                mma_bf16(tmem + blk * 2 * C + dcol, make_desc(a_addr, XPITCH, 128), bdesc, idesc, acc);
+                            }
+                        }
+                    }
+                    mma_commit(&empty[s]);  // ring slot free once these MMAs have read it
+                    if (++s == NSTAGE) { s = 0; ph ^= 1; }
+                }
+                mma_commit(done);
+                if (!ok) atomicExch(status, 3);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ================= epilogue warps =================
+        const int wg = warp >> 2, q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+        const float *bias_base = packed;  // fp32 blob: biases at bias_offset(layer)
+
+        // ---- load the input tile: R <- x (fp32, exact), X <- split(lrelu(x))
+        for (int blk = wg; blk < NBLK; blk += NWG) {
+            const int p = blk * 128 + row, t = o + p;
+            const bool inr = (t >= 0 && t < L);
+            const float *xp = x + (size_t)b * C * L + (inr ? t : 0);
+#pragma unroll 1
+            for (int c0 = 0; c0 < C; c0 += 16) {
+                uint32_t v[16];
+                float f[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float xv = inr ? __ldg(xp + (size_t)(c0 + j) * L) : 0.f;
+                    v[j] = __float_as_uint(xv);
+                    f[j] = lrelu(xv);
+                }
+                tmem_st16(lane_addr + blk * 2 * C + c0, v);
+                store_x16(Xh, Xl, XPITCH, c0, (p + SLACK) * 16, f);
+            }
+        }
+        tmem_st_wait();
+
+        bool ok = true;
+        for (int conv = 0; conv < 6; ++conv) {
+            fence_proxy_async();
+            tc_fence_before();
+            named_bar_sync(1, NEPI + 32);  // hand X to the MMA warp
+            if (ok && !mbar_wait(done, conv & 1)) { ok = false; if (lane == 0) atomicExch(status, 4); }
+            tc_fence_after();
+            const int layer = l0 + (conv >> 1) + 3 * (conv & 1);
+            const float *bias = bias_base + bias_offset(layer);
+            if (conv & 1) {  // a c2 finished: R holds x_new - b2; fold b2 into pend
+                for (int c = tid; c < C; c += NEPI) pend[c] += __ldg(bias + c);
+                named_bar_sync(2, NEPI);
+            }
+            if (conv == 5) break;
+            const uint32_t scol = (conv & 1) ? 0 : C;  // next input comes from R (after c2) or D1 (after c1)
+            for (int blk = wg; blk < NBLK; blk += NWG) {
+                const int p = blk * 128 + row, t = o + p;
+                const bool inr = (t >= 0 && t < L);
+#pragma unroll 1
+                for (int c0 = 0; c0 < C; c0 += 16) {
+                    uint32_t v[16];
+                    float f[16];
+                    tmem_ld16(lane_addr + blk * 2 * C + scol + c0, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float bj = (conv & 1) ? pend[c0 + j] : __ldg(bias + c0 + j);
+                        f[j] = inr ? lrelu(__uint_as_float(v[j]) + bj) : 0.f;
+                    }
+                    store_x16(Xh, Xl, XPITCH, c0, (p + SLACK) * 16, f);
+                }
+            }
+        }
+        // ---- store the valid part of R + pend
+        for (int blk = wg; blk < NBLK; blk += NWG) {
+            const int p = blk * 128 + row, t = o + p;
+            const bool valid = (p >= HALO && p < P - HALO && t < L);
+            float *yp = y + (size_t)b * C * L + (valid ? t : 0);
+#pragma unroll 1
+            for (int c0 = 0; c0 < C; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(lane_addr + blk * 2 * C + c0, v);
+                tmem_ld_wait();
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) yp[(size_t)(c0 + j) * L] = __uint_as_float(v[j]) + pend[c0 + j];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+template <class Cfg>
+static int launch_resblock(const float *x, float *y, const float *packed, int stage, int B, int L, int *status,
+                           cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        MG_CUDA_TRY(cudaFuncSetAttribute(resblock_tc_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        configured = true;
+    }
+    dim3 grid((L + Cfg::PVALID - 1) / Cfg::PVALID, B);
+    resblock_tc_kernel<Cfg><<<grid, Cfg::NT, Cfg::SMEM_BYTES, s>>>(x, y, packed, stage, L, status);
+    MG_CUDA_TRY(cudaGetLastError());
+    return MG_OK;
+}
+
+// x, y: [B][C][L] fp32 NCL with C = 256 >> stage; status: device int, set non-zero if a pipeline wait timed out.
+int launch_resblock_tc(const float *x, float *y, const float *packed, int stage, int B, int L, int *status, cudaStream_t s) {
+    switch (stage) {
+        case 0: return launch_resblock<RbCfg<256>>(x, y, packed, stage, B, L, status, s);
+        case 1: return launch_resblock<RbCfg<128>>(x, y, packed, stage, B, L, status, s);
+        case 2: return launch_resblock<RbCfg<64>>(x, y, packed, stage, B, L, status, s);
+        case 3: return launch_resblock<RbCfg<32>>(x, y, packed, stage, B, L, status, s);
+    }
+    return set_error(MG_ERR_INVALID_ARGUMENT, "launch_resblock_tc: stage %d", stage);
+}
+
+}  // namespace mg

@@ -44,6 +44,11 @@ def lib():
                                      ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
         L.mg_gen_forward_timed.restype = ctypes.c_int
         L.mg_gen_forward_timed.argtypes = L.mg_gen_forward.argtypes + [ctypes.POINTER(ctypes.c_float)]
+        L.mg_gen_check_status.restype = ctypes.c_int
+        L.mg_gen_check_status.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        L.mg_gen_resblock.restype = ctypes.c_int
+        L.mg_gen_resblock.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                      ctypes.c_int, ctypes.c_void_p]
         L.mg_gen_stage_output.restype = ctypes.c_int
         L.mg_gen_stage_output.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                           ctypes.c_int, ctypes.c_void_p]
@@ -86,7 +91,7 @@ class GeneratorDevice:
             raise EngineError("the B200 engine runs on CUDA devices only (got %s)" % (device,))
         with torch.cuda.device(self.device):
             check(lib().mg_device_check())
-        self.packed = torch.empty(lib().mg_gen_packed_bytes() // 4, dtype=torch.float32, device=self.device)
+        self.packed = torch.empty((lib().mg_gen_packed_bytes() + 3) // 4, dtype=torch.float32, device=self.device)
         self._ws = None
         self._ws_key = None
 
@@ -146,6 +151,26 @@ class GeneratorDevice:
             check(lib().mg_gen_forward_timed(self.packed.data_ptr(), mel.data_ptr(), out.data_ptr(), B, T,
                                              ws.data_ptr(), ws.numel() * 4, stream, ms))
         return list(ms)
+
+    def check_status(self, B, T):
+        """Synchronises and raises if the tensor-core pipeline of the last forward timed out."""
+        torch = self.torch
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            check(lib().mg_gen_check_status(self._ws.data_ptr(), B, T, stream))
+
+    def resblock(self, stage, x):
+        """One tensor-core ResBlock (stage 0..3) on x [B, 256>>stage, L]; synchronous."""
+        torch = self.torch
+        x = x.contiguous()
+        B, C, L = x.shape
+        if C != (256 >> stage):
+            raise EngineError("stage %d expects %d channels" % (stage, 256 >> stage))
+        y = torch.empty_like(x)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            check(lib().mg_gen_resblock(self.packed.data_ptr(), stage, x.data_ptr(), y.data_ptr(), B, L, stream))
+        return y
 
     def stage_output(self, which, B, T):
         """Activation after conv_pre (0) or stage 0..2 (1..3) of the last forward, NCL."""
