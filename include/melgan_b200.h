@@ -88,6 +88,11 @@ int mg_gen_forward_timed(const void *packed, const float *mel, float *audio, int
  * of hanging the device). */
 int mg_gen_check_status(const void *workspace, int B, int T, void *stream);
 
+/* LeakyReLU -> ConvTranspose1d (models.py:64-65, ups[stage], models.py:48-51) on the tensor-core path:
+ * x [B, 512>>stage, Lin] -> y [B, 256>>stage, S*Lin] (S = 8, 8, 2, 2), device fp32, x != y.  Synchronous;
+ * parity-test entry point for the tcgen05 ConvT kernel. */
+int mg_gen_convt(const void *packed, int stage, const float *x, float *y, int B, int Lin, void *stream);
+
 /* One ResBlock (models.py:32-40) of stage `stage` (C = 256 >> stage channels) on the tensor-core path:
  * x, y [B, C, L] device fp32, x != y.  Synchronous; parity-test entry point for the tcgen05 kernel. */
 int mg_gen_resblock(const void *packed, int stage, const float *x, float *y, int B, int L, void *stream);

@@ -34,7 +34,8 @@ static int run_generator(const float *packed, const float *mel, float *audio, in
     if (!use_tc()) return launch_generator_simt(packed, mel, audio, B, T, ws, s, ev);
     int *st = status_ptr(ws, B, T);
     MG_CUDA_TRY(cudaMemsetAsync(st, 0, sizeof(int), s));
-    return launch_generator_tc(packed, mel, audio, B, T, ws, st, s, ev);
+    const char *up = getenv("MG_UP_PATH");
+    return launch_generator_tc(packed, mel, audio, B, T, ws, st, !(up && strcmp(up, "simt") == 0), s, ev);
 }
 
 static int check_shape(const char *fn, int B, int T) {
@@ -135,6 +136,24 @@ int mg_gen_check_status(const void *workspace, int B, int T, void *stream) {
     MG_CUDA_TRY(cudaMemcpy(&st, status_ptr(const_cast<void *>(workspace), B, T), sizeof(int), cudaMemcpyDeviceToHost));
     if (st) return set_error(MG_ERR_CUDA, "tensor-core pipeline wait timed out (role code %d)", st);
     return MG_OK;
+}
+
+int mg_gen_convt(const void *packed, int stage, const float *x, float *y, int B, int Lin, void *stream) {
+    if (!packed || !x || !y || x == y || stage < 0 || stage > 3 || B < 1 || Lin < 1)
+        return set_error(MG_ERR_INVALID_ARGUMENT, "mg_gen_convt: bad argument");
+    int *st = nullptr;
+    MG_CUDA_TRY(cudaMalloc(&st, sizeof(int)));
+    cudaMemsetAsync(st, 0, sizeof(int), (cudaStream_t)stream);
+    int rc = launch_convt_tc(x, y, (const float *)packed, stage, B, Lin, st, (cudaStream_t)stream);
+    int h = 0;
+    if (rc == MG_OK) {
+        cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+        if (e != cudaSuccess) rc = set_error(MG_ERR_CUDA, "mg_gen_convt: %s", cudaGetErrorString(e));
+        else if (cudaMemcpy(&h, st, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess || h)
+            rc = set_error(MG_ERR_CUDA, "mg_gen_convt: pipeline wait timed out (role code %d)", h);
+    }
+    cudaFree(st);
+    return rc;
 }
 
 int mg_gen_resblock(const void *packed, int stage, const float *x, float *y, int B, int L, void *stream) {

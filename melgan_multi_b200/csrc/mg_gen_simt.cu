@@ -371,7 +371,7 @@ int generator_simt_num_launches() { return 5; }
 int generator_tc_num_launches() { return 10; }
 
 // Tensor-core pipeline (development stage): conv_pre (SIMT) -> 4 x [ConvT (SIMT) -> ResBlock (tcgen05)] -> post (SIMT)
-int launch_generator_tc(const float *packed, const float *mel, float *audio, int B, int T, float *ws, int *status,
+int launch_generator_tc(const float *packed, const float *mel, float *audio, int B, int T, float *ws, int *status, bool up_tc,
                         cudaStream_t s, cudaEvent_t *ev) {
 #define MG_MARK(i) do { if (ev) MG_CUDA_TRY(cudaEventRecord(ev[i], s)); } while (0)
     float *a0 = ws + ws_offset(0, B, T);
@@ -383,16 +383,16 @@ int launch_generator_tc(const float *packed, const float *mel, float *audio, int
     MG_CUDA_TRY(cudaGetLastError());
     int rc;
     MG_MARK(1);
-    if ((rc = launch_stage<Up0>(a0, u, packed, 0, B, T, s))) return rc;
+    if ((rc = up_tc ? launch_convt_tc(a0, u, packed, 0, B, T, status, s) : launch_stage<Up0>(a0, u, packed, 0, B, T, s))) return rc;
     if ((rc = launch_resblock_tc(u, a[0], packed, 0, B, 8 * T, status, s))) return rc;
     MG_MARK(2);
-    if ((rc = launch_stage<Up1>(a[0], u, packed, 1, B, 8 * T, s))) return rc;
+    if ((rc = up_tc ? launch_convt_tc(a[0], u, packed, 1, B, 8 * T, status, s) : launch_stage<Up1>(a[0], u, packed, 1, B, 8 * T, s))) return rc;
     if ((rc = launch_resblock_tc(u, a[1], packed, 1, B, 64 * T, status, s))) return rc;
     MG_MARK(3);
-    if ((rc = launch_stage<Up2>(a[1], u, packed, 2, B, 64 * T, s))) return rc;
+    if ((rc = up_tc ? launch_convt_tc(a[1], u, packed, 2, B, 64 * T, status, s) : launch_stage<Up2>(a[1], u, packed, 2, B, 64 * T, s))) return rc;
     if ((rc = launch_resblock_tc(u, a[2], packed, 2, B, 128 * T, status, s))) return rc;
     MG_MARK(4);
-    if ((rc = launch_stage<Up3>(a[2], u, packed, 3, B, 128 * T, s))) return rc;
+    if ((rc = up_tc ? launch_convt_tc(a[2], u, packed, 3, B, 128 * T, status, s) : launch_stage<Up3>(a[2], u, packed, 3, B, 128 * T, s))) return rc;
     if ((rc = launch_resblock_tc(u, a[3], packed, 3, B, 256 * T, status, s))) return rc;
     dim3 gpost((256 * T + kPostTile - 1) / kPostTile, B);
     gen_post_kernel<<<gpost, 256, 0, s>>>(a[3], audio, packed, 256 * T);

@@ -74,6 +74,17 @@ __global__ void __launch_bounds__(128) pack_kernel(PackArgs a, RowTable rt, floa
             const int co = j / sh.k, k = j - co * sh.k;
             wp[(((size_t)row * sh.cout + co) * S + (k % S)) * 2 + (k / S)] = scale * vr[j];
         }
+        // split-bf16 copy for the tensor-core ConvT kernel (layout: mg_layout.h, up_weight_index)
+        const int stage = l - 1;
+        __nv_bfloat16 *tcw = reinterpret_cast<__nv_bfloat16 *>(reinterpret_cast<char *>(packed) + tc_region_start() +
+                                                              tc_up_offset(stage));
+        for (int j = threadIdx.x; j < inner; j += blockDim.x) {
+            const int co = j / sh.k, k = j - co * sh.k;
+            __nv_bfloat16 hi, lo;
+            tc::split_bf16(scale * vr[j], hi, lo);
+            tcw[up_weight_index(stage, row, co, k, 0)] = hi;
+            tcw[up_weight_index(stage, row, co, k, 1)] = lo;
+        }
     }
     if (threadIdx.x == 0 && row < sh.cout) packed[bias_offset(l) + row] = a.bias[l][row];
 }

@@ -44,20 +44,25 @@ struct RbCfg {
     static constexpr int NCHUNK = tc_chunks_per_conv(C);
     static constexpr int KSL = C / KC;
     static constexpr int NSTAGE = 4;
-    static constexpr int NWG = NBLK >= 2 ? 2 : 1;
+    // epilogue work split: 4 warpgroups; an item = (128-position block, CW-column part of its C columns)
+    static constexpr int NWG = 4;
+    static constexpr int PARTS = NBLK >= 4 ? 1 : 4 / NBLK;
+    static constexpr int CW = C / PARTS;
+    static constexpr int ITEMS = NBLK * PARTS;
     static constexpr int NEPI = 128 * NWG;
     static constexpr int NT = NEPI + 64;
-    static constexpr int SMEM_BYTES = 2 * XBYTES + NSTAGE * CHUNK + C * 4 + (2 * NSTAGE + 1) * 8 + 16;
+    static constexpr int SMEM_BYTES = 2 * XBYTES + NSTAGE * CHUNK + 2 * C * 4 + (2 * NSTAGE + 1) * 8 + 16;
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
     static_assert(XPITCH / 16 < 16384, "LBO field");
+    static_assert(CW % 32 == 0 && ITEMS % NWG == 0, "epilogue split");
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
-// lrelu + mask + split 16 consecutive channels of one position and store them into the two k-panels they span
-__device__ __forceinline__ void store_x16(uint8_t *Xh, uint8_t *Xl, int xpitch, int c0, int xrow_bytes, const float (&f)[16]) {
+// split 16 consecutive channels of one position (already activated / masked) and store them into the two k-panels they span
+__device__ __forceinline__ void store_x16(uint8_t *Xh, uint8_t *Xl, int xpitch, int c0, int xrow_bytes, const float *f) {
     uint32_t h[8], l[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) split2_bf16(f[2 * e], f[2 * e + 1], h[e], l[e]);
@@ -75,11 +80,12 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
                    int *__restrict__ status) {
     constexpr int C = Cfg::C, NBLK = Cfg::NBLK, P = Cfg::P, SLACK = Cfg::SLACK, HALO = Cfg::HALO;
     constexpr int XPITCH = Cfg::XPITCH, XBYTES = Cfg::XBYTES, KC = Cfg::KC, CHUNK = Cfg::CHUNK, NSTAGE = Cfg::NSTAGE;
-    constexpr int NEPI = Cfg::NEPI, NWG = Cfg::NWG;
+    constexpr int NEPI = Cfg::NEPI, NWG = Cfg::NWG, PARTS = Cfg::PARTS, CW = Cfg::CW, ITEMS = Cfg::ITEMS;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *Xh = smem, *Xl = smem + XBYTES, *ring = smem + 2 * XBYTES;
-    float *pend = reinterpret_cast<float *>(ring + NSTAGE * CHUNK);
-    uint64_t *full = reinterpret_cast<uint64_t *>(pend + C);
+    float *pend = reinterpret_cast<float *>(ring + NSTAGE * CHUNK);  // sum of the c2 biases folded so far
+    float *b1s = pend + C;                                            // bias of the c1 in flight
+    uint64_t *full = reinterpret_cast<uint64_t *>(b1s + C);
     uint64_t *empty = full + NSTAGE;
     uint64_t *done = empty + NSTAGE;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done + 1);
@@ -171,19 +177,20 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
             __syncwarp();
         }
     } else {
-        // ================= epilogue warps =================
+        // ================= epilogue warps (16): lane = position, 4 warpgroups split blocks / column ranges =========
         const int wg = warp >> 2, q = warp & 3;
         const int row = q * 32 + lane;
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
-        const float *bias_base = packed;  // fp32 blob: biases at bias_offset(layer)
 
         // ---- load the input tile: R <- x (fp32, exact), X <- split(lrelu(x))
-        for (int blk = wg; blk < NBLK; blk += NWG) {
+#pragma unroll 1
+        for (int it = wg; it < ITEMS; it += NWG) {
+            const int blk = it / PARTS, cbeg = (it % PARTS) * CW;
             const int p = blk * 128 + row, t = o + p;
             const bool inr = (t >= 0 && t < L);
             const float *xp = x + (size_t)b * C * L + (inr ? t : 0);
 #pragma unroll 1
-            for (int c0 = 0; c0 < C; c0 += 16) {
+            for (int c0 = cbeg; c0 < cbeg + CW; c0 += 16) {
                 uint32_t v[16];
                 float f[16];
 #pragma unroll
@@ -199,51 +206,57 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
         tmem_st_wait();
 
         bool ok = true;
+#pragma unroll 1
         for (int conv = 0; conv < 6; ++conv) {
             fence_proxy_async();
             tc_fence_before();
             named_bar_sync(1, NEPI + 32);  // hand X to the MMA warp
+            // while the tensor core works: stage this conv's bias (c1: its own; c2: fold into pend)
+            const float *bias = packed + bias_offset(l0 + (conv >> 1) + 3 * (conv & 1));
+            if (conv & 1) {
+                for (int c = tid; c < C; c += NEPI) pend[c] += __ldg(bias + c);
+            } else {
+                for (int c = tid; c < C; c += NEPI) b1s[c] = __ldg(bias + c);
+            }
+            named_bar_sync(2, NEPI);
             if (ok && !mbar_wait(done, conv & 1)) { ok = false; if (lane == 0) atomicExch(status, 4); }
             tc_fence_after();
-            const int layer = l0 + (conv >> 1) + 3 * (conv & 1);
-            const float *bias = bias_base + bias_offset(layer);
-            if (conv & 1) {  // a c2 finished: R holds x_new - b2; fold b2 into pend
-                for (int c = tid; c < C; c += NEPI) pend[c] += __ldg(bias + c);
-                named_bar_sync(2, NEPI);
-            }
             if (conv == 5) break;
             const uint32_t scol = (conv & 1) ? 0 : C;  // next input comes from R (after c2) or D1 (after c1)
-            for (int blk = wg; blk < NBLK; blk += NWG) {
+            const float *bsrc = (conv & 1) ? pend : b1s;
+#pragma unroll 1
+            for (int it = wg; it < ITEMS; it += NWG) {
+                const int blk = it / PARTS, cbeg = (it % PARTS) * CW;
                 const int p = blk * 128 + row, t = o + p;
                 const bool inr = (t >= 0 && t < L);
 #pragma unroll 1
-                for (int c0 = 0; c0 < C; c0 += 16) {
-                    uint32_t v[16];
-                    float f[16];
-                    tmem_ld16(lane_addr + blk * 2 * C + scol + c0, v);
+                for (int c0 = cbeg; c0 < cbeg + CW; c0 += 32) {
+                    uint32_t v[32];
+                    float f[32];
+                    tmem_ld32(lane_addr + blk * 2 * C + scol + c0, v);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float bj = (conv & 1) ? pend[c0 + j] : __ldg(bias + c0 + j);
-                        f[j] = inr ? lrelu(__uint_as_float(v[j]) + bj) : 0.f;
-                    }
+                    for (int j = 0; j < 32; ++j) f[j] = inr ? lrelu(__uint_as_float(v[j]) + bsrc[c0 + j]) : 0.f;
                     store_x16(Xh, Xl, XPITCH, c0, (p + SLACK) * 16, f);
+                    store_x16(Xh, Xl, XPITCH, c0 + 16, (p + SLACK) * 16, f + 16);
                 }
             }
         }
         // ---- store the valid part of R + pend
-        for (int blk = wg; blk < NBLK; blk += NWG) {
+#pragma unroll 1
+        for (int it = wg; it < ITEMS; it += NWG) {
+            const int blk = it / PARTS, cbeg = (it % PARTS) * CW;
             const int p = blk * 128 + row, t = o + p;
             const bool valid = (p >= HALO && p < P - HALO && t < L);
             float *yp = y + (size_t)b * C * L + (valid ? t : 0);
 #pragma unroll 1
-            for (int c0 = 0; c0 < C; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(lane_addr + blk * 2 * C + c0, v);
+            for (int c0 = cbeg; c0 < cbeg + CW; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(lane_addr + blk * 2 * C + c0, v);
                 tmem_ld_wait();
                 if (valid) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) yp[(size_t)(c0 + j) * L] = __uint_as_float(v[j]) + pend[c0 + j];
+                    for (int j = 0; j < 32; ++j) yp[(size_t)(c0 + j) * L] = __uint_as_float(v[j]) + pend[c0 + j];
                 }
             }
         }

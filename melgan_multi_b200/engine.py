@@ -46,6 +46,9 @@ def lib():
         L.mg_gen_forward_timed.argtypes = L.mg_gen_forward.argtypes + [ctypes.POINTER(ctypes.c_float)]
         L.mg_gen_check_status.restype = ctypes.c_int
         L.mg_gen_check_status.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        L.mg_gen_convt.restype = ctypes.c_int
+        L.mg_gen_convt.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                   ctypes.c_int, ctypes.c_void_p]
         L.mg_gen_resblock.restype = ctypes.c_int
         L.mg_gen_resblock.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                       ctypes.c_int, ctypes.c_void_p]
@@ -158,6 +161,19 @@ class GeneratorDevice:
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream().cuda_stream
             check(lib().mg_gen_check_status(self._ws.data_ptr(), B, T, stream))
+
+    def convt(self, stage, x):
+        """LeakyReLU -> ConvTranspose1d of stage 0..3 on the tensor cores; x [B, 512>>stage, Lin]; synchronous."""
+        torch = self.torch
+        x = x.contiguous()
+        B, C, L = x.shape
+        if C != (512 >> stage):
+            raise EngineError("stage %d expects %d input channels" % (stage, 512 >> stage))
+        y = torch.empty((B, 256 >> stage, L * (8 if stage < 2 else 2)), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            check(lib().mg_gen_convt(self.packed.data_ptr(), stage, x.data_ptr(), y.data_ptr(), B, L, stream))
+        return y
 
     def resblock(self, stage, x):
         """One tensor-core ResBlock (stage 0..3) on x [B, 256>>stage, L]; synchronous."""

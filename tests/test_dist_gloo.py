@@ -1,0 +1,125 @@
+"""world_size-2 gloo tests (CPU) of the N>1 host logic: the data-parallel gradient wrapper that replaces the
+reference's distributed.py functions, and batch sharding of generator inference (no data-path collective)."""
+import os
+import socket
+import warnings
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+warnings.filterwarnings("ignore")
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _make_model(seed):
+    torch.manual_seed(seed)
+    from melgan_multi_b200 import models
+    return models.Discriminator()  # stock-op module with weight_g/weight_v/bias leaves; runs on CPU
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from melgan_multi_b200 import distributed as mgd
+    torch.set_num_threads(1)
+    model = _make_model(100 + rank)  # ranks start from DIFFERENT weights; wrap must broadcast rank 0's
+    mgd.apply_gradient_allreduce(model)
+    params_after_bcast = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).clone()
+
+    torch.manual_seed(7 + rank)
+    x = torch.randn(2, 1, 256)
+    logits, _ = model(x)
+    loss = (logits ** 2).mean()
+    red = mgd.reduce_tensor(loss.detach(), world)
+    loss.backward()
+    g1 = torch.cat([p.grad.reshape(-1) for p in model.parameters()]).clone()
+
+    # second step after zero_grad(set_to_none=True): grads are re-adopted into the flat buffer
+    for p in model.parameters():
+        p.grad = None
+    logits, _ = model(x * 0.5)
+    (logits ** 2).mean().backward()
+    g2 = torch.cat([p.grad.reshape(-1) for p in model.parameters()]).clone()
+
+    # skipped reduction keeps the local gradient
+    for p in model.parameters():
+        p.grad = None
+    mgd.skip_next_reduction(model)
+    logits, _ = model(x)
+    (logits ** 2).mean().backward()
+    g3 = torch.cat([p.grad.reshape(-1) for p in model.parameters()]).clone()
+    torch.save({"params": params_after_bcast, "g1": g1, "g2": g2, "g3": g3, "loss": loss.detach(), "red": red},
+               os.path.join(out_dir, "r%d.pt" % rank))
+    dist.destroy_process_group()
+
+
+def _single_rank_grads(rank, scale=1.0):
+    """What rank `rank` would compute alone, starting from rank 0's weights."""
+    model = _make_model(100)
+    torch.manual_seed(7 + rank)
+    x = torch.randn(2, 1, 256) * scale
+    logits, _ = model(x)
+    loss = (logits ** 2).mean()
+    loss.backward()
+    return torch.cat([p.grad.reshape(-1) for p in model.parameters()]), loss.detach()
+
+
+def test_gradient_allreduce_wrapper_two_ranks(tmp_path):
+    world, port = 2, _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r = [torch.load(os.path.join(tmp_path, "r%d.pt" % i)) for i in range(world)]
+    ref_params = torch.cat([p.detach().reshape(-1) for p in _make_model(100).parameters()])
+    for i in range(world):
+        assert torch.equal(r[i]["params"], ref_params)  # broadcast from rank 0
+    singles = [_single_rank_grads(i) for i in range(world)]
+    mean_g = (singles[0][0] + singles[1][0]) / 2
+    mean_loss = (singles[0][1] + singles[1][1]) / 2
+    for i in range(world):
+        assert torch.allclose(r[i]["g1"], mean_g, rtol=1e-5, atol=1e-7)
+        assert torch.allclose(r[i]["red"], mean_loss, rtol=1e-6)
+    assert torch.equal(r[0]["g1"], r[1]["g1"]) and torch.equal(r[0]["g2"], r[1]["g2"])
+    halves = [_single_rank_grads(i, 0.5)[0] for i in range(world)]
+    assert torch.allclose(r[0]["g2"], (halves[0] + halves[1]) / 2, rtol=1e-5, atol=1e-7)
+    for i in range(world):  # skipped reduction: local gradient untouched
+        assert torch.allclose(r[i]["g3"], singles[i][0], rtol=1e-5, atol=1e-7)
+    assert not torch.allclose(r[0]["g3"], r[1]["g3"])
+
+
+def _shard_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from melgan_multi_b200 import synth
+    from oracle import torch_port
+    torch.set_num_threads(2)
+    ws, bs = torch_port.fold_state(synth.generator_state(1234))
+    mel = synth.mel_input(4, 6, 11)  # every rank can build the whole batch from the seed ...
+    mine = torch.from_numpy(mel[rank::world])  # ... and owns the items rank, rank+world, ...
+    y = torch_port.generator_forward(ws, bs, mine)
+    gathered = [torch.empty_like(y) for _ in range(world)]
+    dist.all_gather(gathered, y)  # test-only gather; the serving path keeps outputs on their rank
+    if rank == 0:
+        full = torch.empty(4, 1, 6 * 256)
+        for r_, g in enumerate(gathered):
+            full[r_::world] = g
+        np.save(os.path.join(out_dir, "sharded.npy"), full.numpy())
+    dist.destroy_process_group()
+
+
+def test_batch_sharded_inference_equals_unsharded(tmp_path):
+    """Generator inference shards by batch with no data-path collective: rank r computes items r::N and the
+    union equals the unsharded result bit for bit (batch items are independent)."""
+    world, port = 2, _free_port()
+    mp.spawn(_shard_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    from melgan_multi_b200 import synth
+    from oracle import torch_port
+    ws, bs = torch_port.fold_state(synth.generator_state(1234))
+    whole = torch_port.generator_forward(ws, bs, torch.from_numpy(synth.mel_input(4, 6, 11))).numpy()
+    sharded = np.load(os.path.join(tmp_path, "sharded.npy"))
+    np.testing.assert_allclose(sharded, whole, rtol=0, atol=1e-6)

@@ -65,6 +65,23 @@ def test_resblock_tc_matches_oracle(state, dev, stage, B, L):
     assert m < TOL and l2 < TOL, (stage, B, L, m, l2)
 
 
+@pytest.mark.parametrize("stage,B,L", [(0, 2, 32), (0, 64, 32), (0, 1, 1), (0, 3, 130), (1, 2, 256), (1, 1, 5),
+                                       (2, 2, 700), (2, 1, 1), (3, 2, 1500), (3, 1, 511), (3, 1, 512), (3, 1, 513)])
+def test_convt_tc_matches_oracle(state, dev, stage, B, L):
+    cin = 512 >> stage
+    S, pad = (8, 4) if stage < 2 else (2, 1)
+    rs = np.random.RandomState(stage * 1000 + L + B)
+    x = rs.standard_normal((B, cin, L)).astype(np.float32)
+    name = "ups.%d" % stage
+    w = cport.fold_weight_norm(state[name + ".weight_g"], state[name + ".weight_v"])
+    lr = np.where(x > 0, x, x * np.float32(0.01)).astype(np.float32)
+    ref = cport.conv_transpose1d(lr, w, state[name + ".bias"], S, pad)
+    y = dev.convt(stage, torch.from_numpy(x).cuda()).cpu().numpy()
+    assert y.shape == ref.shape
+    m, l2 = rel_errors(y, ref)
+    assert m < TOL and l2 < TOL, (stage, B, L, m, l2)
+
+
 @pytest.mark.parametrize("case", cases.GEN_CASES)
 def test_tc_pipeline_matches_golden(golden, state, tc_path, case):
     B, T, seed, realistic = case
