@@ -243,34 +243,50 @@ def main():
     value = K * frames_per_step / (total_ms * 1e-3)
 
     # ---- per-kernel pass (roofline) -------------------------------------------------------
-    kms = np.zeros(5)
+    names, kms = None, None
     for k in range(K):
         flush.zero_()
-        kms += np.array(gd.forward_timed(mels[k % 4], out))
+        timed = gd.forward_timed(mels[k % 4], out)
+        if names is None:
+            names, kms = [n for n, _ in timed], np.zeros(len(timed))
+        kms += np.array([v for _, v in timed])
     kms /= K
     clocks = sampler.stop()
     pre_f, stage_f, post_f = flops_per_mel_frame()
     frames = B * T
-    k_flops = [pre_f * frames] + [f * frames for f in stage_f]
-    k_flops[4] += post_f * frames
-    dom = 2  # kernel index of stage 1
+    up_f = [[8, 64, 128, 256][i] * (2 * 2 * cin * cout) * frames
+            for i, (cin, cout) in enumerate([(512, 256), (256, 128), (128, 64), (64, 32)])]
+    res_f = [stage_f[i] * frames - up_f[i] for i in range(4)]
+    flops_of = {"conv_pre": pre_f * frames, "post": post_f * frames}
+    for i in range(4):
+        flops_of["up%d" % i] = up_f[i]
+        flops_of["res%d" % i] = res_f[i]
+        flops_of["stage%d(up+res)" % i] = up_f[i] + res_f[i]
+    flops_of["stage3(up+res+post)"] = up_f[3] + res_f[3] + post_f * frames
+    k_flops = [flops_of[n] for n in names]
+    tc_path = os.environ.get("MG_GEN_PATH") == "tc"
+    dom = names.index("res1") if tc_path else names.index("stage1(up+res)")
     dom_tflops = k_flops[dom] / (kms[dom] * 1e-3) / 1e12
     fwd_flops = sum(k_flops)
     packed_bytes = engine.lib().mg_gen_packed_bytes()
-    fwd_bytes = ALG_BYTES_PER_FRAME * frames + packed_bytes
+    # algorithmic HBM bytes: SURVEY 8(d) per-stage-fused figure; the tc pipeline currently makes one extra
+    # round trip of each ConvT output (written by up_i, re-read by res_i): + 2 * (8+32+32+32) KB per mel frame
+    extra = 2 * (8192 + 32768 + 32768 + 32768) if tc_path else 0
+    fwd_bytes = (ALG_BYTES_PER_FRAME + extra) * frames + packed_bytes
     fwd_ms = total_ms / K
     roofline = {
-        "kernel": "gen_stage_kernel<stage 1: lrelu+ConvT(256->128,k16,s8)+ResBlock(128)>",
+        "kernel": ("resblock_tc_kernel<C=128> (stage-1 ResBlock: 6 k3 convs, 36% of generator FLOPs)" if tc_path else
+                   "gen_stage_kernel<stage 1: lrelu+ConvT(256->128,k16,s8)+ResBlock(128)>"),
         "bound": "tensor", "achieved": dom_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
         "frac": dom_tflops / peaks["bf16_tflops"], "traffic": None,
         "peak_source": "%s bf16 dense burst (MEASURED_PEAKS.json)" % peaks["source"],
         "algorithmic_flops_per_launch": k_flops[dom], "avg_launch_ms": float(kms[dom]),
-        "math": ("split-bf16 tcgen05 (3 MMA passes per product) in the ResBlocks; ConvT/pre/post fp32 SIMT"
-                 if os.environ.get("MG_GEN_PATH") == "tc" else "fp32 FFMA (SIMT), 1 pass; tensor pipe not used"),
-        "path": os.environ.get("MG_GEN_PATH", "simt"),
-        "kernel_ms": {n: float(v) for n, v in zip(["conv_pre", "stage0", "stage1", "stage2", "stage3+post"], kms)},
-        "kernel_tflops": {n: k_flops[i] / (kms[i] * 1e-3) / 1e12 for i, n in
-                          enumerate(["conv_pre", "stage0", "stage1", "stage2", "stage3+post"])},
+        "math": ("split-bf16 tcgen05: 3 MMA passes per product, so tensor-pipe work is 3x the algorithmic FLOPs "
+                 "(pipe-level fraction = 3 * frac); conv_pre/post fp32 SIMT" if tc_path else
+                 "fp32 FFMA (SIMT), 1 pass; tensor pipe not used"),
+        "path": "tc" if tc_path else "simt",
+        "kernel_ms": {n: float(v) for n, v in zip(names, kms)},
+        "kernel_tflops": {n: k_flops[i] / (kms[i] * 1e-3) / 1e12 for i, n in enumerate(names)},
         "hbm": {"achieved": fwd_bytes / (fwd_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": fwd_bytes / (fwd_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                 "algorithmic_bytes_per_forward": fwd_bytes,

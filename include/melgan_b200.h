@@ -79,7 +79,8 @@ int mg_gen_forward(const void *packed, const float *mel, float *audio, int B, in
 
 /* Same as mg_gen_forward, but brackets each of the mg_gen_forward_launches() kernels with CUDA
  * events on `stream`, waits for the last one and returns the per-kernel device times in
- * kernel_ms[0..4] (conv_pre, stage 0..3).  Used by bench.py for the per-kernel roofline. */
+ * kernel_ms[0 .. mg_gen_forward_launches()-1] (names: mg_gen_kernel_name(i)).  Used by bench.py for the
+ * per-kernel roofline. */
 int mg_gen_forward_timed(const void *packed, const float *mel, float *audio, int B, int T,
                          void *workspace, size_t workspace_bytes, void *stream, float *kernel_ms);
 
@@ -122,8 +123,10 @@ int mg_gen_engine_forward(mg_gen_engine *e, const float *mel_host, float *audio_
 int mg_gen_engine_last_kernel_ms(mg_gen_engine *e, float *ms);
 void mg_gen_engine_destroy(mg_gen_engine *e);
 
-/* Number of kernel launches one mg_gen_forward enqueues (for bench.py's gpu_launches). */
+/* Number of kernel launches one mg_gen_forward enqueues (for bench.py's gpu_launches; at most 16) and the
+ * name of the i-th one. */
 int mg_gen_forward_launches(void);
+const char *mg_gen_kernel_name(int i);
 
 #ifdef __cplusplus
 }

@@ -99,18 +99,26 @@ int mg_gen_forward_timed(const void *packed, const float *mel, float *audio, int
         return set_error(MG_ERR_INVALID_ARGUMENT, "mg_gen_forward_timed: null argument");
     if (workspace_bytes < mg_gen_workspace_bytes(B, T))
         return set_error(MG_ERR_WORKSPACE_TOO_SMALL, "mg_gen_forward_timed: workspace too small");
-    cudaEvent_t ev[6];
-    for (int i = 0; i < 6; ++i) MG_CUDA_TRY(cudaEventCreate(&ev[i]));
+    const int n = mg_gen_forward_launches();  // events: one before each launch + one after the last
+    cudaEvent_t ev[17];
+    for (int i = 0; i <= n; ++i) MG_CUDA_TRY(cudaEventCreate(&ev[i]));
     rc = run_generator((const float *)packed, mel, audio, B, T, (float *)workspace, (cudaStream_t)stream, ev);
     if (rc == MG_OK) {
-        cudaError_t e = cudaEventSynchronize(ev[5]);
+        cudaError_t e = cudaEventSynchronize(ev[n]);
         if (e != cudaSuccess) rc = set_error(MG_ERR_CUDA, "mg_gen_forward_timed: %s", cudaGetErrorString(e));
-        for (int i = 0; i < 5 && rc == MG_OK; ++i)
+        for (int i = 0; i < n && rc == MG_OK; ++i)
             if (cudaEventElapsedTime(&kernel_ms[i], ev[i], ev[i + 1]) != cudaSuccess)
                 rc = set_error(MG_ERR_CUDA, "mg_gen_forward_timed: cudaEventElapsedTime failed");
     }
-    for (int i = 0; i < 6; ++i) cudaEventDestroy(ev[i]);
+    for (int i = 0; i <= n; ++i) cudaEventDestroy(ev[i]);
     return rc;
+}
+
+const char *mg_gen_kernel_name(int i) {
+    static const char *simt[] = {"conv_pre", "stage0(up+res)", "stage1(up+res)", "stage2(up+res)", "stage3(up+res+post)"};
+    static const char *tcn[] = {"conv_pre", "up0", "res0", "up1", "res1", "up2", "res2", "up3", "res3", "post"};
+    if (i < 0 || i >= mg_gen_forward_launches()) return "";
+    return use_tc() ? tcn[i] : simt[i];
 }
 
 int mg_gen_stage_output(const void *workspace, int which, float *out, int B, int T, void *stream) {

@@ -384,20 +384,25 @@ int launch_generator_tc(const float *packed, const float *mel, float *audio, int
     int rc;
     MG_MARK(1);
     if ((rc = up_tc ? launch_convt_tc(a0, u, packed, 0, B, T, status, s) : launch_stage<Up0>(a0, u, packed, 0, B, T, s))) return rc;
-    if ((rc = launch_resblock_tc(u, a[0], packed, 0, B, 8 * T, status, s))) return rc;
     MG_MARK(2);
-    if ((rc = up_tc ? launch_convt_tc(a[0], u, packed, 1, B, 8 * T, status, s) : launch_stage<Up1>(a[0], u, packed, 1, B, 8 * T, s))) return rc;
-    if ((rc = launch_resblock_tc(u, a[1], packed, 1, B, 64 * T, status, s))) return rc;
+    if ((rc = launch_resblock_tc(u, a[0], packed, 0, B, 8 * T, status, s))) return rc;
     MG_MARK(3);
-    if ((rc = up_tc ? launch_convt_tc(a[1], u, packed, 2, B, 64 * T, status, s) : launch_stage<Up2>(a[1], u, packed, 2, B, 64 * T, s))) return rc;
-    if ((rc = launch_resblock_tc(u, a[2], packed, 2, B, 128 * T, status, s))) return rc;
+    if ((rc = up_tc ? launch_convt_tc(a[0], u, packed, 1, B, 8 * T, status, s) : launch_stage<Up1>(a[0], u, packed, 1, B, 8 * T, s))) return rc;
     MG_MARK(4);
+    if ((rc = launch_resblock_tc(u, a[1], packed, 1, B, 64 * T, status, s))) return rc;
+    MG_MARK(5);
+    if ((rc = up_tc ? launch_convt_tc(a[1], u, packed, 2, B, 64 * T, status, s) : launch_stage<Up2>(a[1], u, packed, 2, B, 64 * T, s))) return rc;
+    MG_MARK(6);
+    if ((rc = launch_resblock_tc(u, a[2], packed, 2, B, 128 * T, status, s))) return rc;
+    MG_MARK(7);
     if ((rc = up_tc ? launch_convt_tc(a[2], u, packed, 3, B, 128 * T, status, s) : launch_stage<Up3>(a[2], u, packed, 3, B, 128 * T, s))) return rc;
+    MG_MARK(8);
     if ((rc = launch_resblock_tc(u, a[3], packed, 3, B, 256 * T, status, s))) return rc;
+    MG_MARK(9);
     dim3 gpost((256 * T + kPostTile - 1) / kPostTile, B);
     gen_post_kernel<<<gpost, 256, 0, s>>>(a[3], audio, packed, 256 * T);
     MG_CUDA_TRY(cudaGetLastError());
-    MG_MARK(5);
+    MG_MARK(10);
 #undef MG_MARK
     return MG_OK;
 }

@@ -56,6 +56,8 @@ def lib():
         L.mg_gen_stage_output.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                           ctypes.c_int, ctypes.c_void_p]
         L.mg_gen_forward_launches.restype = ctypes.c_int
+        L.mg_gen_kernel_name.restype = ctypes.c_char_p
+        L.mg_gen_kernel_name.argtypes = [ctypes.c_int]
         L.mg_gen_engine_create.restype = ctypes.c_int
         L.mg_gen_engine_create.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int]
         L.mg_gen_engine_load_state.restype = ctypes.c_int
@@ -143,12 +145,13 @@ class GeneratorDevice:
         return out
 
     def forward_timed(self, mel, out):
-        """Like forward, returns the 5 per-kernel device times in ms (conv_pre, stage 0..3)."""
+        """Like forward; returns {kernel name: device time in ms} for every launch of the forward."""
         torch = self.torch
         mel = mel.contiguous()
         B, _, T = mel.shape
         ws = self.workspace(B, T)
-        ms = (ctypes.c_float * 5)()
+        n = lib().mg_gen_forward_launches()
+        ms = (ctypes.c_float * 16)()
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream().cuda_stream
             check(lib().mg_gen_forward_timed(self.packed.data_ptr(), mel.data_ptr(), out.data_ptr(), B, T,
