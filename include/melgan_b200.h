@@ -98,6 +98,10 @@ int mg_gen_convt(const void *packed, int stage, const float *x, float *y, int B,
  * x, y [B, C, L] device fp32, x != y.  Synchronous; parity-test entry point for the tcgen05 kernel. */
 int mg_gen_resblock(const void *packed, int stage, const float *x, float *y, int B, int L, void *stream);
 
+/* Diagnostic twin of mg_gen_resblock: also returns 128 clock64 stamps (host buffer) of one interior CTA's
+ * epilogue and MMA roles (slot meaning documented at the definition in csrc/mg_api.cu). */
+int mg_gen_resblock_trace(const void *packed, int stage, const float *x, float *y, int B, int L, long long *trace_host);
+
 /* Debug/parity tap: copies the activation after stage `which` (0 = conv_pre output [B,512,T],
  * 1..3 = ResBlock 0..2 output [B,C,L]; the last stage is fused with conv_post and has no tap) of the LAST mg_gen_forward that used `workspace` into
  * `out` (device, NCL).  Only valid immediately after that call on the same stream. */

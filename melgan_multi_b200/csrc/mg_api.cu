@@ -164,6 +164,27 @@ int mg_gen_convt(const void *packed, int stage, const float *x, float *y, int B,
     return rc;
 }
 
+/* Diagnostic: runs one tensor-core ResBlock and returns clock64 stamps of one interior CTA in trace[0..127]
+ * (host buffer): [0] start, [1] input loaded, per conv c: [2+3c] X handed to MMA warp, [3+3c] accumulator ready,
+ * [4+3c] next X written, [20] output stored; MMA thread: [64+3c] X received, [65+3c] first weights landed,
+ * [66+3c] last MMA issued. */
+int mg_gen_resblock_trace(const void *packed, int stage, const float *x, float *y, int B, int L, long long *trace_host) {
+    if (!packed || !x || !y || x == y || !trace_host || stage < 0 || stage > 3)
+        return set_error(MG_ERR_INVALID_ARGUMENT, "mg_gen_resblock_trace: bad argument");
+    int *st = nullptr;
+    long long *tr = nullptr;
+    MG_CUDA_TRY(cudaMalloc(&st, sizeof(int)));
+    MG_CUDA_TRY(cudaMalloc(&tr, 128 * sizeof(long long)));
+    cudaMemset(st, 0, sizeof(int));
+    cudaMemset(tr, 0, 128 * sizeof(long long));
+    int rc = launch_resblock_tc(x, y, (const float *)packed, stage, B, L, st, 0, tr);
+    if (rc == MG_OK && cudaDeviceSynchronize() != cudaSuccess) rc = set_error(MG_ERR_CUDA, "mg_gen_resblock_trace: kernel failed");
+    if (rc == MG_OK) cudaMemcpy(trace_host, tr, 128 * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(st);
+    cudaFree(tr);
+    return rc;
+}
+
 int mg_gen_resblock(const void *packed, int stage, const float *x, float *y, int B, int L, void *stream) {
     if (!packed || !x || !y || x == y || stage < 0 || stage > 3 || B < 1 || L < 1)
         return set_error(MG_ERR_INVALID_ARGUMENT, "mg_gen_resblock: bad argument");

@@ -45,6 +45,7 @@ int generator_tc_num_launches();
 int launch_generator_tc(const float *packed, const float *mel, float *audio, int B, int T, float *ws, int *status, bool up_tc,
                         cudaStream_t s, cudaEvent_t *ev = nullptr);
 int launch_convt_tc(const float *x, float *y, const float *packed, int stage, int B, int Lin, int *status, cudaStream_t s);
-int launch_resblock_tc(const float *x, float *y, const float *packed, int stage, int B, int L, int *status, cudaStream_t s);
+int launch_resblock_tc(const float *x, float *y, const float *packed, int stage, int B, int L, int *status, cudaStream_t s,
+                       long long *trace = nullptr);
 
 }  // namespace mg

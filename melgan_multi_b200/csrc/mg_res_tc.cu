@@ -50,7 +50,8 @@ struct RbCfg {
     static constexpr int CW = C / PARTS;
     static constexpr int ITEMS = NBLK * PARTS;
     static constexpr int NEPI = 128 * NWG;
-    static constexpr int NT = NEPI + 64;
+    static constexpr int NIW = NBLK >= 4 ? 4 : NBLK;  // MMA issuer warps
+    static constexpr int NT = NEPI + 32 + 32 * NIW;
     static constexpr int SMEM_BYTES = 2 * XBYTES + NSTAGE * CHUNK + 2 * C * 4 + (2 * NSTAGE + 1) * 8 + 16;
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
     static_assert(XPITCH / 16 < 16384, "LBO field");
@@ -77,10 +78,10 @@ __device__ __forceinline__ void store_x16(uint8_t *Xh, uint8_t *Xl, int xpitch, 
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::NT, 1)
 resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const float *__restrict__ packed, int stage, int L,
-                   int *__restrict__ status) {
+                   int *__restrict__ status, long long *__restrict__ trace) {
     constexpr int C = Cfg::C, NBLK = Cfg::NBLK, P = Cfg::P, SLACK = Cfg::SLACK, HALO = Cfg::HALO;
     constexpr int XPITCH = Cfg::XPITCH, XBYTES = Cfg::XBYTES, KC = Cfg::KC, CHUNK = Cfg::CHUNK, NSTAGE = Cfg::NSTAGE;
-    constexpr int NEPI = Cfg::NEPI, NWG = Cfg::NWG, PARTS = Cfg::PARTS, CW = Cfg::CW, ITEMS = Cfg::ITEMS;
+    constexpr int NEPI = Cfg::NEPI, NWG = Cfg::NWG, PARTS = Cfg::PARTS, CW = Cfg::CW, ITEMS = Cfg::ITEMS, NIW = Cfg::NIW;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *Xh = smem, *Xl = smem + XBYTES, *ring = smem + 2 * XBYTES;
     float *pend = reinterpret_cast<float *>(ring + NSTAGE * CHUNK);  // sum of the c2 biases folded so far
@@ -101,9 +102,9 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
     if (tid == 32) {
         for (int s = 0; s < NSTAGE; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], NIW);  // every issuer warp commits its own arrival
         }
-        mbar_init(done, 1);
+        mbar_init(done, NIW);
         fence_mbar_init();
     }
     for (int i = tid; i < 2 * Cfg::KP * 2 * SLACK; i += Cfg::NT) {  // zero the slack rows of Xh and Xl
@@ -117,6 +118,9 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    // optional timeline of one interior CTA (clock64 stamps; see mg_gen_resblock_trace)
+    const bool tr = trace && blockIdx.y == 0 && blockIdx.x == (gridDim.x > 1 ? 1u : 0u) && lane == 0 && (warp == 0 || warp == NEPI / 32 + 1);  // epilogue warp 0 and issuer 0
+#define MG_TR(slot) do { if (tr) trace[slot] = clock64(); } while (0)
 
     if (warp == NEPI / 32) {
         // ================= TMA producer: streams the 6 * NCHUNK weight chunks through the ring =================
@@ -135,45 +139,54 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
             }
             if (!ok) atomicExch(status, 2);
         }
-    } else if (warp == NEPI / 32 + 1) {
-        // ================= MMA issuer =================
+    } else if (warp > NEPI / 32) {
+        // ================= MMA issuers: NIW warps, issuer w owns the 128-position blocks w, w+NIW, ... =================
+        // (each warp runs the loop warp-uniform and one elected lane issues; a single issuing thread sustains only
+        //  one tcgen05.mma per ~50 cycles, which starves the pipe when N = C <= 64)
+        const int iw = warp - (NEPI / 32 + 1);
         const uint32_t idesc = make_idesc_bf16(128, C);
+        const uint64_t adesc_t = desc_template(XPITCH, 128), bdesc_t = desc_template(C * 16, 128);
+        const uint32_t xh_addr = smem_u32(Xh), xl_addr = smem_u32(Xl), ring_addr = smem_u32(ring);
         int s = 0, ph = 0;
-        bool ok = true;
+        bool ok = true;  // a timed-out wait only raises the status word: control flow stays warp-uniform
+#pragma unroll 1
         for (int conv = 0; conv < 6; ++conv) {
-            named_bar_sync(1, NEPI + 32);  // X for this conv is complete
+            named_bar_sync(1, NEPI + 32 * NIW);  // X for this conv is complete
             tc_fence_after();
-            if (lane == 0 && ok) {
-                const int dil = (conv & 1) ? 1 : (conv == 0 ? 1 : conv == 2 ? 3 : 9);
-                const uint32_t dcol = (conv & 1) ? 0 : C;  // c1 -> D1, c2 -> R (accumulating onto the residual)
-                const bool fresh = !(conv & 1);
-                for (int ch = 0; ch < Cfg::NCHUNK && ok; ++ch) {
-                    const int tap = ch / Cfg::KSL, ks = ch % Cfg::KSL;
-                    if (!mbar_wait(&full[s], ph)) { ok = false; break; }
-                    tc_fence_after();
-                    const uint32_t wbase = smem_u32(ring + s * CHUNK);
+            if (iw == 0) MG_TR(64 + 3 * conv);
+            const int dil = (conv & 1) ? 1 : (conv == 0 ? 1 : conv == 2 ? 3 : 9);
+            const uint32_t dcol = (conv & 1) ? 0 : C;  // c1 -> D1, c2 -> R (accumulating onto the residual)
+            const bool fresh = !(conv & 1);
+#pragma unroll 1
+            for (int ch = 0; ch < Cfg::NCHUNK; ++ch) {
+                const int tap = ch / Cfg::KSL, ks = ch % Cfg::KSL;
+                ok &= mbar_wait(&full[s], ph);
+                tc_fence_after();
+                if (ch == 0 && iw == 0) MG_TR(65 + 3 * conv);
+                // per-chunk base descriptors; every MMA below adds a compile-time constant to the address field
+                const uint64_t bbase = desc_at(bdesc_t, ring_addr + s * CHUNK);
+                const uint32_t arow = (SLACK + (tap - 1) * dil) * 16 + ks * (KC / 8) * XPITCH;
+                const uint64_t ah = desc_at(adesc_t, xh_addr + arow), al = desc_at(adesc_t, xl_addr + arow);
 #pragma unroll
-                    for (int pass = 0; pass < 3; ++pass) {
-                        const uint32_t xa = smem_u32(pass == 1 ? Xl : Xh);
-                        const uint32_t wb = wbase + (pass == 2 ? Cfg::HALF : 0);
+                for (int pass = 0; pass < 3; ++pass) {
 #pragma unroll
-                        for (int k16 = 0; k16 < KC / 16; ++k16) {
-                            const uint64_t bdesc = make_desc(wb + 2 * k16 * (C * 16), C * 16, 128);
+                    for (int k16 = 0; k16 < KC / 16; ++k16) {
+                        const uint64_t bdesc = bbase + (uint64_t)(((pass == 2 ? Cfg::HALF : 0) + 2 * k16 * (C * 16)) >> 4);
 #pragma unroll
-                            for (int blk = 0; blk < NBLK; ++blk) {
-                                const uint32_t a_addr = xa + (ks * (KC / 8) + 2 * k16) * XPITCH +
-                                                        (blk * 128 + SLACK + (tap - 1) * dil) * 16;
-                                const bool acc = !(fresh && ch == 0 && pass == 0 && k16 == 0);
-                                mma_bf16(tmem + blk * 2 * C + dcol, make_desc(a_addr, XPITCH, 128), bdesc, idesc, acc);
-                            }
+                        for (int bi = 0; bi < NBLK / NIW; ++bi) {
+                            const int blk = iw + bi * NIW;
+                            const uint64_t adesc = (pass == 1 ? al : ah) + (uint64_t)((2 * k16 * XPITCH) >> 4) + (uint64_t)(blk * 128);
+                            const bool acc = !(fresh && ch == 0 && pass == 0 && k16 == 0);
+                            if (elect_one()) mma_bf16(tmem + blk * 2 * C + dcol, adesc, bdesc, idesc, acc);
                         }
                     }
-                    mma_commit(&empty[s]);  // ring slot free once these MMAs have read it
-                    if (++s == NSTAGE) { s = 0; ph ^= 1; }
                 }
-                mma_commit(done);
-                if (!ok) atomicExch(status, 3);
+                if (elect_one()) mma_commit(&empty[s]);  // ring slot free once these MMAs have read it
+                if (++s == NSTAGE) { s = 0; ph ^= 1; }
             }
+            if (elect_one()) mma_commit(done);
+            if (iw == 0) MG_TR(66 + 3 * conv);
+            if (!ok && lane == 0) atomicExch(status, 3);
             __syncwarp();
         }
     } else {
@@ -182,6 +195,7 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
         const int row = q * 32 + lane;
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
 
+        if (warp == 0) MG_TR(0);
         // ---- load the input tile: R <- x (fp32, exact), X <- split(lrelu(x))
 #pragma unroll 1
         for (int it = wg; it < ITEMS; it += NWG) {
@@ -189,28 +203,33 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
             const int p = blk * 128 + row, t = o + p;
             const bool inr = (t >= 0 && t < L);
             const float *xp = x + (size_t)b * C * L + (inr ? t : 0);
-#pragma unroll 1
-            for (int c0 = cbeg; c0 < cbeg + CW; c0 += 16) {
-                uint32_t v[16];
+            // all CW loads of the item are issued before the first use: one memory round trip, not CW/16
+            uint32_t v[CW];
+#pragma unroll
+            for (int j = 0; j < CW; ++j) v[j] = inr ? __float_as_uint(__ldg(xp + (size_t)(cbeg + j) * L)) : 0u;
+#pragma unroll
+            for (int c0 = 0; c0 < CW; c0 += 16) {
+                uint32_t w[16];
                 float f[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const float xv = inr ? __ldg(xp + (size_t)(c0 + j) * L) : 0.f;
-                    v[j] = __float_as_uint(xv);
-                    f[j] = lrelu(xv);
+                    w[j] = v[c0 + j];
+                    f[j] = lrelu(__uint_as_float(v[c0 + j]));
                 }
-                tmem_st16(lane_addr + blk * 2 * C + c0, v);
-                store_x16(Xh, Xl, XPITCH, c0, (p + SLACK) * 16, f);
+                tmem_st16(lane_addr + blk * 2 * C + cbeg + c0, w);
+                store_x16(Xh, Xl, XPITCH, cbeg + c0, (p + SLACK) * 16, f);
             }
         }
         tmem_st_wait();
+        if (warp == 0) MG_TR(1);
 
         bool ok = true;
 #pragma unroll 1
         for (int conv = 0; conv < 6; ++conv) {
             fence_proxy_async();
             tc_fence_before();
-            named_bar_sync(1, NEPI + 32);  // hand X to the MMA warp
+            if (warp == 0) MG_TR(2 + 3 * conv);
+            named_bar_sync(1, NEPI + 32 * NIW);  // hand X to the MMA warps
             // while the tensor core works: stage this conv's bias (c1: its own; c2: fold into pend)
             const float *bias = packed + bias_offset(l0 + (conv >> 1) + 3 * (conv & 1));
             if (conv & 1) {
@@ -221,6 +240,7 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
             named_bar_sync(2, NEPI);
             if (ok && !mbar_wait(done, conv & 1)) { ok = false; if (lane == 0) atomicExch(status, 4); }
             tc_fence_after();
+            if (warp == 0) MG_TR(3 + 3 * conv);
             if (conv == 5) break;
             const uint32_t scol = (conv & 1) ? 0 : C;  // next input comes from R (after c2) or D1 (after c1)
             const float *bsrc = (conv & 1) ? pend : b1s;
@@ -241,6 +261,7 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
                     store_x16(Xh, Xl, XPITCH, c0 + 16, (p + SLACK) * 16, f + 16);
                 }
             }
+            if (warp == 0) MG_TR(4 + 3 * conv);
         }
         // ---- store the valid part of R + pend
 #pragma unroll 1
@@ -260,7 +281,9 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
                 }
             }
         }
+        if (warp == 0) MG_TR(20);
     }
+#undef MG_TR
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 512);
@@ -268,25 +291,26 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
 
 template <class Cfg>
 static int launch_resblock(const float *x, float *y, const float *packed, int stage, int B, int L, int *status,
-                           cudaStream_t s) {
+                           long long *trace, cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
         MG_CUDA_TRY(cudaFuncSetAttribute(resblock_tc_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         configured = true;
     }
     dim3 grid((L + Cfg::PVALID - 1) / Cfg::PVALID, B);
-    resblock_tc_kernel<Cfg><<<grid, Cfg::NT, Cfg::SMEM_BYTES, s>>>(x, y, packed, stage, L, status);
+    resblock_tc_kernel<Cfg><<<grid, Cfg::NT, Cfg::SMEM_BYTES, s>>>(x, y, packed, stage, L, status, trace);
     MG_CUDA_TRY(cudaGetLastError());
     return MG_OK;
 }
 
 // x, y: [B][C][L] fp32 NCL with C = 256 >> stage; status: device int, set non-zero if a pipeline wait timed out.
-int launch_resblock_tc(const float *x, float *y, const float *packed, int stage, int B, int L, int *status, cudaStream_t s) {
+int launch_resblock_tc(const float *x, float *y, const float *packed, int stage, int B, int L, int *status, cudaStream_t s,
+                       long long *trace) {
     switch (stage) {
-        case 0: return launch_resblock<RbCfg<256>>(x, y, packed, stage, B, L, status, s);
-        case 1: return launch_resblock<RbCfg<128>>(x, y, packed, stage, B, L, status, s);
-        case 2: return launch_resblock<RbCfg<64>>(x, y, packed, stage, B, L, status, s);
-        case 3: return launch_resblock<RbCfg<32>>(x, y, packed, stage, B, L, status, s);
+        case 0: return launch_resblock<RbCfg<256>>(x, y, packed, stage, B, L, status, trace, s);
+        case 1: return launch_resblock<RbCfg<128>>(x, y, packed, stage, B, L, status, trace, s);
+        case 2: return launch_resblock<RbCfg<64>>(x, y, packed, stage, B, L, status, trace, s);
+        case 3: return launch_resblock<RbCfg<32>>(x, y, packed, stage, B, L, status, trace, s);
     }
     return set_error(MG_ERR_INVALID_ARGUMENT, "launch_resblock_tc: stage %d", stage);
 }

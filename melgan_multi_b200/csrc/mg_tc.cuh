@@ -89,6 +89,24 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// One lane of a fully converged warp.  Issue loops run warp-uniform (all 32 lanes compute the descriptors, so they
+// live in uniform registers) and only the tcgen05 instruction itself sits under this predicate; issuing from inside
+// an `if (lane == 0)` region makes ptxas emit a per-MMA R2UR/ELECT "waterfall" loop (~70 cycles per instruction).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+// descriptor = constant high part (LBO, SBO, version) | 14-bit start-address field
+__device__ __forceinline__ uint64_t desc_template(uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ uint64_t desc_at(uint64_t tmpl, uint32_t saddr) { return tmpl | (uint64_t)((saddr >> 4) & 0x3FFF); }
+
 // D[tmem] (+)= A[smem] * B[smem]; one thread issues.
 __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
     asm volatile(

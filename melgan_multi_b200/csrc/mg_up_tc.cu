@@ -42,7 +42,10 @@ struct UpCfg {
     static constexpr int NCHUNK = CIN / 16;
     static constexpr int NWG = NB >= 2 ? 2 : 1;
     static constexpr int NCONV = 128 * NWG;               // converter / epilogue threads
-    static constexpr int NT = NCONV + 64;
+    static constexpr int NIW = 4;                         // MMA issuer warps
+    static constexpr bool BY_PHASE = (NB == 1);           // issuers split the S phases (NB == 1) or the NB row blocks
+    static constexpr int NT = NCONV + 32 + 32 * NIW;
+    static_assert(BY_PHASE ? (S % NIW == 0) : (NB % NIW == 0), "issuer split");
     static constexpr int SMEM_BYTES = NSA * ASLOT + NSB * BSLOT + (2 * NSA + 2 * NSB + 1) * 8 + 16;
     static_assert(COLS <= 512, "TMEM columns");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
@@ -54,7 +57,7 @@ convt_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const float 
                 int *__restrict__ status) {
     constexpr int CIN = Cfg::CIN, COUT = Cfg::COUT, S = Cfg::S, PAD = Cfg::PAD, NG = Cfg::NG, NB = Cfg::NB;
     constexpr int ROWS = Cfg::ROWS, APITCH = Cfg::APITCH, ASLOT = Cfg::ASLOT, BSLOT = Cfg::BSLOT;
-    constexpr int NSA = Cfg::NSA, NSB = Cfg::NSB, NCHUNK = Cfg::NCHUNK, NCONV = Cfg::NCONV, NWG = Cfg::NWG;
+    constexpr int NSA = Cfg::NSA, NSB = Cfg::NSB, NCHUNK = Cfg::NCHUNK, NCONV = Cfg::NCONV, NWG = Cfg::NWG, NIW = Cfg::NIW;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *aring = smem, *bring = smem + NSA * ASLOT;
     uint64_t *fullA = reinterpret_cast<uint64_t *>(bring + NSB * BSLOT);
@@ -68,9 +71,9 @@ convt_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const float 
 
     if (warp == 0) tmem_alloc(tmem_slot, Cfg::TCOLS);
     if (tid == 32) {
-        for (int s = 0; s < NSA; ++s) { mbar_init(&fullA[s], NCONV); mbar_init(&emptyA[s], 1); }
-        for (int s = 0; s < NSB; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
-        mbar_init(done, 1);
+        for (int s = 0; s < NSA; ++s) { mbar_init(&fullA[s], NCONV); mbar_init(&emptyA[s], Cfg::NIW); }
+        for (int s = 0; s < NSB; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], Cfg::BY_PHASE ? 1 : Cfg::NIW); }
+        mbar_init(done, Cfg::NIW);
         fence_mbar_init();
     }
     tc_fence_before();
@@ -93,42 +96,48 @@ convt_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const float 
             }
             if (!ok) atomicExch(status, 12);
         }
-    } else if (warp == NCONV / 32 + 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(128, NG);
-            int sa = 0, pha = 0, sb = 0, phb = 0;
-            bool ok = true;
-            for (int ch = 0; ch < NCHUNK && ok; ++ch) {
-                if (!mbar_wait(&fullA[sa], pha)) { ok = false; break; }
+    } else if (warp > NCONV / 32) {
+        // ================= MMA issuers (NIW warps; each runs the loop warp-uniform, one elected lane issues) ==========
+        // A single issuing thread sustains about one tcgen05.mma per 50 cycles, slower than these N <= 64 MMAs execute,
+        // so the accumulators are split across issuers: by 128-row block when NB > 1, else by output phase.
+        const int iw = warp - (NCONV / 32 + 1);
+        const uint32_t idesc = make_idesc_bf16(128, NG);
+        const uint64_t adesc_t = desc_template(APITCH, 128), bdesc_t = desc_template(NG * 16, 128);
+        const uint32_t aring_addr = smem_u32(aring), bring_addr = smem_u32(bring);
+        int sa = 0, pha = 0;
+        bool ok = true;  // a timed-out wait only raises the status word: control flow stays uniform
+#pragma unroll 1
+        for (int ch = 0; ch < NCHUNK; ++ch) {
+            ok &= mbar_wait(&fullA[sa], pha);
+            tc_fence_after();
+            const uint64_t abase = desc_at(adesc_t, aring_addr + sa * ASLOT);
+#pragma unroll 1
+            for (int phi = (Cfg::BY_PHASE ? iw : 0); phi < S; phi += (Cfg::BY_PHASE ? NIW : 1)) {
+                const int n = ch * S + phi, sb = n % NSB, phb = (n / NSB) & 1;
+                ok &= mbar_wait(&fullB[sb], phb);
                 tc_fence_after();
-                const uint32_t abase = smem_u32(aring + sa * ASLOT);
-                for (int phi = 0; phi < S && ok; ++phi) {
-                    if (!mbar_wait(&fullB[sb], phb)) { ok = false; break; }
-                    tc_fence_after();
-                    const uint32_t bbase = smem_u32(bring + sb * BSLOT);
+                const uint64_t bbase = desc_at(bdesc_t, bring_addr + sb * BSLOT);
 #pragma unroll
-                    for (int tap = 0; tap < 2; ++tap)
+                for (int tap = 0; tap < 2; ++tap)
 #pragma unroll
-                        for (int pass = 0; pass < 3; ++pass) {
-                            const int ahalf = (pass == 1), bhalf = (pass == 2);
-                            const uint64_t bdesc = make_desc(bbase + ((tap * 2 + bhalf) * 2) * NG * 16, NG * 16, 128);
+                    for (int pass = 0; pass < 3; ++pass) {
+                        const int ahalf = (pass == 1), bhalf = (pass == 2);
+                        const uint64_t bdesc = bbase + (uint64_t)((((tap * 2 + bhalf) * 2) * NG * 16) >> 4);
 #pragma unroll
-                            for (int blk = 0; blk < NB; ++blk) {
-                                const uint32_t a_addr = abase + ahalf * 2 * APITCH + (blk * 128 + 1 - tap) * 16;
-                                mma_bf16(tmem + (blk * S + phi) * NG, make_desc(a_addr, APITCH, 128), bdesc, idesc,
-                                         !(ch == 0 && tap == 0 && pass == 0));
-                            }
+                        for (int bi = 0; bi < (Cfg::BY_PHASE ? NB : NB / NIW); ++bi) {
+                            const int blk = Cfg::BY_PHASE ? bi : iw + bi * NIW;
+                            const uint64_t adesc = abase + (uint64_t)((ahalf * 2 * APITCH + (1 - tap) * 16) >> 4) + (uint64_t)(blk * 128);
+                            const bool acc = !(ch == 0 && tap == 0 && pass == 0);
+                            if (elect_one()) mma_bf16(tmem + (blk * S + phi) * NG, adesc, bdesc, idesc, acc);
                         }
-                    mma_commit(&emptyB[sb]);
-                    if (++sb == NSB) { sb = 0; phb ^= 1; }
-                }
-                mma_commit(&emptyA[sa]);
-                if (++sa == NSA) { sa = 0; pha ^= 1; }
+                    }
+                if (elect_one()) mma_commit(&emptyB[sb]);
             }
-            mma_commit(done);
-            if (!ok) atomicExch(status, 13);
+            if (elect_one()) mma_commit(&emptyA[sa]);
+            if (++sa == NSA) { sa = 0; pha ^= 1; }
         }
+        if (elect_one()) mma_commit(done);
+        if (!ok && lane == 0) atomicExch(status, 13);
     } else {
         // ================= converter warps: A chunks = split(lrelu(x)) =================
         int sa = 0, pha = 0;

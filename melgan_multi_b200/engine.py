@@ -156,7 +156,7 @@ class GeneratorDevice:
             stream = torch.cuda.current_stream().cuda_stream
             check(lib().mg_gen_forward_timed(self.packed.data_ptr(), mel.data_ptr(), out.data_ptr(), B, T,
                                              ws.data_ptr(), ws.numel() * 4, stream, ms))
-        return list(ms)
+        return [(lib().mg_gen_kernel_name(i).decode(), ms[i]) for i in range(n)]
 
     def check_status(self, B, T):
         """Synchronises and raises if the tensor-core pipeline of the last forward timed out."""
