@@ -92,7 +92,7 @@ MG_HD constexpr size_t tc_res_offset(int l) {  // bytes from the start of the TC
 // out[t] = sum_ci x[s]*W[ci][co][phi] + x[s-1]*W[ci][co][phi+S], phi = (t+pad) mod S: per output phase a
 // 2-tap conv on the INPUT positions.  One ring slot = (co-group, 16-channel K chunk, phase):
 //   [cg][chunk = ci/16][phi][tap][half: hi, lo][k-panel = (ci%16)/8][co % NG][ci % 8]   (bf16), 128*NG bytes per slot
-MG_HD constexpr int up_ng(int stage) { return (stage == 1 || stage == 2) ? 64 : 32; }  // output channels per CTA
+MG_HD constexpr int up_ng(int stage) { return stage == 2 ? 64 : 32; }  // output channels per CTA
 MG_HD constexpr int up_slot_bytes(int stage) { return 128 * up_ng(stage); }
 MG_HD constexpr size_t up_tc_bytes(int stage) {  // = Cin*Cout*K*4 (hi + lo)
     return (size_t)stage_cin(stage) * stage_cout(stage) * stage_kup(stage) * 4;

@@ -26,10 +26,14 @@
 namespace mg {
 using namespace tc;
 
-template <int C_>
+// C channels; NBLK 128-position blocks per CTA (a block needs 2C of the 512 TMEM columns); NSTAGE weight-ring slots;
+// NWG epilogue warpgroups; MINB CTAs per SM.  With MINB = 2 (C <= 64: the per-CTA weight stream is small) one CTA's
+// epilogue / tile load / store overlaps the other CTA's MMAs; C >= 128 needs the whole SM's shared memory for one tile.
+template <int C_, int NBLK_, int NSTAGE_, int NWG_, int MINB_>
 struct RbCfg {
     static constexpr int C = C_;
-    static constexpr int NBLK = 256 / C;  // 128-position blocks per CTA: TMEM has 512 columns, a block needs 2C
+    static constexpr int NBLK = NBLK_, MINB = MINB_;
+    static constexpr int TCOLS = NBLK * 2 * C;  // TMEM columns (power of two: 256 or 512)
     static constexpr int P = 128 * NBLK;
     static constexpr int SLACK = 16;      // zero rows either side of X (dilation-9 taps reach 9 rows out)
     static constexpr int HALO = 16;       // 1+1+3+1+9+1
@@ -43,17 +47,18 @@ struct RbCfg {
     static constexpr int HALF = CHUNK / 2;
     static constexpr int NCHUNK = tc_chunks_per_conv(C);
     static constexpr int KSL = C / KC;
-    static constexpr int NSTAGE = 4;
-    // epilogue work split: 4 warpgroups; an item = (128-position block, CW-column part of its C columns)
-    static constexpr int NWG = 4;
-    static constexpr int PARTS = NBLK >= 4 ? 1 : 4 / NBLK;
+    static constexpr int NSTAGE = NSTAGE_;
+    // epilogue work split: NWG warpgroups; an item = (128-position block, CW-column part of its C columns)
+    static constexpr int NWG = NWG_;
+    static constexpr int PARTS = NBLK >= NWG ? 1 : NWG / NBLK;
     static constexpr int CW = C / PARTS;
     static constexpr int ITEMS = NBLK * PARTS;
     static constexpr int NEPI = 128 * NWG;
-    static constexpr int NIW = NBLK >= 4 ? 4 : NBLK;  // MMA issuer warps
+    static constexpr int NIW = NBLK >= 2 ? 2 : 1;  // MMA issuer warps (the MMAs are smem-bandwidth bound, not issue bound)
     static constexpr int NT = NEPI + 32 + 32 * NIW;
     static constexpr int SMEM_BYTES = 2 * XBYTES + NSTAGE * CHUNK + 2 * C * 4 + (2 * NSTAGE + 1) * 8 + 16;
-    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+    static_assert(MINB * (SMEM_BYTES + 1024) <= 228 * 1024, "shared memory budget");
+    static_assert(MINB * TCOLS <= 512 && (TCOLS == 256 || TCOLS == 512), "TMEM budget");
     static_assert(XPITCH / 16 < 16384, "LBO field");
     static_assert(CW % 32 == 0 && ITEMS % NWG == 0, "epilogue split");
 };
@@ -76,7 +81,7 @@ __device__ __forceinline__ void store_x16(uint8_t *Xh, uint8_t *Xl, int xpitch, 
 }
 
 template <class Cfg>
-__global__ void __launch_bounds__(Cfg::NT, 1)
+__global__ void __launch_bounds__(Cfg::NT, Cfg::MINB)
 resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const float *__restrict__ packed, int stage, int L,
                    int *__restrict__ status, long long *__restrict__ trace) {
     constexpr int C = Cfg::C, NBLK = Cfg::NBLK, P = Cfg::P, SLACK = Cfg::SLACK, HALO = Cfg::HALO;
@@ -98,7 +103,7 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
     const int l0 = 5 + 6 * stage;
     const uint8_t *tc_base = reinterpret_cast<const uint8_t *>(packed) + tc_region_start();
 
-    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    if (warp == 0) tmem_alloc(tmem_slot, Cfg::TCOLS);
     if (tid == 32) {
         for (int s = 0; s < NSTAGE; ++s) {
             mbar_init(&full[s], 1);
@@ -286,7 +291,7 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
 #undef MG_TR
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 512);
+    if (warp == 0) tmem_dealloc(tmem, Cfg::TCOLS);
 }
 
 template <class Cfg>
@@ -307,10 +312,11 @@ static int launch_resblock(const float *x, float *y, const float *packed, int st
 int launch_resblock_tc(const float *x, float *y, const float *packed, int stage, int B, int L, int *status, cudaStream_t s,
                        long long *trace) {
     switch (stage) {
-        case 0: return launch_resblock<RbCfg<256>>(x, y, packed, stage, B, L, status, trace, s);
-        case 1: return launch_resblock<RbCfg<128>>(x, y, packed, stage, B, L, status, trace, s);
-        case 2: return launch_resblock<RbCfg<64>>(x, y, packed, stage, B, L, status, trace, s);
-        case 3: return launch_resblock<RbCfg<32>>(x, y, packed, stage, B, L, status, trace, s);
+        //                                       C  NBLK NSTAGE NWG MINB
+        case 0: return launch_resblock<RbCfg<256, 1, 4, 4, 1>>(x, y, packed, stage, B, L, status, trace, s);
+        case 1: return launch_resblock<RbCfg<128, 2, 4, 4, 1>>(x, y, packed, stage, B, L, status, trace, s);
+        case 2: return launch_resblock<RbCfg<64, 2, 2, 2, 2>>(x, y, packed, stage, B, L, status, trace, s);
+        case 3: return launch_resblock<RbCfg<32, 4, 4, 2, 2>>(x, y, packed, stage, B, L, status, trace, s);
     }
     return set_error(MG_ERR_INVALID_ARGUMENT, "launch_resblock_tc: stage %d", stage);
 }

@@ -30,29 +30,30 @@ struct UpCfg {
     static constexpr int CIN = stage_cin(STAGE), COUT = stage_cout(STAGE), S = stage_stride(STAGE), PAD = stage_pad(STAGE);
     static constexpr int NG = up_ng(STAGE);
     static constexpr int NCG = COUT / NG;
-    static constexpr int NB = (S == 8) ? 1 : 4;          // 128-row blocks per CTA
+    static constexpr int NB = (S == 8) ? 1 : 2;          // 128-row blocks per CTA
     static constexpr int COLS = NB * S * NG;              // TMEM columns in use
-    static constexpr int TCOLS = COLS <= 256 ? 256 : 512;
+    static constexpr int TCOLS = COLS <= 128 ? 128 : COLS <= 256 ? 256 : 512;
+    static constexpr int MINB = 2;                        // CTAs per SM: one CTA's loads / stores hide under the other's MMAs
     static constexpr int ROWS = 128 * NB;
     static constexpr int AROWS = ROWS + 8;                // row index i <-> input position r0 - 1 + i, i in [0, ROWS]
     static constexpr int APITCH = AROWS * 16;             // bytes between the two k-panels of a chunk
     static constexpr int ASLOT = 4 * APITCH;              // [half: hi, lo][k-panel: 2][AROWS][16 B]
     static constexpr int BSLOT = up_slot_bytes(STAGE);    // [tap][half][k-panel][NG][16 B]
-    static constexpr int NSA = 3, NSB = 8;
+    static constexpr int NSA = 3, NSB = (S == 8) ? 8 : 4;
     static constexpr int NCHUNK = CIN / 16;
     static constexpr int NWG = NB >= 2 ? 2 : 1;
     static constexpr int NCONV = 128 * NWG;               // converter / epilogue threads
-    static constexpr int NIW = 4;                         // MMA issuer warps
     static constexpr bool BY_PHASE = (NB == 1);           // issuers split the S phases (NB == 1) or the NB row blocks
+    static constexpr int NIW = BY_PHASE ? 4 : NB;         // MMA issuer warps
     static constexpr int NT = NCONV + 32 + 32 * NIW;
     static_assert(BY_PHASE ? (S % NIW == 0) : (NB % NIW == 0), "issuer split");
     static constexpr int SMEM_BYTES = NSA * ASLOT + NSB * BSLOT + (2 * NSA + 2 * NSB + 1) * 8 + 16;
-    static_assert(COLS <= 512, "TMEM columns");
-    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+    static_assert(MINB * TCOLS <= 512, "TMEM columns");
+    static_assert(MINB * (SMEM_BYTES + 1024) <= 228 * 1024, "shared memory budget");
 };
 
 template <class Cfg>
-__global__ void __launch_bounds__(Cfg::NT, 1)
+__global__ void __launch_bounds__(Cfg::NT, Cfg::MINB)
 convt_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const float *__restrict__ packed, int Lin, int B,
                 int *__restrict__ status) {
     constexpr int CIN = Cfg::CIN, COUT = Cfg::COUT, S = Cfg::S, PAD = Cfg::PAD, NG = Cfg::NG, NB = Cfg::NB;
