@@ -263,8 +263,9 @@ def main():
         flops_of["res%d" % i] = res_f[i]
         flops_of["stage%d(up+res)" % i] = up_f[i] + res_f[i]
     flops_of["stage3(up+res+post)"] = up_f[3] + res_f[3] + post_f * frames
+    flops_of["res3+post"] = res_f[3] + post_f * frames
     k_flops = [flops_of[n] for n in names]
-    tc_path = os.environ.get("MG_GEN_PATH") == "tc"
+    tc_path = os.environ.get("MG_GEN_PATH", "tc") != "simt"
     dom = names.index("res1") if tc_path else names.index("stage1(up+res)")
     dom_tflops = k_flops[dom] / (kms[dom] * 1e-3) / 1e12
     fwd_flops = sum(k_flops)

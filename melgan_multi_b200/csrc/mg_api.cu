@@ -19,10 +19,11 @@ int set_error(int code, const char *fmt, ...) {
     return code;
 }
 
-// Development switch between the two generator pipelines: MG_GEN_PATH=simt (default) | tc
+// The product pipeline is the tensor-core one.  MG_GEN_PATH=simt selects the first-generation fp32 SIMT kernels, kept as
+// an independent second implementation for cross-checks (tests/test_tc_gpu.py), never as a fallback.
 static bool use_tc() {
     const char *e = getenv("MG_GEN_PATH");
-    return e && strcmp(e, "tc") == 0;
+    return !(e && strcmp(e, "simt") == 0);
 }
 
 static int *status_ptr(void *workspace, int B, int T) {
@@ -116,7 +117,7 @@ int mg_gen_forward_timed(const void *packed, const float *mel, float *audio, int
 
 const char *mg_gen_kernel_name(int i) {
     static const char *simt[] = {"conv_pre", "stage0(up+res)", "stage1(up+res)", "stage2(up+res)", "stage3(up+res+post)"};
-    static const char *tcn[] = {"conv_pre", "up0", "res0", "up1", "res1", "up2", "res2", "up3", "res3", "post"};
+    static const char *tcn[] = {"conv_pre", "up0", "res0", "up1", "res1", "up2", "res2", "up3", "res3+post"};
     if (i < 0 || i >= mg_gen_forward_launches()) return "";
     return use_tc() ? tcn[i] : simt[i];
 }

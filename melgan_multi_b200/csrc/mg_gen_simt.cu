@@ -276,26 +276,31 @@ gen_stage_kernel(const float *__restrict__ x, float *__restrict__ y, const float
     }
 }
 
-// conv_pre: Conv1d(80 -> 512, k7, pad 3) (models.py:46,62).  One thread per output channel, TT frames per CTA.
-constexpr int kPreTT = 32;
-__global__ void __launch_bounds__(512, 1)
+// conv_pre: Conv1d(80 -> 512, k7, pad 3) (models.py:46,62).  CTA = kPreTT frames x 128 output channels (one per thread);
+// 0.5% of the generator FLOPs, so plain fp32 FMAs with the mel tile broadcast from shared memory.
+constexpr int kPreTT = 16;
+constexpr int kPreCG = 128;
+__global__ void __launch_bounds__(kPreCG)
 gen_pre_kernel(const float *__restrict__ mel, float *__restrict__ y, const float *__restrict__ packed, int T) {
     constexpr int XS = kPreTT + 8;  // row stride (floats), multiple of 4
     __shared__ __align__(16) float xs[kMelBins * XS];
-    const int b = blockIdx.y, t0 = blockIdx.x * kPreTT, co = threadIdx.x;
-    for (int idx = threadIdx.x; idx < kMelBins * XS; idx += 512) {
+    const int b = blockIdx.z, t0 = blockIdx.x * kPreTT, co = blockIdx.y * kPreCG + threadIdx.x;
+    for (int idx = threadIdx.x; idx < kMelBins * XS; idx += kPreCG) {
         const int ci = idx / XS, i = idx - ci * XS;
         const int t = t0 + i - 3;
         xs[idx] = (i < kPreTT + 6 && t >= 0 && t < T) ? mel[((size_t)b * kMelBins + ci) * T + t] : 0.f;
     }
     __syncthreads();
-    const float *__restrict__ wg = packed + weight_offset(0);
+    const float *__restrict__ wg = packed + weight_offset(0) + co;
     float acc[kPreTT];
     const float bias = packed[bias_offset(0) + co];
 #pragma unroll
     for (int t = 0; t < kPreTT; ++t) acc[t] = bias;
-#pragma unroll 1
+#pragma unroll 2
     for (int ci = 0; ci < kMelBins; ++ci) {
+        float w[kPreK];
+#pragma unroll
+        for (int k = 0; k < kPreK; ++k) w[k] = __ldg(wg + (size_t)(ci * kPreK + k) * kPreCout);
         float xr[XS];
 #pragma unroll
         for (int q = 0; q < XS / 4; ++q) {
@@ -303,11 +308,9 @@ gen_pre_kernel(const float *__restrict__ mel, float *__restrict__ y, const float
             xr[4 * q] = v.x; xr[4 * q + 1] = v.y; xr[4 * q + 2] = v.z; xr[4 * q + 3] = v.w;
         }
 #pragma unroll
-        for (int k = 0; k < kPreK; ++k) {
-            const float w = wg[(size_t)(ci * kPreK + k) * kPreCout + co];
+        for (int k = 0; k < kPreK; ++k)
 #pragma unroll
-            for (int t = 0; t < kPreTT; ++t) acc[t] = fmaf(w, xr[t + k], acc[t]);
-        }
+            for (int t = 0; t < kPreTT; ++t) acc[t] = fmaf(w[k], xr[t + k], acc[t]);
     }
     float *yr = y + ((size_t)b * kPreCout + co) * T + t0;
 #pragma unroll
@@ -316,30 +319,58 @@ gen_pre_kernel(const float *__restrict__ mel, float *__restrict__ y, const float
 }
 
 // LeakyReLU -> conv_post (32->1, k7) -> tanh (models.py:67-69) as its own kernel (tensor-core pipeline).
-constexpr int kPostTile = 256;
+// CTA = kPostTile outputs, 4 consecutive outputs per thread (10 activations + 7 weights feed 28 FMAs).
+constexpr int kPostTile = 1024;
+constexpr int kPostXS = kPostTile + 8;
 __global__ void __launch_bounds__(256)
 gen_post_kernel(const float *__restrict__ x, float *__restrict__ audio, const float *__restrict__ packed, int L) {
-    __shared__ float xs[32][kPostTile + 8];
-    __shared__ float ws[32 * kPostK];
+    extern __shared__ __align__(16) float post_smem[];
+    float *xs = post_smem;                    // [32][kPostXS], xs[ci][i] = lrelu(x[t0 - 4 + i])
+    float *ws = post_smem + 32 * kPostXS;     // [32][8] (7 taps + pad)
     const int b = blockIdx.y, t0 = blockIdx.x * kPostTile;
-    for (int i = threadIdx.x; i < 32 * kPostK; i += 256) ws[i] = packed[weight_offset(29) + i];
-    for (int idx = threadIdx.x; idx < 32 * (kPostTile + 6); idx += 256) {
-        const int ci = idx / (kPostTile + 6), i = idx - ci * (kPostTile + 6);
-        const int t = t0 + i - 3;
-        xs[ci][i] = (t >= 0 && t < L) ? lrelu(x[((size_t)b * 32 + ci) * L + t]) : 0.f;
+    for (int i = threadIdx.x; i < 32 * 8; i += 256) ws[i] = (i & 7) < kPostK ? packed[weight_offset(29) + (i >> 3) * kPostK + (i & 7)] : 0.f;
+    const float *xb = x + (size_t)b * 32 * L;
+    for (int idx = threadIdx.x; idx < 32 * (kPostXS / 4); idx += 256) {
+        const int ci = idx / (kPostXS / 4), i4 = (idx - ci * (kPostXS / 4)) * 4;
+        const int t = t0 - 4 + i4;
+        float4 v;
+        if (t >= 0 && t + 3 < L && (L & 3) == 0) {
+            v = *reinterpret_cast<const float4 *>(xb + (size_t)ci * L + t);
+        } else {
+            v.x = (t >= 0 && t < L) ? xb[(size_t)ci * L + t] : 0.f;
+            v.y = (t + 1 >= 0 && t + 1 < L) ? xb[(size_t)ci * L + t + 1] : 0.f;
+            v.z = (t + 2 >= 0 && t + 2 < L) ? xb[(size_t)ci * L + t + 2] : 0.f;
+            v.w = (t + 3 >= 0 && t + 3 < L) ? xb[(size_t)ci * L + t + 3] : 0.f;
+        }
+        *reinterpret_cast<float4 *>(xs + ci * kPostXS + i4) = make_float4(lrelu(v.x), lrelu(v.y), lrelu(v.z), lrelu(v.w));
     }
     __syncthreads();
     const float bias = packed[bias_offset(29)];
-    for (int i = threadIdx.x; i < kPostTile; i += 256) {
-        if (t0 + i >= L) break;
-        float acc = bias;
+    const int i0 = threadIdx.x * 4;  // outputs t0 + i0 .. + 3 need xs[i0 + 1 .. i0 + 10]
+    float acc[4] = {bias, bias, bias, bias};
 #pragma unroll 4
-        for (int ci = 0; ci < 32; ++ci)
+    for (int ci = 0; ci < 32; ++ci) {
+        const float *r = xs + ci * kPostXS + i0;
+        const float4 a = *reinterpret_cast<const float4 *>(r), c = *reinterpret_cast<const float4 *>(r + 4),
+                     d = *reinterpret_cast<const float4 *>(r + 8);
+        const float xv[12] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
+        const float4 w0 = *reinterpret_cast<const float4 *>(ws + ci * 8), w1 = *reinterpret_cast<const float4 *>(ws + ci * 8 + 4);
+        const float wv[7] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z};
 #pragma unroll
-            for (int k = 0; k < kPostK; ++k) acc = fmaf(ws[ci * kPostK + k], xs[ci][i + k], acc);
-        audio[(size_t)b * L + t0 + i] = tanhf(acc);
+        for (int k = 0; k < kPostK; ++k)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j] = fmaf(wv[k], xv[1 + j + k], acc[j]);
+    }
+    float *ap = audio + (size_t)b * L + t0 + i0;
+    if (t0 + i0 + 3 < L && (L & 3) == 0) {
+        *reinterpret_cast<float4 *>(ap) = make_float4(tanhf(acc[0]), tanhf(acc[1]), tanhf(acc[2]), tanhf(acc[3]));
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (t0 + i0 + j < L) ap[j] = tanhf(acc[j]);
     }
 }
+constexpr int kPostSmem = (32 * kPostXS + 32 * 8) * (int)sizeof(float);
 
 //                     CIN  COUT S  PTOT WC WP WBUF  POST
 using Stage0 = StageCfg<512, 256, 8,  96, 16, 1, 4096, false>;
@@ -368,18 +399,19 @@ static int launch_stage(const float *x, float *y, const float *packed, int stage
 }
 
 int generator_simt_num_launches() { return 5; }
-int generator_tc_num_launches() { return 10; }
+int generator_tc_num_launches() { return 9; }
 
-// Tensor-core pipeline (development stage): conv_pre (SIMT) -> 4 x [ConvT (SIMT) -> ResBlock (tcgen05)] -> post (SIMT)
+// Tensor-core pipeline: conv_pre (fp32 SIMT, 0.5% of the FLOPs) -> 4 x [ConvT (tcgen05) -> ResBlock (tcgen05)], the last
+// ResBlock with LeakyReLU -> conv_post -> tanh fused into its epilogue.  (up_tc = false swaps in the SIMT ConvT kernels.)
 int launch_generator_tc(const float *packed, const float *mel, float *audio, int B, int T, float *ws, int *status, bool up_tc,
                         cudaStream_t s, cudaEvent_t *ev) {
 #define MG_MARK(i) do { if (ev) MG_CUDA_TRY(cudaEventRecord(ev[i], s)); } while (0)
     float *a0 = ws + ws_offset(0, B, T);
     float *a[4] = {ws + ws_offset(1, B, T), ws + ws_offset(2, B, T), ws + ws_offset(3, B, T), ws + ws_offset(4, B, T)};
     float *u = ws + ws_offset(5, B, T);  // ConvT output of the current stage (largest: B*8192*T floats)
-    dim3 gpre((T + kPreTT - 1) / kPreTT, B);
+    dim3 gpre((T + kPreTT - 1) / kPreTT, kPreCout / kPreCG, B);
     MG_MARK(0);
-    gen_pre_kernel<<<gpre, 512, 0, s>>>(mel, a0, packed, T);
+    gen_pre_kernel<<<gpre, kPreCG, 0, s>>>(mel, a0, packed, T);
     MG_CUDA_TRY(cudaGetLastError());
     int rc;
     MG_MARK(1);
@@ -397,13 +429,11 @@ int launch_generator_tc(const float *packed, const float *mel, float *audio, int
     MG_MARK(7);
     if ((rc = up_tc ? launch_convt_tc(a[2], u, packed, 3, B, 128 * T, status, s) : launch_stage<Up3>(a[2], u, packed, 3, B, 128 * T, s))) return rc;
     MG_MARK(8);
-    if ((rc = launch_resblock_tc(u, a[3], packed, 3, B, 256 * T, status, s))) return rc;
+    // stage 4 = ResBlock 3 with LeakyReLU -> conv_post -> tanh fused into its final epilogue: writes the audio
+    if ((rc = launch_resblock_tc(u, audio, packed, 4, B, 256 * T, status, s))) return rc;
     MG_MARK(9);
-    dim3 gpost((256 * T + kPostTile - 1) / kPostTile, B);
-    gen_post_kernel<<<gpost, 256, 0, s>>>(a[3], audio, packed, 256 * T);
-    MG_CUDA_TRY(cudaGetLastError());
-    MG_MARK(10);
 #undef MG_MARK
+    (void)a;
     return MG_OK;
 }
 
@@ -414,9 +444,9 @@ int launch_generator_simt(const float *packed, const float *mel, float *audio, i
     float *a1 = ws + ws_offset(1, B, T);  // [B,256,8T]
     float *a2 = ws + ws_offset(2, B, T);  // [B,128,64T]
     float *a3 = ws + ws_offset(3, B, T);  // [B,64,128T]
-    dim3 gpre((T + kPreTT - 1) / kPreTT, B);
+    dim3 gpre((T + kPreTT - 1) / kPreTT, kPreCout / kPreCG, B);
     MG_MARK(0);
-    gen_pre_kernel<<<gpre, 512, 0, s>>>(mel, a0, packed, T);
+    gen_pre_kernel<<<gpre, kPreCG, 0, s>>>(mel, a0, packed, T);
     MG_CUDA_TRY(cudaGetLastError());
     int rc;
     MG_MARK(1);

@@ -90,10 +90,12 @@ MG_HD constexpr size_t tc_res_offset(int l) {  // bytes from the start of the TC
 }
 // ---- tensor-core blob for the 4 ConvTranspose1d layers (after the ResBlock convs) -----------------------
 // out[t] = sum_ci x[s]*W[ci][co][phi] + x[s-1]*W[ci][co][phi+S], phi = (t+pad) mod S: per output phase a
-// 2-tap conv on the INPUT positions.  One ring slot = (co-group, 16-channel K chunk, phase):
-//   [cg][chunk = ci/16][phi][tap][half: hi, lo][k-panel = (ci%16)/8][co % NG][ci % 8]   (bf16), 128*NG bytes per slot
-MG_HD constexpr int up_ng(int stage) { return stage == 2 ? 64 : 32; }  // output channels per CTA
-MG_HD constexpr int up_slot_bytes(int stage) { return 128 * up_ng(stage); }
+// 2-tap conv on the INPUT positions.  All S phases of a tap read the SAME activation rows, so they are stacked along
+// the MMA N dimension (N = S*NG <= 256: one instruction per (tap, pass) covers every phase).  One ring slot =
+// (co-group, 16-channel K chunk):
+//   [cg][chunk = ci/16][tap][half: hi, lo][k-panel = (ci%16)/8][row = phi*NG + co%NG][ci % 8]   (bf16), 128*S*NG bytes
+MG_HD constexpr int up_ng(int stage) { return stage == 2 ? 64 : 32; }  // output channels per CTA (S*NG = 256,256,128,64)
+MG_HD constexpr int up_slot_bytes(int stage) { return 128 * stage_stride(stage) * up_ng(stage); }
 MG_HD constexpr size_t up_tc_bytes(int stage) {  // = Cin*Cout*K*4 (hi + lo)
     return (size_t)stage_cin(stage) * stage_cout(stage) * stage_kup(stage) * 4;
 }
@@ -105,8 +107,8 @@ MG_HD constexpr size_t tc_up_offset(int stage) {  // bytes from the start of the
 MG_HD constexpr size_t up_weight_index(int stage, int ci, int co, int k, int h) {  // bf16 element index in the layer's block
     const int S = stage_stride(stage), NG = up_ng(stage), CIN = stage_cin(stage);
     const int phi = k % S, tap = k / S;
-    return ((((((size_t)(co / NG) * (CIN / 16) + ci / 16) * S + phi) * 2 + tap) * 2 + h) * 2 + (ci % 16) / 8) * NG * 8 +
-           (size_t)(co % NG) * 8 + (ci % 8);
+    return (((((size_t)(co / NG) * (CIN / 16) + ci / 16) * 2 + tap) * 2 + h) * 2 + (ci % 16) / 8) * (S * NG) * 8 +
+           (size_t)(phi * NG + co % NG) * 8 + (ci % 8);
 }
 MG_HD constexpr size_t tc_region_bytes() { return tc_up_offset(4); }
 MG_HD constexpr size_t packed_total_bytes() { return ((packed_float_count() * 4 + 255) / 256) * 256 + tc_region_bytes(); }

@@ -29,14 +29,15 @@ using namespace tc;
 // C channels; NBLK 128-position blocks per CTA (a block needs 2C of the 512 TMEM columns); NSTAGE weight-ring slots;
 // NWG epilogue warpgroups; MINB CTAs per SM.  With MINB = 2 (C <= 64: the per-CTA weight stream is small) one CTA's
 // epilogue / tile load / store overlaps the other CTA's MMAs; C >= 128 needs the whole SM's shared memory for one tile.
-template <int C_, int NBLK_, int NSTAGE_, int NWG_, int MINB_>
+template <int C_, int NBLK_, int NSTAGE_, int NWG_, int MINB_, bool POST_ = false>
 struct RbCfg {
     static constexpr int C = C_;
     static constexpr int NBLK = NBLK_, MINB = MINB_;
+    static constexpr bool POST = POST_;  // fuse LeakyReLU -> conv_post -> tanh into the final epilogue (last stage)
     static constexpr int TCOLS = NBLK * 2 * C;  // TMEM columns (power of two: 256 or 512)
     static constexpr int P = 128 * NBLK;
     static constexpr int SLACK = 16;      // zero rows either side of X (dilation-9 taps reach 9 rows out)
-    static constexpr int HALO = 16;       // 1+1+3+1+9+1
+    static constexpr int HALO = 16 + (POST ? 3 : 0);  // 1+1+3+1+9+1 (+3 for the fused k7 conv_post)
     static constexpr int PVALID = P - 2 * HALO;
     static constexpr int ROWS = P + 2 * SLACK;
     static constexpr int XPITCH = ROWS * 16;  // bytes between k-panels
@@ -268,6 +269,50 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
             }
             if (warp == 0) MG_TR(4 + 3 * conv);
         }
+        if constexpr (Cfg::POST) {
+            // ---- fused LeakyReLU -> conv_post (32 -> 1, k7, pad 3) -> tanh (models.py:67-69); y is audio [B][1][L].
+            // Each position turns its 32 channels into the 7 per-tap partial sums q_k[p] = sum_ci w[ci][k] * lrelu(x[ci][p]),
+            // parks them in shared memory (the X buffer is dead now), then audio[p] = tanh(b + sum_k q_k[p + k - 3]).
+            static_assert(!Cfg::POST || (C == 32 && PARTS == 1), "conv_post fusion is for the 32-channel stage");
+            float *Q = reinterpret_cast<float *>(Xh);      // [7][P]
+            float *wpost = reinterpret_cast<float *>(Xl);  // [32][8]
+            for (int i = tid; i < 32 * 8; i += NEPI)
+                wpost[i] = (i & 7) < kPostK ? __ldg(packed + weight_offset(29) + (i >> 3) * kPostK + (i & 7)) : 0.f;
+            named_bar_sync(2, NEPI);
+#pragma unroll 1
+            for (int it = wg; it < ITEMS; it += NWG) {
+                const int p = it * 128 + row, t = o + p;
+                const bool inr = (t >= 0 && t < L);
+                uint32_t v[32];
+                tmem_ld32(lane_addr + it * 2 * C, v);
+                tmem_ld_wait();
+                float q[kPostK];
+#pragma unroll
+                for (int k = 0; k < kPostK; ++k) q[k] = 0.f;
+#pragma unroll
+                for (int ci = 0; ci < 32; ++ci) {
+                    const float a = inr ? lrelu(__uint_as_float(v[ci]) + pend[ci]) : 0.f;
+                    const float4 w0 = *reinterpret_cast<const float4 *>(wpost + ci * 8);
+                    const float4 w1 = *reinterpret_cast<const float4 *>(wpost + ci * 8 + 4);
+                    q[0] = fmaf(w0.x, a, q[0]); q[1] = fmaf(w0.y, a, q[1]); q[2] = fmaf(w0.z, a, q[2]); q[3] = fmaf(w0.w, a, q[3]);
+                    q[4] = fmaf(w1.x, a, q[4]); q[5] = fmaf(w1.y, a, q[5]); q[6] = fmaf(w1.z, a, q[6]);
+                }
+#pragma unroll
+                for (int k = 0; k < kPostK; ++k) Q[k * P + p] = q[k];
+            }
+            named_bar_sync(2, NEPI);
+            const float bpost = __ldg(packed + bias_offset(29));
+#pragma unroll 1
+            for (int it = wg; it < ITEMS; it += NWG) {
+                const int p = it * 128 + row, t = o + p;
+                if (p >= HALO && p < P - HALO && t < L) {
+                    float acc = bpost;
+#pragma unroll
+                    for (int k = 0; k < kPostK; ++k) acc += Q[k * P + p + k - 3];
+                    y[(size_t)b * L + t] = tanhf(acc);
+                }
+            }
+        } else {
         // ---- store the valid part of R + pend
 #pragma unroll 1
         for (int it = wg; it < ITEMS; it += NWG) {
@@ -285,6 +330,7 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
                     for (int j = 0; j < 32; ++j) yp[(size_t)(c0 + j) * L] = __uint_as_float(v[j]) + pend[c0 + j];
                 }
             }
+        }
         }
         if (warp == 0) MG_TR(20);
     }
@@ -317,6 +363,8 @@ int launch_resblock_tc(const float *x, float *y, const float *packed, int stage,
         case 1: return launch_resblock<RbCfg<128, 2, 4, 4, 1>>(x, y, packed, stage, B, L, status, trace, s);
         case 2: return launch_resblock<RbCfg<64, 2, 2, 2, 2>>(x, y, packed, stage, B, L, status, trace, s);
         case 3: return launch_resblock<RbCfg<32, 4, 4, 2, 2>>(x, y, packed, stage, B, L, status, trace, s);
+        // stage 4 = ResBlock 3 with LeakyReLU -> conv_post -> tanh fused: y is the audio [B][1][L]
+        case 4: return launch_resblock<RbCfg<32, 4, 4, 2, 2, true>>(x, y, packed, 3, B, L, status, trace, s);
     }
     return set_error(MG_ERR_INVALID_ARGUMENT, "launch_resblock_tc: stage %d", stage);
 }

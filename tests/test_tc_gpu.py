@@ -36,7 +36,7 @@ def tc_path():
     os.environ["MG_GEN_PATH"] = "tc"
     yield
     if old is None:
-        del os.environ["MG_GEN_PATH"]
+        os.environ.pop("MG_GEN_PATH", None)
     else:
         os.environ["MG_GEN_PATH"] = old
 
