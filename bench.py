@@ -62,27 +62,72 @@ def load_peaks():
 
 
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and clock-event (throttle) reasons of one GPU WHILE the timed region runs: an in-process NVML
+    poller thread (2 ms period; the main thread sits in ctypes/CUDA calls that release the GIL).  nvidia-smi -lms is the
+    fallback, but its ~1 s start-up and >=100 ms period see at most one sample of a 25 ms timed region."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        import threading
+        self.samples, self.mask, self.max_mhz, self._stop = [], 0, None, False
+        self.smi = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
-                                      stderr=subprocess.DEVNULL)
-        except OSError:
-            self.p = None
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES if it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis and all(v.strip().isdigit() for v in vis.split(",")) and index < len(vis.split(",")):
+                phys = int(vis.split(",")[index])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+
+            def poll():
+                while not self._stop:
+                    try:
+                        self.samples.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                        self.mask |= int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+            self.t = threading.Thread(target=poll, daemon=True)
+            self.t.start()
+        except Exception:
+            self.nv = None
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_power_cap")
+            try:
+                self.smi = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + q,
+                                             "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                            stderr=subprocess.DEVNULL)
+            except OSError:
+                self.smi = None
+
+    def mark(self):
+        """Call right before the timed region: only later samples count."""
+        self.samples, self.mask = [], 0
 
     def stop(self):
-        if self.p is None:
+        if self.nv is not None:
+            self._stop = True
+            self.t.join(timeout=1)
+            if not self.samples:
+                return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples"], "source": "nvml"}
+            hi = [c for c in self.samples if c >= 0.5 * max(self.samples)]
+            return {"sm_mhz": statistics.median(hi), "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(n for bit, n in self.REASONS.items() if self.mask & bit),
+                    "samples": len(self.samples), "source": "nvml poll, 2 ms"}
+        if self.smi is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.p.terminate()
+        self.smi.terminate()
         try:
-            self.p.wait(timeout=5)
+            self.smi.wait(timeout=5)
         except Exception:
-            self.p.kill()
+            self.smi.kill()
         self.f.flush()
         rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
         os.unlink(self.f.name)
@@ -99,11 +144,10 @@ class ClockSampler:
                 if v.strip() == "Active":
                     reasons.add(n)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        # "under load": samples in the upper half of the observed range
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"], "source": "nvidia-smi"}
         hi = [c for c in sm if c >= 0.5 * max(sm)]
         return {"sm_mhz": statistics.median(hi), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 def usable_cpus():
@@ -154,7 +198,7 @@ def run_reference(args):
     sample_B = 16
     ws, bs = torch_port.fold_state(synth.generator_state(1234))
     x = torch.from_numpy(synth.mel_input(sample_B, T_FRAMES, 0))
-    for _ in range(max(1, min(args.warmup, 3))):
+    for _ in range(max(5, args.warmup)):  # oneDNN primitive creation + thread-pool spin-up take several calls
         torch_port.generator_forward(ws, bs, x)
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -231,6 +275,7 @@ def main():
         gd.forward(mels[i % 4], out)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     barrier()
+    sampler.mark()
     for k in range(K):
         flush.zero_()
         ev[k][0].record()

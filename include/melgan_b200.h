@@ -108,6 +108,26 @@ int mg_gen_resblock_trace(const void *packed, int stage, const float *x, float *
 int mg_gen_stage_output(const void *workspace, int which, float *out, int B, int T, void *stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Multi-scale discriminator forward.   Replaces: models.MultiScaleDiscriminator.forward (models.py:119-135) and
+ * Discriminator.forward (models.py:87-103) for a batch in which the caller has stacked real and generated audio
+ * (Bt = 2B: every weight is streamed once for both; the reference calls d(y) and d(y_hat) separately), with the
+ * AvgPool1d chain (models.py:114-117) fused into each scale's first conv and the 21 weight-norm folds done by one
+ * mg_msd_pack launch.
+ *
+ * v, g, bias: HOST arrays of 21 DEVICE pointers, discriminator-major, layers in reference registration order
+ *   (conv_pre, grouped_convs.0-3, conv_post1, conv_post2).
+ * y [Bt, 1, L] device fp32.  fmaps: HOST array of 21 DEVICE pointers (scale-major, 7 per scale) receiving the feature
+ *   maps [Bt, C_l, len] with len = lens[scale*7 + l] from mg_msd_lengths(L, lens); the first six of a scale are
+ *   post-LeakyReLU, the seventh is conv_post2's raw output, i.e. the flattened logits [Bt, len].
+ * status_word: >= 4 bytes of device memory; check it with mg_msd_check_status after the call (bounded waits).
+ */
+size_t mg_msd_packed_bytes(void);
+int mg_msd_pack(const float *const *v, const float *const *g, const float *const *bias, void *packed, void *stream);
+int mg_msd_lengths(int L, int *lens);
+int mg_msd_forward(const void *packed, const float *y, int Bt, int L, float *const *fmaps, void *status_word, void *stream);
+int mg_msd_check_status(const void *status_word, void *stream);
+
+/* ---------------------------------------------------------------------------------------
  * Host-buffer engine.   The call a non-PyTorch host makes: owns its device buffers, takes and
  * returns HOST memory, and performs the host<->device copies itself (this is the path
  * bench.py times as "e2e").  One engine per host thread / CUDA stream.

@@ -204,6 +204,45 @@ int mg_gen_resblock(const void *packed, int stage, const float *x, float *y, int
     return rc;
 }
 
+/* ------------------------------- multi-scale discriminator ------------------------------- */
+
+size_t mg_msd_packed_bytes(void) { return msd_packed_bytes(); }
+
+int mg_msd_pack(const float *const *v, const float *const *g, const float *const *bias, void *packed, void *stream) {
+    if (!v || !g || !bias || !packed) return set_error(MG_ERR_INVALID_ARGUMENT, "mg_msd_pack: null argument");
+    if ((uintptr_t)packed % 256) return set_error(MG_ERR_INVALID_ARGUMENT, "mg_msd_pack: packed must be 256-byte aligned");
+    return launch_disc_pack(v, g, bias, packed, (cudaStream_t)stream);
+}
+
+int mg_msd_lengths(int L, int *lens) {
+    if (L < 1 || !lens) return set_error(MG_ERR_INVALID_ARGUMENT, "mg_msd_lengths: bad argument");
+    msd_lengths(L, lens);
+    for (int i = 0; i < 21; ++i)
+        if (lens[i] < 1) return set_error(MG_ERR_INVALID_ARGUMENT, "mg_msd_lengths: L = %d is too short for the discriminators", L);
+    return MG_OK;
+}
+
+int mg_msd_forward(const void *packed, const float *y, int Bt, int L, float *const *fmaps, void *status_word, void *stream) {
+    if (!packed || !y || !fmaps || !status_word || Bt < 1 || L < 1)
+        return set_error(MG_ERR_INVALID_ARGUMENT, "mg_msd_forward: bad argument");
+    int lens[21];
+    int rc = mg_msd_lengths(L, lens);
+    if (rc) return rc;
+    for (int i = 0; i < 21; ++i)
+        if (!fmaps[i]) return set_error(MG_ERR_INVALID_ARGUMENT, "mg_msd_forward: null feature-map pointer %d", i);
+    MG_CUDA_TRY(cudaMemsetAsync(status_word, 0, sizeof(int), (cudaStream_t)stream));
+    return launch_msd_forward(packed, y, Bt, L, fmaps, (int *)status_word, (cudaStream_t)stream);
+}
+
+int mg_msd_check_status(const void *status_word, void *stream) {
+    if (!status_word) return set_error(MG_ERR_INVALID_ARGUMENT, "mg_msd_check_status: null argument");
+    MG_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    int st = 0;
+    MG_CUDA_TRY(cudaMemcpy(&st, status_word, sizeof(int), cudaMemcpyDeviceToHost));
+    if (st) return set_error(MG_ERR_CUDA, "tensor-core pipeline wait timed out (role code %d)", st);
+    return MG_OK;
+}
+
 /* ------------------------------- host-buffer engine ------------------------------------- */
 
 struct mg_gen_engine {

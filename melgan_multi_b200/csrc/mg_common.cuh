@@ -44,6 +44,12 @@ int generator_simt_num_launches();
 int generator_tc_num_launches();
 int launch_generator_tc(const float *packed, const float *mel, float *audio, int B, int T, float *ws, int *status, bool up_tc,
                         cudaStream_t s, cudaEvent_t *ev = nullptr);
+int launch_gen_pre_tc(const float *mel, float *y, const float *packed, int B, int T, int *status, cudaStream_t s);
+int launch_disc_post1_tc(const float *x, float *y, const uint8_t *wtc, const float *bias, int Bt, int L, int *status,
+                         cudaStream_t s);
+int launch_disc_pack(const float *const *v, const float *const *g, const float *const *bias, void *packed, cudaStream_t s);
+void msd_lengths(int L, int *lens);
+int launch_msd_forward(const void *packed, const float *y, int Bt, int L, float *const *fmaps, int *status, cudaStream_t s);
 int launch_convt_tc(const float *x, float *y, const float *packed, int stage, int B, int Lin, int *status, cudaStream_t s);
 int launch_resblock_tc(const float *x, float *y, const float *packed, int stage, int B, int L, int *status, cudaStream_t s,
                        long long *trace = nullptr);

@@ -409,11 +409,15 @@ int launch_generator_tc(const float *packed, const float *mel, float *audio, int
     float *a0 = ws + ws_offset(0, B, T);
     float *a[4] = {ws + ws_offset(1, B, T), ws + ws_offset(2, B, T), ws + ws_offset(3, B, T), ws + ws_offset(4, B, T)};
     float *u = ws + ws_offset(5, B, T);  // ConvT output of the current stage (largest: B*8192*T floats)
-    dim3 gpre((T + kPreTT - 1) / kPreTT, kPreCout / kPreCG, B);
-    MG_MARK(0);
-    gen_pre_kernel<<<gpre, kPreCG, 0, s>>>(mel, a0, packed, T);
-    MG_CUDA_TRY(cudaGetLastError());
     int rc;
+    MG_MARK(0);
+    if (up_tc) {
+        if ((rc = launch_gen_pre_tc(mel, a0, packed, B, T, status, s))) return rc;
+    } else {
+        dim3 gpre((T + kPreTT - 1) / kPreTT, kPreCout / kPreCG, B);
+        gen_pre_kernel<<<gpre, kPreCG, 0, s>>>(mel, a0, packed, T);
+        MG_CUDA_TRY(cudaGetLastError());
+    }
     MG_MARK(1);
     if ((rc = up_tc ? launch_convt_tc(a0, u, packed, 0, B, T, status, s) : launch_stage<Up0>(a0, u, packed, 0, B, T, s))) return rc;
     MG_MARK(2);

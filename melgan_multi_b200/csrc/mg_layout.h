@@ -110,7 +110,16 @@ MG_HD constexpr size_t up_weight_index(int stage, int ci, int co, int k, int h) 
     return (((((size_t)(co / NG) * (CIN / 16) + ci / 16) * 2 + tap) * 2 + h) * 2 + (ci % 16) / 8) * (S * NG) * 8 +
            (size_t)(phi * NG + co % NG) * 8 + (ci % 8);
 }
-MG_HD constexpr size_t tc_region_bytes() { return tc_up_offset(4); }
+// ---- tensor-core blob for stride-1 dense convs run by conv_rows_tc_kernel (mg_conv_tc.cu): conv_pre here, the
+// discriminators' conv_post1 in their own blob.  One ring slot = (256-channel output group, 16-channel K chunk, tap):
+//   [cg = co/256][chunk = ci/16][tap][half: hi, lo][k-panel = (ci%16)/8][co%256][ci%8]   (bf16), 16 KB per slot
+MG_HD constexpr size_t conv_tc_weight_index(int CIN, int NTAP, int co, int ci, int tap, int h) {
+    return (((((size_t)(co / 256) * (CIN / 16) + ci / 16) * NTAP + tap) * 2 + h) * 2 + (ci % 16) / 8) * 256 * 8 +
+           (size_t)(co % 256) * 8 + (ci % 8);
+}
+MG_HD constexpr size_t tc_pre_offset() { return tc_up_offset(4); }
+MG_HD constexpr size_t tc_pre_bytes() { return (size_t)kMelBins * kPreCout * kPreK * 4; }
+MG_HD constexpr size_t tc_region_bytes() { return tc_pre_offset() + tc_pre_bytes(); }
 MG_HD constexpr size_t packed_total_bytes() { return ((packed_float_count() * 4 + 255) / 256) * 256 + tc_region_bytes(); }
 MG_HD constexpr size_t tc_region_start() { return ((packed_float_count() * 4 + 255) / 256) * 256; }  // bytes
 // element (bf16) index of w[co][ci][tap] (half h) inside its conv's TC block
@@ -118,6 +127,44 @@ MG_HD constexpr size_t tc_weight_index(int C, int co, int ci, int tap, int h) {
     const int KC = tc_kc(C);
     return ((((size_t)(tap * (C / KC) + ci / KC) * 2 + h) * (KC / 8) + (ci % KC) / 8) * C + co) * 8 + (ci % 8);
 }
+
+// =========================================================================================================
+// Discriminator (models.py:74-103) layer table and packed layout.  7 layers per Discriminator, 3 per MSD:
+//   0 conv_pre 1->16 k15 | 1..4 grouped k41 (groups 4,16,64,256; stride 4,4,4,1) | 5 conv_post1 1024->1024 k5 | 6 conv_post2 1024->1 k3
+struct DLayer {
+    int cin, cout, k, stride, groups, pad;
+};
+MG_HD constexpr DLayer d_layer(int l) {
+    return l == 0 ? DLayer{1, 16, 15, 1, 1, 7}
+         : l == 1 ? DLayer{16, 64, 41, 4, 4, 20}
+         : l == 2 ? DLayer{64, 256, 41, 4, 16, 20}
+         : l == 3 ? DLayer{256, 1024, 41, 4, 64, 20}
+         : l == 4 ? DLayer{1024, 1024, 41, 1, 256, 20}
+         : l == 5 ? DLayer{1024, 1024, 5, 1, 1, 2}
+                  : DLayer{1024, 1, 3, 1, 1, 1};
+}
+constexpr int kDiscLayers = 7;
+constexpr int kDiscRows = 16 + 64 + 256 + 1024 + 1024 + 1024 + 1;  // weight-norm rows (= biases) per Discriminator
+// fp32 part of one Discriminator's blob (floats).  Layouts:
+//   conv_pre   [tap 15][co 16]            grouped l=1..4  [group][ci 4][tap 41][co within group]      conv_post2 [ci 1024][tap 3]
+MG_HD constexpr size_t d_weight_count(int l) {
+    return l == 5 ? 0 : (size_t)d_layer(l).cout * (d_layer(l).cin / d_layer(l).groups) * d_layer(l).k;
+}
+MG_HD constexpr size_t d_weight_offset(int l) {
+    size_t o = 0;
+    for (int i = 0; i < l; ++i) o += d_weight_count(i);
+    return o;
+}
+MG_HD constexpr size_t d_bias_offset(int l) {
+    size_t o = d_weight_offset(kDiscLayers);
+    for (int i = 0; i < l; ++i) o += (size_t)d_layer(i).cout;
+    return o;
+}
+MG_HD constexpr size_t d_fp32_floats() { return d_bias_offset(kDiscLayers); }
+MG_HD constexpr size_t d_tc_start() { return ((d_fp32_floats() * 4 + 255) / 256) * 256; }  // conv_post1, conv_tc_weight_index layout
+MG_HD constexpr size_t d_tc_bytes() { return (size_t)1024 * 1024 * 5 * 4; }
+MG_HD constexpr size_t d_blob_bytes() { return d_tc_start() + d_tc_bytes(); }
+MG_HD constexpr size_t msd_packed_bytes() { return 3 * d_blob_bytes(); }
 
 // Activation workspace (floats per batch item per mel frame): conv_pre out, stage 0..2 outs.
 MG_HD constexpr size_t ws_offset(int which, size_t B, size_t T) {  // which: 0 pre, 1..3 stage 0..2

@@ -55,6 +55,17 @@ __global__ void __launch_bounds__(128) pack_kernel(PackArgs a, RowTable rt, floa
     if (sh.kind == 0) {
         // v[co=row][ci][k] -> wp[(ci*K + k)*Cout + co]
         for (int j = threadIdx.x; j < inner; j += blockDim.x) wp[(size_t)j * sh.cout + row] = scale * vr[j];
+        if (l == 0) {
+            // split-bf16 copy of conv_pre for conv_rows_tc_kernel (layout: mg_layout.h, conv_tc_weight_index)
+            __nv_bfloat16 *tcw = reinterpret_cast<__nv_bfloat16 *>(reinterpret_cast<char *>(packed) + tc_region_start() + tc_pre_offset());
+            for (int j = threadIdx.x; j < inner; j += blockDim.x) {
+                const int ci = j / kPreK, tap = j - kPreK * ci;
+                __nv_bfloat16 hi, lo;
+                tc::split_bf16(scale * vr[j], hi, lo);
+                tcw[conv_tc_weight_index(kMelBins, kPreK, row, ci, tap, 0)] = hi;
+                tcw[conv_tc_weight_index(kMelBins, kPreK, row, ci, tap, 1)] = lo;
+            }
+        }
         if (l >= 5 && l <= 28) {
             // split-bf16 copy for the tensor-core ResBlock kernels (layout: mg_layout.h, tc_weight_index)
             __nv_bfloat16 *tcw = reinterpret_cast<__nv_bfloat16 *>(reinterpret_cast<char *>(packed) + tc_region_start() +

@@ -61,6 +61,7 @@ def test_cabi_library_exports_every_declared_symbol():
     fp32_blob = (4524290 - 4353) * 4
     tc_blob = 6 * 12 * (256 * 256 + 128 * 128 + 64 * 64 + 32 * 32)  # split-bf16 copy of the 24 ResBlock convs
     tc_blob += 4 * (512 * 256 * 16 + 256 * 128 * 16 + 128 * 64 * 4 + 64 * 32 * 4)  # ... and of the 4 ConvTranspose1d
+    tc_blob += 4 * 80 * 512 * 7  # ... and of conv_pre
     assert engine.lib().mg_gen_packed_bytes() == (fp32_blob + 255) // 256 * 256 + tc_blob
     assert engine.lib().mg_gen_workspace_bytes(64, 32) == 64 * 32 * (18944 + 2 * 8192) * 4 + 256
     assert engine.lib().mg_gen_workspace_bytes(0, 32) == 0
