@@ -99,7 +99,12 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.y;
-    const int o = blockIdx.x * Cfg::PVALID - HALO;  // global position of tile-local p = 0
+    // Edge-aware tiling: a halo is only needed where the tile borders MORE sequence.  Tile 0 starts at position 0 (its
+    // left edge is the real zero padding) and keeps P - HALO outputs; later tiles keep P - 2*HALO, and a tile that reaches
+    // the end of the sequence keeps its right HALO rows too.  (L = 2048, P = 256: 9 tiles instead of 10.)
+    const int o = blockIdx.x == 0 ? 0 : (P - HALO) + ((int)blockIdx.x - 1) * Cfg::PVALID - HALO;  // position of tile-local p = 0
+    const int p_lo = blockIdx.x == 0 ? 0 : HALO;
+    const int p_hi = (o + P >= L) ? P : P - HALO;  // first tile-local row that is NOT a valid output
     // consumption order of the six convs of ResBlock `stage`: c1[0], c2[0], c1[1], c2[1], c1[2], c2[2]
     const int l0 = 5 + 6 * stage;
     const uint8_t *tc_base = reinterpret_cast<const uint8_t *>(packed) + tc_region_start();
@@ -305,10 +310,13 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
 #pragma unroll 1
             for (int it = wg; it < ITEMS; it += NWG) {
                 const int p = it * 128 + row, t = o + p;
-                if (p >= HALO && p < P - HALO && t < L) {
+                if (p >= p_lo && p < p_hi && t < L) {
                     float acc = bpost;
 #pragma unroll
-                    for (int k = 0; k < kPostK; ++k) acc += Q[k * P + p + k - 3];
+                    for (int k = 0; k < kPostK; ++k) {
+                        const int pp = p + k - 3;  // outside the tile only where it is outside the sequence too (zero padding)
+                        if (pp >= 0 && pp < P) acc += Q[k * P + pp];
+                    }
                     y[(size_t)b * L + t] = tanhf(acc);
                 }
             }
@@ -318,7 +326,7 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
         for (int it = wg; it < ITEMS; it += NWG) {
             const int blk = it / PARTS, cbeg = (it % PARTS) * CW;
             const int p = blk * 128 + row, t = o + p;
-            const bool valid = (p >= HALO && p < P - HALO && t < L);
+            const bool valid = (p >= p_lo && p < p_hi && t < L);
             float *yp = y + (size_t)b * C * L + (valid ? t : 0);
 #pragma unroll 1
             for (int c0 = cbeg; c0 < cbeg + CW; c0 += 32) {
@@ -348,7 +356,8 @@ static int launch_resblock(const float *x, float *y, const float *packed, int st
         MG_CUDA_TRY(cudaFuncSetAttribute(resblock_tc_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         configured = true;
     }
-    dim3 grid((L + Cfg::PVALID - 1) / Cfg::PVALID, B);
+    const int ntiles = 1 + (L > Cfg::P ? (L - Cfg::P + Cfg::PVALID - 1) / Cfg::PVALID : 0);  // edge-aware tiling, see the kernel
+    dim3 grid(ntiles, B);
     resblock_tc_kernel<Cfg><<<grid, Cfg::NT, Cfg::SMEM_BYTES, s>>>(x, y, packed, stage, L, status, trace);
     MG_CUDA_TRY(cudaGetLastError());
     return MG_OK;

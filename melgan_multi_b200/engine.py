@@ -58,6 +58,16 @@ def lib():
         L.mg_gen_forward_launches.restype = ctypes.c_int
         L.mg_gen_kernel_name.restype = ctypes.c_char_p
         L.mg_gen_kernel_name.argtypes = [ctypes.c_int]
+        L.mg_msd_packed_bytes.restype = ctypes.c_size_t
+        L.mg_msd_pack.restype = ctypes.c_int
+        L.mg_msd_pack.argtypes = [ctypes.c_void_p] * 5
+        L.mg_msd_lengths.restype = ctypes.c_int
+        L.mg_msd_lengths.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+        L.mg_msd_forward.restype = ctypes.c_int
+        L.mg_msd_forward.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                     ctypes.c_void_p, ctypes.c_void_p]
+        L.mg_msd_check_status.restype = ctypes.c_int
+        L.mg_msd_check_status.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.mg_gen_engine_create.restype = ctypes.c_int
         L.mg_gen_engine_create.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int]
         L.mg_gen_engine_load_state.restype = ctypes.c_int
@@ -200,6 +210,77 @@ class GeneratorDevice:
             stream = torch.cuda.current_stream().cuda_stream
             check(lib().mg_gen_stage_output(self._ws.data_ptr(), which, out.data_ptr(), B, T, stream))
         return out
+
+
+D_CHANNELS = (16, 64, 256, 1024, 1024, 1024, 1)  # channels of the seven feature maps of one Discriminator
+
+
+def msd_lengths(L):
+    """Feature-map lengths [3][7] of the multi-scale discriminator for an input of L samples."""
+    lens = (ctypes.c_int * 21)()
+    check(lib().mg_msd_lengths(int(L), lens))
+    return [[lens[s * 7 + l] for l in range(7)] for s in range(3)]
+
+
+class DiscriminatorDevice:
+    """Packed multi-scale-discriminator weights on one CUDA device, driven with torch tensors."""
+
+    def __init__(self, device):
+        import torch
+        self.torch = torch
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise EngineError("the B200 engine runs on CUDA devices only (got %s)" % (device,))
+        with torch.cuda.device(self.device):
+            check(lib().mg_device_check())
+        nbytes = lib().mg_msd_packed_bytes()
+        self.packed = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=self.device)
+        self.status = torch.zeros(64, dtype=torch.int32, device=self.device)
+
+    def pack(self, vs, gs, bs):
+        """vs/gs/bs: 21 fp32 CUDA tensors each (discriminator-major, layers in registration order)."""
+        torch = self.torch
+        if not (len(vs) == len(gs) == len(bs) == 21):
+            raise EngineError("expected 21 discriminator layers")
+        keep = []
+
+        def ptrs(ts):
+            out = []
+            for t in ts:
+                t = t.detach()
+                if t.device != self.device or t.dtype != torch.float32:
+                    raise EngineError("discriminator parameters must be fp32 tensors on %s" % (self.device,))
+                t = t.contiguous()
+                keep.append(t)
+                out.append(t.data_ptr())
+            return _ptr_array(out)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            check(lib().mg_msd_pack(ptrs(vs), ptrs(gs), ptrs(bs), self.packed.data_ptr(), stream))
+
+    def forward(self, y):
+        """y [Bt, 1, L] -> list of 3 lists of 7 feature maps [Bt, C, len] (fresh tensors)."""
+        torch = self.torch
+        if y.dim() != 3 or y.shape[1] != 1:
+            raise EngineError("audio must be [B, 1, L], got %s" % (tuple(y.shape),))
+        if y.device != self.device or y.dtype != torch.float32:
+            raise EngineError("audio must be an fp32 tensor on %s" % (self.device,))
+        y = y.contiguous()
+        Bt, _, L = y.shape
+        lens = msd_lengths(L)
+        fmaps = [[torch.empty((Bt, D_CHANNELS[l], lens[s][l]), dtype=torch.float32, device=self.device)
+                  for l in range(7)] for s in range(3)]
+        ptrs = _ptr_array([f.data_ptr() for sc in fmaps for f in sc])
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            check(lib().mg_msd_forward(self.packed.data_ptr(), y.data_ptr(), Bt, L, ptrs, self.status.data_ptr(), stream))
+        return fmaps
+
+    def check_status(self):
+        torch = self.torch
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            check(lib().mg_msd_check_status(self.status.data_ptr(), stream))
 
 
 # ------------------------------------------------------------------------------------------

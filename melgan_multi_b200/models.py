@@ -13,9 +13,12 @@ What runs where
     ResBlock) stage, the last one also doing LeakyReLU -> conv_post -> tanh -- plus one launch
     that folds weight-norm for all 30 layers whenever the parameters changed.  CUDA only; a CPU
     tensor raises (the reference's CPU path lives in oracle/ as test infrastructure).
-  * Backward of the generator, and the discriminators (forward and backward), are NOT native yet:
-    they run as stock PyTorch ops so that train.py keeps working.  They are listed as open rows
-    in DESIGN.md and are never part of a benchmark or parity claim.
+  * ``MultiScaleDiscriminator.forward`` (models.py:119-135, Discriminator.forward :87-103) on CUDA: real and generated
+    audio are stacked into one batch and run through hand-written kernels -- AvgPool chain fused into each scale's
+    conv_pre, grouped k41 convs in fp32 SIMT, conv_post1 (88% of the FLOPs) on tcgen05 -- after one launch that folds
+    weight-norm for the 21 layers.
+  * Backward passes (generator and discriminators) are NOT native yet: they run as recomputation through stock
+    PyTorch ops so that train.py keeps working.  Open row in DESIGN.md, never part of a benchmark or parity claim.
 """
 import torch
 import torch.nn as nn
@@ -157,7 +160,9 @@ class Generator(nn.Module):
 
 
 class Discriminator(nn.Module):
-    """Reference models.py:74-103.  Stock PyTorch ops for now (open row in DESIGN.md)."""
+    """Parameter container with the reference's layout (models.py:74-85).  ``forward`` is the stock PyTorch restatement
+    (reference models.py:87-103): it serves CPU tensors and the autograd (backward) path; CUDA inference of the
+    three-scale stack goes through the fused kernels in ``MultiScaleDiscriminator``."""
 
     def __init__(self):
         super().__init__()
@@ -170,6 +175,9 @@ class Discriminator(nn.Module):
         self.conv_post1 = mk("conv_post1")
         self.conv_post2 = mk("conv_post2")
 
+    def layers(self):
+        return [self.conv_pre] + list(self.grouped_convs) + [self.conv_post1, self.conv_post2]
+
     def forward(self, x):
         fmap = []
         for layer in [self.conv_pre] + list(self.grouped_convs) + [self.conv_post1]:
@@ -180,15 +188,80 @@ class Discriminator(nn.Module):
         return torch.flatten(x, 1, -1), fmap
 
 
+class _MSDFunction(torch.autograd.Function):
+    """Forward on the fused sm_100a kernels (real and generated stacked as one batch); backward by recomputation through
+    stock PyTorch ops (open row: native backward).  Inputs: stacked audio [2B,1,L], then 21 x (weight_v, weight_g, bias);
+    outputs: the 21 feature maps, scale-major."""
+
+    @staticmethod
+    def forward(ctx, msd, y2, *params):
+        ctx.msd = msd
+        ctx.save_for_backward(y2, *params)
+        fmaps = msd._engine_forward(y2)
+        return tuple(f for sc in fmaps for f in sc)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        msd = ctx.msd
+        y2, *params = ctx.saved_tensors
+        with torch.enable_grad():
+            y_ = y2.detach().requires_grad_(ctx.needs_input_grad[1])
+            leaves = [p.detach().requires_grad_(True) for p in params]
+            outs = msd._torch_forward(y_, leaves)
+            pairs = [(o, g) for o, g in zip(outs, grads) if g is not None]
+            wanted = ([y_] if ctx.needs_input_grad[1] else []) + leaves
+            gs = torch.autograd.grad([o for o, _ in pairs], wanted, [g for _, g in pairs], allow_unused=True)
+        gs = list(gs)
+        gy = gs.pop(0) if ctx.needs_input_grad[1] else None
+        return (None, gy, *gs)
+
+
 class MultiScaleDiscriminator(nn.Module):
-    """Reference models.py:106-135: three Discriminators on y, pool(y), pool(pool(y))."""
+    """Reference models.py:106-135: three Discriminators on y, pool(y), pool(pool(y)); returns
+    (y_d_rs, y_d_gs, fmap_rs, fmap_gs).  On CUDA the whole stack runs in the hand-written kernels of
+    libmelgan_b200.so with y and y_hat stacked into one batch (the reference calls each discriminator twice)."""
 
     def __init__(self):
         super().__init__()
         self.discriminators = nn.ModuleList([Discriminator() for _ in range(3)])
         self.meanpools = nn.ModuleList([AvgPool1d(4, 2, padding=2), AvgPool1d(4, 4, padding=2)])
+        self._dev = None
+        self._packed_key = None
 
-    def forward(self, y, y_hat):
+    def _param_triplets(self):
+        mods = [m for d in self.discriminators for m in d.layers()]
+        return [m.weight_v for m in mods], [m.weight_g for m in mods], [m.bias for m in mods]
+
+    def _engine_forward(self, y2):
+        vs, gs, bs = self._param_triplets()
+        dev = vs[0].device
+        if self._dev is None or self._dev.device != dev:
+            self._dev = _engine.DiscriminatorDevice(dev)
+            self._packed_key = None
+        key = tuple((t.data_ptr(), t._version) for t in vs + gs + bs)
+        if key != self._packed_key:
+            self._dev.pack(vs, gs, bs)
+            self._packed_key = key
+        return self._dev.forward(y2)
+
+    # -- stock-PyTorch restatement on folded weights, used ONLY to differentiate (backward) -----------------
+    def _torch_forward(self, y2, leaves):
+        outs = []
+        x_in = y2
+        for s in range(3):
+            if s > 0:
+                x_in = self.meanpools[s - 1](x_in)
+            x = x_in
+            for l, (_n, _cin, _cout, _k, stride, groups, pad) in enumerate(DISCRIMINATOR_LAYERS):
+                i = 3 * (7 * s + l)
+                w = torch._weight_norm(leaves[i], leaves[i + 1], 0)
+                x = F.conv1d(x, w, leaves[i + 2], stride=stride, padding=pad, groups=groups)
+                if l < 6:
+                    x = F.leaky_relu(x)
+                outs.append(x)
+        return outs
+
+    def _reference_style_forward(self, y, y_hat):
         y_d_rs, y_d_gs, fmap_rs, fmap_gs = [], [], [], []
         for i, d in enumerate(self.discriminators):
             if i > 0:
@@ -196,6 +269,31 @@ class MultiScaleDiscriminator(nn.Module):
             r, fr = d(y)
             g, fg = d(y_hat)
             y_d_rs.append(r); fmap_rs.append(fr); y_d_gs.append(g); fmap_gs.append(fg)
+        return y_d_rs, y_d_gs, fmap_rs, fmap_gs
+
+    def forward(self, y, y_hat):
+        if not (y.is_cuda and y_hat.is_cuda):
+            # the discriminators' backward is not native yet, so the stock-op graph exists anyway; it also serves CPU
+            # tensors (CPU-side tests of the training wrapper).  It is never used for a CUDA forward.
+            return self._reference_style_forward(y, y_hat)
+        B = y.shape[0]
+        y2 = torch.cat([y, y_hat], dim=0).float()
+        vs, gs, bs = self._param_triplets()
+        needs_grad = torch.is_grad_enabled() and (y2.requires_grad or any(p.requires_grad for p in vs + gs + bs))
+        if needs_grad:
+            flat = []
+            for v, g, b in zip(vs, gs, bs):
+                flat += [v, g, b]
+            flat_maps = _MSDFunction.apply(self, y2, *flat)
+            fmaps = [list(flat_maps[7 * s:7 * s + 7]) for s in range(3)]
+        else:
+            fmaps = self._engine_forward(y2)
+        y_d_rs, y_d_gs, fmap_rs, fmap_gs = [], [], [], []
+        for s in range(3):
+            fmap_rs.append([f[:B] for f in fmaps[s]])
+            fmap_gs.append([f[B:] for f in fmaps[s]])
+            y_d_rs.append(torch.flatten(fmaps[s][6][:B], 1, -1))
+            y_d_gs.append(torch.flatten(fmaps[s][6][B:], 1, -1))
         return y_d_rs, y_d_gs, fmap_rs, fmap_gs
 
 
