@@ -320,11 +320,19 @@ def main():
     extra = 2 * (8192 + 32768 + 32768 + 32768) if tc_path else 0
     fwd_bytes = (ALG_BYTES_PER_FRAME + extra) * frames + packed_bytes
     fwd_ms = total_ms / K
+    traffic = None  # dram bytes per launch of the dominant kernel, from the committed ncu --set full capture
+    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if tc_path and os.path.exists(tpath):
+        t = json.load(open(tpath)).get("res1")
+        if t:
+            traffic = t["dram_read_bytes"] + t["dram_write_bytes"]
     roofline = {
         "kernel": ("resblock_tc_kernel<C=128> (stage-1 ResBlock: 6 k3 convs, 36% of generator FLOPs)" if tc_path else
                    "gen_stage_kernel<stage 1: lrelu+ConvT(256->128,k16,s8)+ResBlock(128)>"),
         "bound": "tensor", "achieved": dom_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-        "frac": dom_tflops / peaks["bf16_tflops"], "traffic": None,
+        "frac": dom_tflops / peaks["bf16_tflops"], "traffic": traffic,
+        "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r01_ncu_res1_key_metrics.txt); "
+                        "algorithmic HBM bytes of this kernel: 2 * 64*128*2048*4 = 134.2 MB (the 126 MB L2 keeps part of the output)",
         "peak_source": "%s bf16 dense burst (MEASURED_PEAKS.json)" % peaks["source"],
         "algorithmic_flops_per_launch": k_flops[dom], "avg_launch_ms": float(kms[dom]),
         "math": ("split-bf16 tcgen05: 3 MMA passes per product, so tensor-pipe work is 3x the algorithmic FLOPs "
