@@ -160,9 +160,9 @@ class Generator(nn.Module):
 
 
 class Discriminator(nn.Module):
-    """Parameter container with the reference's layout (models.py:74-85).  ``forward`` is the stock PyTorch restatement
-    (reference models.py:87-103): it serves CPU tensors and the autograd (backward) path; CUDA inference of the
-    three-scale stack goes through the fused kernels in ``MultiScaleDiscriminator``."""
+    """Parameter container with the reference's layout (models.py:74-85).  The three-scale stack runs as one fused
+    pipeline in ``MultiScaleDiscriminator`` (the only caller in the reference, models.py:109-113), so a lone
+    ``Discriminator`` has no forward of its own here and calling it raises: there is no silent stock-op path."""
 
     def __init__(self):
         super().__init__()
@@ -179,13 +179,9 @@ class Discriminator(nn.Module):
         return [self.conv_pre] + list(self.grouped_convs) + [self.conv_post1, self.conv_post2]
 
     def forward(self, x):
-        fmap = []
-        for layer in [self.conv_pre] + list(self.grouped_convs) + [self.conv_post1]:
-            x = F.leaky_relu(layer(x))
-            fmap.append(x)
-        x = self.conv_post2(x)
-        fmap.append(x)
-        return torch.flatten(x, 1, -1), fmap
+        raise _engine.EngineError(
+            "melgan_multi_b200.Discriminator is a parameter container: run MultiScaleDiscriminator (CUDA), which drives the "
+            "three discriminators through the fused sm_100a kernels; there is deliberately no stock-PyTorch fallback")
 
 
 class _MSDFunction(torch.autograd.Function):
@@ -261,21 +257,10 @@ class MultiScaleDiscriminator(nn.Module):
                 outs.append(x)
         return outs
 
-    def _reference_style_forward(self, y, y_hat):
-        y_d_rs, y_d_gs, fmap_rs, fmap_gs = [], [], [], []
-        for i, d in enumerate(self.discriminators):
-            if i > 0:
-                y, y_hat = self.meanpools[i - 1](y), self.meanpools[i - 1](y_hat)
-            r, fr = d(y)
-            g, fg = d(y_hat)
-            y_d_rs.append(r); fmap_rs.append(fr); y_d_gs.append(g); fmap_gs.append(fg)
-        return y_d_rs, y_d_gs, fmap_rs, fmap_gs
-
     def forward(self, y, y_hat):
         if not (y.is_cuda and y_hat.is_cuda):
-            # the discriminators' backward is not native yet, so the stock-op graph exists anyway; it also serves CPU
-            # tensors (CPU-side tests of the training wrapper).  It is never used for a CUDA forward.
-            return self._reference_style_forward(y, y_hat)
+            raise _engine.EngineError(
+                "melgan_multi_b200.MultiScaleDiscriminator.forward needs CUDA tensors (no CPU fallback)")
         B = y.shape[0]
         y2 = torch.cat([y, y_hat], dim=0).float()
         vs, gs, bs = self._param_triplets()

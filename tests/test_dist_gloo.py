@@ -18,10 +18,27 @@ def _free_port():
         return s.getsockname()[1]
 
 
+class _TinyDisc(torch.nn.Module):
+    """A small weight-normed conv stack with the parameter structure the wrapper meets in practice (weight_g /
+    weight_v / bias leaves, grouped conv); plain PyTorch so that it runs on CPU under gloo."""
+
+    def __init__(self):
+        super().__init__()
+        wn = torch.nn.utils.weight_norm
+        self.pre = wn(torch.nn.Conv1d(1, 16, 15, padding=7))
+        self.grp = wn(torch.nn.Conv1d(16, 64, 41, 4, groups=4, padding=20))
+        self.post = wn(torch.nn.Conv1d(64, 1, 3, padding=1))
+
+    def forward(self, x):
+        fm = [torch.nn.functional.leaky_relu(self.pre(x))]
+        fm.append(torch.nn.functional.leaky_relu(self.grp(fm[-1])))
+        out = self.post(fm[-1])
+        return out.flatten(1), fm
+
+
 def _make_model(seed):
     torch.manual_seed(seed)
-    from melgan_multi_b200 import models
-    return models.Discriminator()  # stock-op module with weight_g/weight_v/bias leaves; runs on CPU
+    return _TinyDisc()
 
 
 def _worker(rank, world, port, out_dir):

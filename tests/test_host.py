@@ -99,16 +99,33 @@ def test_torch_restatement_used_for_backward_matches_golden(golden):
 
 
 def test_losses_match_reference_values(golden):
+    """Loss functions on the stock-op graph that autograd differentiates (MultiScaleDiscriminator._torch_forward, CPU)."""
     import cases
     from melgan_multi_b200 import models
     B, L, seed = cases.MSD_CASES[1]
     d = models.MultiScaleDiscriminator()
     d.load_state_dict({k: torch.from_numpy(v) for k, v in synth.discriminator_state(4321).items()})
+    vs, gs_, bs = d._param_triplets()
+    leaves = []
+    for v, g, b in zip(vs, gs_, bs):
+        leaves += [v, g, b]
+    y2 = torch.cat([torch.from_numpy(synth.audio_input(B, L, seed)), torch.from_numpy(synth.audio_input(B, L, seed + 7))])
     with torch.no_grad():
-        rs, gs, frs, fgs = d(torch.from_numpy(synth.audio_input(B, L, seed)),
-                             torch.from_numpy(synth.audio_input(B, L, seed + 7)))
+        outs = d._torch_forward(y2, leaves)
+    fm = [outs[7 * s:7 * s + 7] for s in range(3)]
+    frs, fgs = [[f[:B] for f in sc] for sc in fm], [[f[B:] for f in sc] for sc in fm]
+    rs, gs = [sc[6][:B].flatten(1) for sc in fm], [sc[6][B:].flatten(1) for sc in fm]
     tag = "msd_B%d_L%d_s%d" % (B, L, seed)
     assert abs(models.feature_loss(frs, fgs).item() - float(golden[tag + "_feature_loss"])) < 1e-4
     assert abs(models.generator_loss(gs).item() - float(golden[tag + "_generator_loss"])) < 1e-5
     dl, rl, gl = models.discriminator_loss(rs, gs)
     np.testing.assert_allclose([dl.item()] + rl + gl, golden[tag + "_discriminator_loss"], rtol=1e-4, atol=1e-6)
+
+
+def test_discriminators_refuse_cpu_tensors():
+    from melgan_multi_b200 import models
+    d = models.MultiScaleDiscriminator()
+    with pytest.raises(engine.EngineError):
+        d(torch.zeros(1, 1, 64), torch.zeros(1, 1, 64))
+    with pytest.raises(engine.EngineError):
+        d.discriminators[0](torch.zeros(1, 1, 64))
