@@ -198,36 +198,29 @@ __global__ void __launch_bounds__(128) disc_group_kernel(const float *__restrict
 }
 
 // conv_post2 (1024 -> 1, k3, pad 1), no activation.  x [Bt][1024][L] -> out [Bt][1][L]
-__global__ void __launch_bounds__(256) disc_post2_kernel(const float *__restrict__ x, float *__restrict__ out,
+// CTA = 32 positions of one item (lane = position: coalesced 128-byte rows); 16 warps split the 1024 input channels.
+__global__ void __launch_bounds__(512) disc_post2_kernel(const float *__restrict__ x, float *__restrict__ out,
                                                          const float *__restrict__ w, const float *__restrict__ bias, int L) {
-    __shared__ float part[8][128];
+    __shared__ float part[16][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int t0 = blockIdx.x * 128, b = blockIdx.y;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const int t = blockIdx.x * 32 + lane, b = blockIdx.y;
     const float *xb = x + (size_t)b * 1024 * L;
-    for (int ci = warp * 128; ci < warp * 128 + 128; ++ci) {
-        const float w0 = __ldg(w + ci * 3), w1 = __ldg(w + ci * 3 + 1), w2 = __ldg(w + ci * 3 + 2);
-        const float *xr = xb + (size_t)ci * L;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int t = t0 + lane + 32 * j;
-            if (t < L) {
-                const float xm = t >= 1 ? __ldg(xr + t - 1) : 0.f, xc = __ldg(xr + t), xp = t + 1 < L ? __ldg(xr + t + 1) : 0.f;
-                acc[j] = fmaf(w0, xm, fmaf(w1, xc, fmaf(w2, xp, acc[j])));
-            }
+    float acc = 0.f;
+    if (t < L) {
+#pragma unroll 8
+        for (int ci = warp * 64; ci < warp * 64 + 64; ++ci) {
+            const float *xr = xb + (size_t)ci * L + t;
+            const float xm = t >= 1 ? __ldg(xr - 1) : 0.f, xc = __ldg(xr), xp = t + 1 < L ? __ldg(xr + 1) : 0.f;
+            acc = fmaf(__ldg(w + ci * 3), xm, fmaf(__ldg(w + ci * 3 + 1), xc, fmaf(__ldg(w + ci * 3 + 2), xp, acc)));
         }
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) part[warp][lane + 32 * j] = acc[j];
+    part[warp][lane] = acc;
     __syncthreads();
-    if (threadIdx.x < 128) {
-        const int t = t0 + threadIdx.x;
-        if (t < L) {
-            float s = __ldg(bias);
+    if (warp == 0 && t < L) {
+        float s = __ldg(bias);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) s += part[q][threadIdx.x];
-            out[(size_t)b * L + t] = s;
-        }
+        for (int q = 0; q < 16; ++q) s += part[q][lane];
+        out[(size_t)b * L + t] = s;
     }
 }
 
@@ -264,31 +257,58 @@ static int launch_group(const float *x, float *out, const float *w, const float 
     return MG_OK;
 }
 
+// Side streams for the three scales (they are independent until the caller consumes the feature maps): forked from and
+// joined back into the caller's stream with events, so the call stays asynchronous and stream-ordered for the caller.
+struct ScaleStreams {
+    cudaStream_t st[2] = {nullptr, nullptr};
+    cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+    bool ready = false;
+    int init() {
+        if (ready) return MG_OK;
+        for (int i = 0; i < 2; ++i) {
+            MG_CUDA_TRY(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+            MG_CUDA_TRY(cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming));
+        }
+        MG_CUDA_TRY(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+        ready = true;
+        return MG_OK;
+    }
+};
+
 // y [Bt][1][L] -> fmaps[sc*7 + l] (device pointers, fp32 NCL, lengths from msd_lengths); status: device int
 int launch_msd_forward(const void *packed, const float *y, int Bt, int L, float *const *fmaps, int *status, cudaStream_t s) {
+    static thread_local ScaleStreams ss;  // per host thread, like the rest of the library's state
+    int rc = ss.init();
+    if (rc) return rc;
     int lens[3 * kDiscLayers];
     msd_lengths(L, lens);
     const int L1 = (L + 4 - 4) / 2 + 1, L2 = (L1 + 4 - 4) / 4 + 1;
+    MG_CUDA_TRY(cudaEventRecord(ss.fork, s));
     for (int sc = 0; sc < 3; ++sc) {
+        cudaStream_t q = sc == 0 ? s : ss.st[sc - 1];  // scale 0 (the largest) stays on the caller's stream
+        if (sc > 0) MG_CUDA_TRY(cudaStreamWaitEvent(q, ss.fork, 0));
         const uint8_t *blob = reinterpret_cast<const uint8_t *>(packed) + (size_t)sc * d_blob_bytes();
         const float *fw = reinterpret_cast<const float *>(blob);
         float *const *f = fmaps + sc * kDiscLayers;
         const int *ln = lens + sc * kDiscLayers;
         const int Ls = sc == 0 ? L : sc == 1 ? L1 : L2;
         dim3 gpre((Ls + 255) / 256, Bt);
-        if (sc == 0) disc_pre_kernel<0><<<gpre, 256, 0, s>>>(y, f[0], fw, L, L1, L2);
-        else if (sc == 1) disc_pre_kernel<1><<<gpre, 256, 0, s>>>(y, f[0], fw, L, L1, L2);
-        else disc_pre_kernel<2><<<gpre, 256, 0, s>>>(y, f[0], fw, L, L1, L2);
+        if (sc == 0) disc_pre_kernel<0><<<gpre, 256, 0, q>>>(y, f[0], fw, L, L1, L2);
+        else if (sc == 1) disc_pre_kernel<1><<<gpre, 256, 0, q>>>(y, f[0], fw, L, L1, L2);
+        else disc_pre_kernel<2><<<gpre, 256, 0, q>>>(y, f[0], fw, L, L1, L2);
         MG_CUDA_TRY(cudaGetLastError());
-        int rc;
-        if ((rc = launch_group<16, 4>(f[0], f[1], fw + d_weight_offset(1), fw + d_bias_offset(1), Bt, 16, 64, ln[0], ln[1], s))) return rc;
-        if ((rc = launch_group<16, 4>(f[1], f[2], fw + d_weight_offset(2), fw + d_bias_offset(2), Bt, 64, 256, ln[1], ln[2], s))) return rc;
-        if ((rc = launch_group<16, 4>(f[2], f[3], fw + d_weight_offset(3), fw + d_bias_offset(3), Bt, 256, 1024, ln[2], ln[3], s))) return rc;
-        if ((rc = launch_group<4, 1>(f[3], f[4], fw + d_weight_offset(4), fw + d_bias_offset(4), Bt, 1024, 1024, ln[3], ln[4], s))) return rc;
-        if ((rc = launch_disc_post1_tc(f[4], f[5], blob + d_tc_start(), fw + d_bias_offset(5), Bt, ln[4], status, s))) return rc;
-        dim3 gp2((ln[5] + 127) / 128, Bt);
-        disc_post2_kernel<<<gp2, 256, 0, s>>>(f[5], f[6], fw + d_weight_offset(6), fw + d_bias_offset(6), ln[5]);
+        if ((rc = launch_group<16, 4>(f[0], f[1], fw + d_weight_offset(1), fw + d_bias_offset(1), Bt, 16, 64, ln[0], ln[1], q))) return rc;
+        if ((rc = launch_group<16, 4>(f[1], f[2], fw + d_weight_offset(2), fw + d_bias_offset(2), Bt, 64, 256, ln[1], ln[2], q))) return rc;
+        if ((rc = launch_group<16, 4>(f[2], f[3], fw + d_weight_offset(3), fw + d_bias_offset(3), Bt, 256, 1024, ln[2], ln[3], q))) return rc;
+        if ((rc = launch_group<4, 1>(f[3], f[4], fw + d_weight_offset(4), fw + d_bias_offset(4), Bt, 1024, 1024, ln[3], ln[4], q))) return rc;
+        if ((rc = launch_disc_post1_tc(f[4], f[5], blob + d_tc_start(), fw + d_bias_offset(5), Bt, ln[4], status, q))) return rc;
+        dim3 gp2((ln[5] + 31) / 32, Bt);
+        disc_post2_kernel<<<gp2, 512, 0, q>>>(f[5], f[6], fw + d_weight_offset(6), fw + d_bias_offset(6), ln[5]);
         MG_CUDA_TRY(cudaGetLastError());
+        if (sc > 0) {
+            MG_CUDA_TRY(cudaEventRecord(ss.join[sc - 1], q));
+            MG_CUDA_TRY(cudaStreamWaitEvent(s, ss.join[sc - 1], 0));
+        }
     }
     return MG_OK;
 }

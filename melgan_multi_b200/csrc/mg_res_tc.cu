@@ -57,7 +57,14 @@ struct RbCfg {
     static constexpr int NEPI = 128 * NWG;
     static constexpr int NIW = NBLK >= 2 ? 2 : 1;  // MMA issuer warps (the MMAs are smem-bandwidth bound, not issue bound)
     static constexpr int NT = NEPI + 32 + 32 * NIW;
-    static constexpr int SMEM_BYTES = 2 * XBYTES + NSTAGE * CHUNK + 2 * C * 4 + (2 * NSTAGE + 1) * 8 + 16;
+    // X is handed to the MMA warps in NH channel halves: the next conv starts on input channels [0, C/NH) while the
+    // epilogue is still writing the rest (K-slice order of the weight chunks follows).  Each epilogue thread owns CW/NH
+    // columns of every half.
+    // (measured: -5 % per conv at C = 128; at C = 256 the early MMAs and the epilogue's stores fight for shared-memory
+    //  bandwidth and it is a wash, so that stage keeps the single hand-off)
+    static constexpr int NH = (C == 128) ? 2 : 1;
+    static constexpr int SMEM_BYTES = 2 * XBYTES + NSTAGE * CHUNK + 2 * C * 4 + (2 * NSTAGE + 1 + NH) * 8 + 16;
+    static_assert(KSL % NH == 0 && (CW / NH) % 32 == 0 && (NH == 1 || ITEMS == NWG), "hand-off split");
     static_assert(MINB * (SMEM_BYTES + 1024) <= 228 * 1024, "shared memory budget");
     static_assert(MINB * TCOLS <= 512 && (TCOLS == 256 || TCOLS == 512), "TMEM budget");
     static_assert(XPITCH / 16 < 16384, "LBO field");
@@ -95,7 +102,8 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
     uint64_t *full = reinterpret_cast<uint64_t *>(b1s + C);
     uint64_t *empty = full + NSTAGE;
     uint64_t *done = empty + NSTAGE;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done + 1);
+    uint64_t *xready = done + 1;  // [NH]: X channels [h*C/NH, (h+1)*C/NH) of the next conv are written (all epilogue threads arrive)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(xready + Cfg::NH);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.y;
@@ -116,6 +124,7 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
             mbar_init(&empty[s], NIW);  // every issuer warp commits its own arrival
         }
         mbar_init(done, NIW);
+        for (int h = 0; h < Cfg::NH; ++h) mbar_init(&xready[h], NEPI);
         fence_mbar_init();
     }
     for (int i = tid; i < 2 * Cfg::KP * 2 * SLACK; i += Cfg::NT) {  // zero the slack rows of Xh and Xl
@@ -141,7 +150,12 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
             for (int conv = 0; conv < 6 && ok; ++conv) {
                 const int layer = l0 + (conv >> 1) + 3 * (conv & 1);
                 const uint8_t *src = tc_base + tc_res_offset(layer);
-                for (int ch = 0; ch < Cfg::NCHUNK; ++ch) {
+                // consumption order: channel half h outermost (hand-off order), then tap, then K-slice within the half;
+                // the blob stores chunk (tap, ks) at index tap*KSL + ks
+                for (int i = 0; i < Cfg::NCHUNK && ok; ++i) {
+                    constexpr int KH = Cfg::KSL / Cfg::NH;
+                    const int h = i / (3 * KH), tap = (i / KH) % 3, ks = h * KH + i % KH;
+                    const int ch = tap * Cfg::KSL + ks;
                     if (!mbar_wait(&empty[s], ph ^ 1)) { ok = false; break; }
                     mbar_arrive_expect_tx(&full[s], CHUNK);
                     bulk_g2s(ring + s * CHUNK, src + (size_t)ch * CHUNK, CHUNK, &full[s]);
@@ -162,15 +176,18 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
         bool ok = true;  // a timed-out wait only raises the status word: control flow stays warp-uniform
 #pragma unroll 1
         for (int conv = 0; conv < 6; ++conv) {
-            named_bar_sync(1, NEPI + 32 * NIW);  // X for this conv is complete
-            tc_fence_after();
-            if (iw == 0) MG_TR(64 + 3 * conv);
             const int dil = (conv & 1) ? 1 : (conv == 0 ? 1 : conv == 2 ? 3 : 9);
             const uint32_t dcol = (conv & 1) ? 0 : C;  // c1 -> D1, c2 -> R (accumulating onto the residual)
             const bool fresh = !(conv & 1);
 #pragma unroll 1
             for (int ch = 0; ch < Cfg::NCHUNK; ++ch) {
-                const int tap = ch / Cfg::KSL, ks = ch % Cfg::KSL;
+                constexpr int KH = Cfg::KSL / Cfg::NH;
+                const int h = ch / (3 * KH), tap = (ch / KH) % 3, ks = h * KH + ch % KH;
+                if (ch % (3 * KH) == 0) {  // first chunk of channel half h: wait until the epilogue has written those channels of X
+                    ok &= mbar_wait(&xready[h], conv & 1);
+                    tc_fence_after();
+                    if (ch == 0 && iw == 0) MG_TR(64 + 3 * conv);
+                }
                 ok &= mbar_wait(&full[s], ph);
                 tc_fence_after();
                 if (ch == 0 && iw == 0) MG_TR(65 + 3 * conv);
@@ -208,18 +225,24 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
 
         if (warp == 0) MG_TR(0);
         // ---- load the input tile: R <- x (fp32, exact), X <- split(lrelu(x))
+        // an item (blk, part) owns, in every channel half h, the CH = CW/NH columns  h*C/NH + part*CH .. + CH
+        constexpr int NH = Cfg::NH, CH = CW / NH;
 #pragma unroll 1
         for (int it = wg; it < ITEMS; it += NWG) {
-            const int blk = it / PARTS, cbeg = (it % PARTS) * CW;
+            const int blk = it / PARTS, part = it % PARTS;
             const int p = blk * 128 + row, t = o + p;
             const bool inr = (t >= 0 && t < L);
             const float *xp = x + (size_t)b * C * L + (inr ? t : 0);
             // all CW loads of the item are issued before the first use: one memory round trip, not CW/16
             uint32_t v[CW];
 #pragma unroll
-            for (int j = 0; j < CW; ++j) v[j] = inr ? __float_as_uint(__ldg(xp + (size_t)(cbeg + j) * L)) : 0u;
+            for (int j = 0; j < CW; ++j) {
+                const int col = (j / CH) * (C / NH) + part * CH + j % CH;
+                v[j] = inr ? __float_as_uint(__ldg(xp + (size_t)col * L)) : 0u;
+            }
 #pragma unroll
             for (int c0 = 0; c0 < CW; c0 += 16) {
+                const int col0 = (c0 / CH) * (C / NH) + part * CH + c0 % CH;
                 uint32_t w[16];
                 float f[16];
 #pragma unroll
@@ -227,21 +250,23 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
                     w[j] = v[c0 + j];
                     f[j] = lrelu(__uint_as_float(v[c0 + j]));
                 }
-                tmem_st16(lane_addr + blk * 2 * C + cbeg + c0, w);
-                store_x16(Xh, Xl, XPITCH, cbeg + c0, (p + SLACK) * 16, f);
+                tmem_st16(lane_addr + blk * 2 * C + col0, w);
+                store_x16(Xh, Xl, XPITCH, col0, (p + SLACK) * 16, f);
             }
         }
         tmem_st_wait();
+        fence_proxy_async();
+        tc_fence_before();
+        for (int h = 0; h < NH; ++h) mbar_arrive(&xready[h]);  // conv 0 may start (phase 0 of both halves)
         if (warp == 0) MG_TR(1);
 
         bool ok = true;
 #pragma unroll 1
         for (int conv = 0; conv < 6; ++conv) {
-            fence_proxy_async();
-            tc_fence_before();
             if (warp == 0) MG_TR(2 + 3 * conv);
-            named_bar_sync(1, NEPI + 32 * NIW);  // hand X to the MMA warps
-            // while the tensor core works: stage this conv's bias (c1: its own; c2: fold into pend)
+            // X for this conv has been handed to the MMA warps through xready[] (by the load pass or the previous
+            // iteration).  While the tensor core works: stage this conv's bias (c1: its own; c2: fold into pend).
+            // (pend and b1s alternate between iterations, so a fast thread never overwrites what a slow one still reads.)
             const float *bias = packed + bias_offset(l0 + (conv >> 1) + 3 * (conv & 1));
             if (conv & 1) {
                 for (int c = tid; c < C; c += NEPI) pend[c] += __ldg(bias + c);
@@ -256,21 +281,28 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
             const uint32_t scol = (conv & 1) ? 0 : C;  // next input comes from R (after c2) or D1 (after c1)
             const float *bsrc = (conv & 1) ? pend : b1s;
 #pragma unroll 1
-            for (int it = wg; it < ITEMS; it += NWG) {
-                const int blk = it / PARTS, cbeg = (it % PARTS) * CW;
-                const int p = blk * 128 + row, t = o + p;
-                const bool inr = (t >= 0 && t < L);
+            for (int h = 0; h < NH; ++h) {
 #pragma unroll 1
-                for (int c0 = cbeg; c0 < cbeg + CW; c0 += 32) {
-                    uint32_t v[32];
-                    float f[32];
-                    tmem_ld32(lane_addr + blk * 2 * C + scol + c0, v);
-                    tmem_ld_wait();
+                for (int it = wg; it < ITEMS; it += NWG) {
+                    const int blk = it / PARTS, cbeg = h * (C / NH) + (it % PARTS) * CH;
+                    const int p = blk * 128 + row, t = o + p;
+                    const bool inr = (t >= 0 && t < L);
+#pragma unroll 1
+                    for (int c0 = cbeg; c0 < cbeg + CH; c0 += 32) {
+                        uint32_t v[32];
+                        float f[32];
+                        tmem_ld32(lane_addr + blk * 2 * C + scol + c0, v);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = inr ? lrelu(__uint_as_float(v[j]) + bsrc[c0 + j]) : 0.f;
-                    store_x16(Xh, Xl, XPITCH, c0, (p + SLACK) * 16, f);
-                    store_x16(Xh, Xl, XPITCH, c0 + 16, (p + SLACK) * 16, f + 16);
+                        for (int j = 0; j < 32; ++j) f[j] = inr ? lrelu(__uint_as_float(v[j]) + bsrc[c0 + j]) : 0.f;
+                        store_x16(Xh, Xl, XPITCH, c0, (p + SLACK) * 16, f);
+                        store_x16(Xh, Xl, XPITCH, c0 + 16, (p + SLACK) * 16, f + 16);
+                    }
                 }
+                // channels [h*C/NH, (h+1)*C/NH) of the next conv's input are in place: let its MMAs start on them
+                fence_proxy_async();
+                tc_fence_before();
+                mbar_arrive(&xready[h]);
             }
             if (warp == 0) MG_TR(4 + 3 * conv);
         }

@@ -129,3 +129,24 @@ def test_discriminators_refuse_cpu_tensors():
         d(torch.zeros(1, 1, 64), torch.zeros(1, 1, 64))
     with pytest.raises(engine.EngineError):
         d.discriminators[0](torch.zeros(1, 1, 64))
+
+
+def test_cabi_argument_errors_are_reported_not_thrown():
+    """Error behaviour of the C ABI that needs no GPU: negative return code + message, never an exception or exit."""
+    L = engine.lib()
+    lens = (ctypes.c_int * 21)()
+    assert L.mg_msd_lengths(0, lens) == -1 and b"mg_msd_lengths" in L.mg_last_error_string()
+    assert L.mg_msd_lengths(8192, lens) == 0
+    assert [lens[i] for i in range(7)] == [8192, 2048, 512, 128, 128, 128, 128]
+    assert [lens[7 + i] for i in range(7)] == [4097, 1025, 257, 65, 65, 65, 65]
+    assert [lens[14 + i] for i in range(7)] == [1025, 257, 65, 17, 17, 17, 17]
+    assert engine.msd_lengths(1031)[2][6] >= 1
+    # null / bad-shape arguments of the device-pointer entry points are rejected before any CUDA call
+    assert L.mg_gen_forward(None, None, None, 1, 1, None, 0, None) == -1
+    assert L.mg_gen_forward(ctypes.c_void_p(256), ctypes.c_void_p(256), ctypes.c_void_p(256), 0, 4,
+                            ctypes.c_void_p(256), 1 << 30, None) == -1
+    assert b"B >= 1" in L.mg_last_error_string()
+    assert L.mg_gen_forward(ctypes.c_void_p(256), ctypes.c_void_p(256), ctypes.c_void_p(256), 1, 4,
+                            ctypes.c_void_p(256), 16, None) == -4  # MG_ERR_WORKSPACE_TOO_SMALL
+    assert L.mg_gen_kernel_name(0) == b"conv_pre" and L.mg_gen_kernel_name(99) == b""
+    assert L.mg_gen_forward_launches() == 9
