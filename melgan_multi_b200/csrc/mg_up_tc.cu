@@ -241,11 +241,183 @@ static int launch_convt(const float *x, float *y, const float *packed, int B, in
     return MG_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Variant for a stage whose whole activation tile fits in shared memory (stage 1: 129 rows x 256 channels, hi+lo =
+// 136 KB): the A operand is converted ONCE per row tile and stays resident, and the CTA loops over the NCG output-channel
+// groups with the accumulators double-buffered in TMEM (2 x 256 columns), so the epilogue (TMEM -> coalesced vector
+// stores) of group g overlaps the MMAs of group g+1 and no activation is loaded or converted twice.
+template <class Cfg>
+__global__ void __launch_bounds__(192, 1)
+convt_resident_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const float *__restrict__ packed, int Lin, int B,
+                         int *__restrict__ status) {
+    constexpr int CIN = Cfg::CIN, COUT = Cfg::COUT, S = Cfg::S, PAD = Cfg::PAD, NG = Cfg::NG, N = Cfg::N, NCG = Cfg::NCG;
+    constexpr int ROWS = 128, APITCH = Cfg::APITCH, BSLOT = Cfg::BSLOT, NCHUNK = Cfg::NCHUNK;
+    constexpr int KPT = CIN / 8;                    // k-panels of the resident A
+    constexpr int AHALF = KPT * APITCH;             // bytes of one of {hi, lo}
+    constexpr int NSB = 2, NCONV = 128;
+    static_assert(S == 8 && N == 256 && 2 * AHALF + NSB * BSLOT + 256 <= 227 * 1024, "resident ConvT shape");
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *abuf = smem, *bring = smem + 2 * AHALF;
+    uint64_t *fullA = reinterpret_cast<uint64_t *>(bring + NSB * BSLOT);  // [CIN/64]: a 64-channel slice of A is written
+    uint64_t *fullB = fullA + CIN / 64, *emptyB = fullB + NSB, *done = emptyB + NSB, *tfree = done + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tfree + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int r0 = blockIdx.x * ROWS;
+    const int Lout = Lin * S, Lv = Lin + 1;
+
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    if (tid == 32) {
+        for (int s = 0; s < CIN / 64; ++s) mbar_init(&fullA[s], NCONV);
+        for (int s = 0; s < NSB; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&done[s], 1); mbar_init(&tfree[s], NCONV); }
+        fence_mbar_init();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == NCONV / 32) {
+        // ================= TMA producer: B slots of every channel group, in consumption order =================
+        if (lane == 0) {
+            const uint8_t *src = reinterpret_cast<const uint8_t *>(packed) + tc_region_start() + tc_up_offset(Cfg::STAGE);
+            int s = 0, ph = 0;
+            bool ok = true;
+            for (int i = 0; i < NCG * NCHUNK && ok; ++i) {  // blob order is [cg][chunk]: exactly this loop
+                if (!mbar_wait(&emptyB[s], ph ^ 1)) { ok = false; break; }
+                mbar_arrive_expect_tx(&fullB[s], BSLOT);
+                bulk_g2s(bring + s * BSLOT, src + (size_t)i * BSLOT, BSLOT, &fullB[s]);
+                if (++s == NSB) { s = 0; ph ^= 1; }
+            }
+            if (!ok) atomicExch(status, 32);
+        }
+    } else if (warp == NCONV / 32 + 1) {
+        // ================= MMA issuer =================
+        const uint32_t idesc = make_idesc_bf16(128, N);
+        const uint64_t adesc_t = desc_template(APITCH, 128), bdesc_t = desc_template(N * 16, 128);
+        const uint32_t a_addr = smem_u32(abuf), bring_addr = smem_u32(bring);
+        int sb = 0, phb = 0;
+        bool ok = true;
+#pragma unroll 1
+        for (int cg = 0; cg < NCG; ++cg) {
+            const int buf = cg & 1, use = cg >> 1;
+            if (use > 0) {  // the epilogue must have drained this accumulator buffer (group cg - 2)
+                ok &= mbar_wait(&tfree[buf], (use - 1) & 1);
+                tc_fence_after();
+            }
+#pragma unroll 1
+            for (int ch = 0; ch < NCHUNK; ++ch) {
+                if (cg == 0 && (ch & 3) == 0) {  // first pass only: wait for the 64-channel slice of A
+                    ok &= mbar_wait(&fullA[ch >> 2], 0);
+                    tc_fence_after();
+                }
+                ok &= mbar_wait(&fullB[sb], phb);
+                tc_fence_after();
+                const uint64_t bbase = desc_at(bdesc_t, bring_addr + sb * BSLOT);
+                const uint64_t abase = desc_at(adesc_t, a_addr + 2 * ch * APITCH);
+#pragma unroll
+                for (int tap = 0; tap < 2; ++tap)
+#pragma unroll
+                    for (int pass = 0; pass < 3; ++pass) {
+                        const uint64_t bdesc = bbase + (uint64_t)((((tap * 2 + (pass == 2)) * 2) * N * 16) >> 4);
+                        const uint64_t adesc = abase + (uint64_t)((((pass == 1) ? AHALF : 0) + (1 - tap) * 16) >> 4);
+                        const bool acc = !(ch == 0 && tap == 0 && pass == 0);
+                        if (elect_one()) mma_bf16(tmem + buf * N, adesc, bdesc, idesc, acc);
+                    }
+                if (elect_one()) mma_commit(&emptyB[sb]);
+                if (++sb == NSB) { sb = 0; phb ^= 1; }
+            }
+            if (elect_one()) mma_commit(&done[buf]);
+        }
+        if (!ok && lane == 0) atomicExch(status, 33);
+    } else if (warp < NCONV / 32) {
+        // ================= converter: the whole A tile, once =================
+#pragma unroll 1
+        for (int ca = 0; ca < CIN / 64; ++ca) {
+#pragma unroll 1
+            for (int i = tid; i <= ROWS; i += NCONV) {
+                const int v = r0 - 1 + i;
+                const int item = v >= 0 ? v / Lv : 0, s = v - item * Lv;
+                const bool inr = (v >= 0 && item < B && s < Lin);
+                const float *xp = x + ((size_t)(inr ? item : 0) * CIN + ca * 64) * Lin + (inr ? s : 0);
+                float f[64];
+#pragma unroll
+                for (int j = 0; j < 64; ++j) f[j] = inr ? __ldg(xp + (size_t)j * Lin) : 0.f;
+#pragma unroll
+                for (int kp = 0; kp < 8; ++kp) {
+                    uint32_t h[4], l[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) split2_bf16(lrelu(f[8 * kp + 2 * e]), lrelu(f[8 * kp + 2 * e + 1]), h[e], l[e]);
+                    *reinterpret_cast<uint4 *>(abuf + (ca * 8 + kp) * APITCH + i * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+                    *reinterpret_cast<uint4 *>(abuf + AHALF + (ca * 8 + kp) * APITCH + i * 16) = make_uint4(l[0], l[1], l[2], l[3]);
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(&fullA[ca]);
+        }
+        // ================= epilogue per channel group (overlaps the next group's MMAs) =================
+        const int q = warp & 3;
+        const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+        const int v = r0 + q * 32 + lane;
+        const int item = v / Lv, s = v - item * Lv;
+        const bool row_ok = item < B;
+        const int t0 = S * s - PAD;
+        const bool lo_ok = row_ok && s >= 1, hi_ok = row_ok && s <= Lin - 1;
+        bool ok = true;
+#pragma unroll 1
+        for (int cg = 0; cg < NCG; ++cg) {
+            const int buf = cg & 1, use = cg >> 1;
+            if (ok && !mbar_wait(&done[buf], use & 1)) { ok = false; if (lane == 0) atomicExch(status, 35); }
+            tc_fence_after();
+            const float *bias = packed + bias_offset(1 + Cfg::STAGE) + cg * NG;
+            float *yb = y + ((size_t)(row_ok ? item : 0) * COUT + cg * NG) * Lout;
+#pragma unroll 1
+            for (int j0 = 0; j0 < NG; j0 += 8) {
+                uint32_t w[8][8];
+#pragma unroll
+                for (int phi = 0; phi < 8; ++phi) tmem_ld8(lane_addr + buf * N + phi * NG + j0, w[phi]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float bj = __ldg(bias + j0 + j);
+                    float *yp = yb + (size_t)(j0 + j) * Lout + t0;
+                    if (lo_ok)
+                        *reinterpret_cast<float4 *>(yp) = make_float4(__uint_as_float(w[0][j]) + bj, __uint_as_float(w[1][j]) + bj,
+                                                                      __uint_as_float(w[2][j]) + bj, __uint_as_float(w[3][j]) + bj);
+                    if (hi_ok)
+                        *reinterpret_cast<float4 *>(yp + 4) = make_float4(__uint_as_float(w[4][j]) + bj, __uint_as_float(w[5][j]) + bj,
+                                                                          __uint_as_float(w[6][j]) + bj, __uint_as_float(w[7][j]) + bj);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tfree[buf]);  // accumulator buffer may be overwritten by group cg + 2
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+template <class Cfg>
+static int launch_convt_resident(const float *x, float *y, const float *packed, int B, int Lin, int *status, cudaStream_t s) {
+    constexpr int smem = 2 * (Cfg::CIN / 8) * Cfg::APITCH + 2 * Cfg::BSLOT + (Cfg::CIN / 64 + 2 * 2 + 4) * 8 + 16;
+    static bool configured = false;
+    if (!configured) {
+        MG_CUDA_TRY(cudaFuncSetAttribute(convt_resident_tc_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    const long long vrows = (long long)B * (Lin + 1);
+    convt_resident_tc_kernel<Cfg><<<(unsigned)((vrows + 127) / 128), 192, smem, s>>>(x, y, packed, Lin, B, status);
+    MG_CUDA_TRY(cudaGetLastError());
+    return MG_OK;
+}
+
 // x [B][Cin][Lin] -> y [B][Cout][S*Lin], fp32 NCL, (Cin, Cout, S) of generator stage `stage`.
 int launch_convt_tc(const float *x, float *y, const float *packed, int stage, int B, int Lin, int *status, cudaStream_t s) {
     switch (stage) {
         case 0: return launch_convt<UpCfg<0>>(x, y, packed, B, Lin, status, s);
-        case 1: return launch_convt<UpCfg<1>>(x, y, packed, B, Lin, status, s);
+        case 1: return launch_convt_resident<UpCfg<1>>(x, y, packed, B, Lin, status, s);
         case 2: return launch_convt<UpCfg<2>>(x, y, packed, B, Lin, status, s);
         case 3: return launch_convt<UpCfg<3>>(x, y, packed, B, Lin, status, s);
     }
