@@ -379,7 +379,9 @@ def main():
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": ("f32 in/out; products as 3 split-bf16 tcgen05 passes with fp32 accumulation (fp32-equivalent, ~1e-5)"
+                      if tc_path else "f32"),
+            "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "mel_frames": T, "global_batch": B * world,
                        "parallelism": "dp%d (independent batches, no collective)" % world,
                        "l2": "flushed between steps (256 MiB memset)", "weights": "seeded random init"},

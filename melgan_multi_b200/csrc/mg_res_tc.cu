@@ -113,6 +113,7 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
     const int o = blockIdx.x == 0 ? 0 : (P - HALO) + ((int)blockIdx.x - 1) * Cfg::PVALID - HALO;  // position of tile-local p = 0
     const int p_lo = blockIdx.x == 0 ? 0 : HALO;
     const int p_hi = (o + P >= L) ? P : P - HALO;  // first tile-local row that is NOT a valid output
+    const bool interior = (o >= 0 && o + P <= L);  // every row of the tile is a real position
     // consumption order of the six convs of ResBlock `stage`: c1[0], c2[0], c1[1], c2[1], c1[2], c2[2]
     const int l0 = 5 + 6 * stage;
     const uint8_t *tc_base = reinterpret_cast<const uint8_t *>(packed) + tc_region_start();
@@ -293,8 +294,13 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
                         float f[32];
                         tmem_ld32(lane_addr + blk * 2 * C + scol + c0, v);
                         tmem_ld_wait();
+                        if (interior) {  // whole tile inside [0, L): no zero-padding mask needed (CTA-uniform branch)
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = inr ? lrelu(__uint_as_float(v[j]) + bsrc[c0 + j]) : 0.f;
+                            for (int j = 0; j < 32; ++j) f[j] = lrelu(__uint_as_float(v[j]) + bsrc[c0 + j]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] = inr ? lrelu(__uint_as_float(v[j]) + bsrc[c0 + j]) : 0.f;
+                        }
                         store_x16(Xh, Xl, XPITCH, c0, (p + SLACK) * 16, f);
                         store_x16(Xh, Xl, XPITCH, c0 + 16, (p + SLACK) * 16, f + 16);
                     }

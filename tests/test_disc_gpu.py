@@ -104,3 +104,17 @@ def test_msd_backward_reaches_parameters_and_input(msd_module):
     for n, p in msd_module.named_parameters():
         assert p.grad is not None and torch.isfinite(p.grad).all(), n
     msd_module.zero_grad()
+
+
+def test_msd_is_deterministic_and_batch_items_are_independent(msd_module):
+    y = torch.from_numpy(synth.audio_input(3, 1500, 11)).cuda()
+    yh = torch.from_numpy(synth.audio_input(3, 1500, 12)).cuda()
+    with torch.no_grad():
+        a = msd_module(y, yh)
+        b = msd_module(y, yh)
+        one = msd_module(y[1:2], yh[1:2])
+    for i in range(3):
+        assert torch.equal(a[0][i], b[0][i]) and torch.equal(a[1][i], b[1][i])
+        for j in range(7):
+            assert torch.equal(a[2][i][j], b[2][i][j]) and torch.equal(a[3][i][j], b[3][i][j])
+            assert torch.equal(a[2][i][j][1:2], one[2][i][j]) and torch.equal(a[3][i][j][1:2], one[3][i][j])

@@ -150,3 +150,22 @@ def test_backward_reaches_every_parameter(gen_module):
     for n, p in gen_module.named_parameters():
         assert p.grad is not None and torch.isfinite(p.grad).all(), n
     gen_module.zero_grad()
+
+
+def test_deterministic_stream_ordered_and_layout_robust(gen_module):
+    """Bitwise run-to-run determinism (no atomics on the data path), correct ordering on a non-default stream, and
+    non-contiguous inputs (the shim makes them contiguous like the reference's Conv1d would accept them)."""
+    x = torch.from_numpy(synth.mel_input(3, 9, 21)).cuda()
+    with torch.no_grad():
+        y0 = gen_module(x).clone()
+        y1 = gen_module(x).clone()
+        assert torch.equal(y0, y1)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            y2 = gen_module(x * 1.0)  # producer and consumer both on the side stream
+        torch.cuda.current_stream().wait_stream(s)
+        assert torch.equal(y0, y2)
+        xt = x.transpose(1, 2).contiguous().transpose(1, 2)  # same values, non-contiguous strides
+        assert not xt.is_contiguous()
+        assert torch.equal(gen_module(xt), y0)
