@@ -66,7 +66,7 @@ struct RbCfg {
     static constexpr int SMEM_BYTES = 2 * XBYTES + NSTAGE * CHUNK + 2 * C * 4 + (2 * NSTAGE + 1 + NH) * 8 + 16;
     static_assert(KSL % NH == 0 && (CW / NH) % 32 == 0 && (NH == 1 || ITEMS == NWG), "hand-off split");
     static_assert(MINB * (SMEM_BYTES + 1024) <= 228 * 1024, "shared memory budget");
-    static_assert(MINB * TCOLS <= 512 && (TCOLS == 256 || TCOLS == 512), "TMEM budget");
+    static_assert(MINB * TCOLS <= 512 && (TCOLS == 128 || TCOLS == 256 || TCOLS == 512), "TMEM budget");
     static_assert(XPITCH / 16 < 16384, "LBO field");
     static_assert(CW % 32 == 0 && ITEMS % NWG == 0, "epilogue split");
 };
@@ -408,6 +408,7 @@ int launch_resblock_tc(const float *x, float *y, const float *packed, int stage,
         //                                       C  NBLK NSTAGE NWG MINB
         case 0: return launch_resblock<RbCfg<256, 1, 4, 4, 1>>(x, y, packed, stage, B, L, status, trace, s);
         case 1: return launch_resblock<RbCfg<128, 2, 4, 4, 1>>(x, y, packed, stage, B, L, status, trace, s);
+        // (3 CTAs/SM with half-size tiles was measured slower for C = 64 / 32: the extra halo recompute outweighs the overlap)
         case 2: return launch_resblock<RbCfg<64, 2, 2, 2, 2>>(x, y, packed, stage, B, L, status, trace, s);
         case 3: return launch_resblock<RbCfg<32, 4, 4, 2, 2>>(x, y, packed, stage, B, L, status, trace, s);
         // stage 4 = ResBlock 3 with LeakyReLU -> conv_post -> tanh fused: y is the audio [B][1][L]

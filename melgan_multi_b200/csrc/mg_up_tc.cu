@@ -40,13 +40,15 @@ struct UpCfg {
     // stride-8 stages: 32 KB B slots, so one CTA per SM with a deep ring and 64-channel A slots (one memory round trip
     // per 64 channels); stride-2 stages: small slots, two CTAs per SM hide each other's loads and stores.
     static constexpr int MINB = (S == 8) ? 1 : 2;
-    static constexpr int KCA = (S == 8) ? 64 : 16;        // channels per A slot
+    // channels per A slot = channels fetched per memory round trip of a converter thread (measured: 16 -> 32 helps the
+    // stride-2 stages; a single 64-channel slot for stage 3 loses the conversion/MMA overlap and is slower)
+    static constexpr int KCA = (S == 8) ? 64 : 32;
     static constexpr int ROWS = 128 * NB;
     static constexpr int AROWS = ROWS + 8;                // row index i <-> virtual position r0 - 1 + i, i in [0, ROWS]
     static constexpr int APITCH = AROWS * 16;             // bytes between k-panels
     static constexpr int ASLOT = 2 * (KCA / 8) * APITCH;  // [half: hi, lo][k-panel][AROWS][16 B]
     static constexpr int BSLOT = up_slot_bytes(STAGE);    // [tap][half][k-panel: 2][N][16 B]
-    static constexpr int NSA = 2, NSB = (S == 8) ? 4 : 3;
+    static constexpr int NSA = (CIN == KCA) ? 1 : 2, NSB = (S == 8) ? 4 : (CIN >= 128 ? 2 : 3);
     static constexpr int NCHUNK = CIN / 16;               // B slots per tile
     static constexpr int NWG = NB >= 2 ? 2 : 1;
     static constexpr int NCONV = 128 * NWG;               // converter / epilogue threads
