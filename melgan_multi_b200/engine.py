@@ -318,6 +318,23 @@ class GeneratorHost:
         """Raw host pointers (e.g. pinned torch tensors' data_ptr())."""
         check(lib().mg_gen_engine_forward(self._h, mel_ptr, out_ptr, B, T))
 
+    HALO_FRAMES = 8  # the generator's receptive field is +-7 mel frames (SURVEY section 5); 8 for slack
+
+    def stream(self, mel, chunk_frames=128):
+        """Long-utterance streaming (BASELINE config 5): yields the audio of `mel` [1, 80, T] chunk by chunk, each chunk
+        computed from its frames plus an 8-frame halo either side, so latency and memory are bounded by the chunk and the
+        concatenation equals the whole-utterance result (every conv of the fused stages re-applies its zero padding only
+        at the true ends, which a chunk touching an end reproduces exactly)."""
+        mel = np.ascontiguousarray(mel, dtype=np.float32)
+        if mel.ndim != 3 or mel.shape[0] != 1 or mel.shape[1] != 80:
+            raise EngineError("stream() takes one utterance [1, 80, T]")
+        T, h = mel.shape[2], self.HALO_FRAMES
+        for lo in range(0, T, chunk_frames):
+            hi = min(T, lo + chunk_frames)
+            a, b = max(0, lo - h), min(T, hi + h)
+            audio = self.forward(mel[:, :, a:b])
+            yield audio[:, :, (lo - a) * 256:(lo - a + hi - lo) * 256]
+
     def last_kernel_ms(self):
         ms = ctypes.c_float()
         check(lib().mg_gen_engine_last_kernel_ms(self._h, ctypes.byref(ms)))

@@ -1,0 +1,6 @@
+# ncu --set full over every kernel of one generator forward + one MSD forward (inside the NVTX range "measured")
+mkdir -p gpurun_out; cd "${GRAFT_REPO_ROOT:-.}"
+timeout 1500 ncu --set full --clock-control none --nvtx --nvtx-include "measured/" -o gpurun_out/prof_all python scripts/one_forward_each.py > gpurun_out/ncu_all.log 2>&1
+tail -3 gpurun_out/ncu_all.log
+ncu -i gpurun_out/prof_all.ncu-rep --page raw --csv > gpurun_out/prof_all_raw.csv 2>/dev/null
+python scripts/ncu_key_metrics.py gpurun_out/prof_all_raw.csv > gpurun_out/prof_all_key_metrics.txt; grep -c "^==" gpurun_out/prof_all_key_metrics.txt

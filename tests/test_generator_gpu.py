@@ -169,3 +169,12 @@ def test_deterministic_stream_ordered_and_layout_robust(gen_module):
         xt = x.transpose(1, 2).contiguous().transpose(1, 2)  # same values, non-contiguous strides
         assert not xt.is_contiguous()
         assert torch.equal(gen_module(xt), y0)
+
+
+def test_streaming_long_utterance_equals_whole(host_engine):
+    """BASELINE config 5 (80 x 1000 mel, 11.6 s): chunked streaming with an 8-frame halo == the whole utterance."""
+    mel = synth.mel_input(1, 1000, 0)
+    whole = host_engine.forward(mel)
+    chunks = list(host_engine.stream(mel, chunk_frames=96))
+    assert len(chunks) == 11 and sum(c.shape[2] for c in chunks) == 256000
+    np.testing.assert_allclose(np.concatenate(chunks, axis=2), whole, rtol=0, atol=1e-6)
