@@ -136,8 +136,98 @@ static int run_case(int dil, int variant, int passes) {
     return (st == 0 && maxerr / maxref < (passes == 3 ? 2e-5 : 2e-2)) ? 0 : 1;
 }
 
+// Toeplitz operand: the k-panels of A OVERLAP (panel j of row m is the 16-byte unit m + j of one linear buffer, i.e. the
+// descriptor's LBO is 16 bytes, equal to the row pitch).  This is what a strided / grouped conv with a channels-last
+// input looks like (row m = a sliding window), and it needs no im2col if the hardware accepts it.
+//     D[m][n] = sum_{j<6} sum_{e<8} U[m + j][e] * W[n][j*8 + e],   M = 128, N = 16, K = 48 (3 MMAs per pass)
+__global__ void __launch_bounds__(128, 1)
+probe_toeplitz(const float *__restrict__ U, const float *__restrict__ W, float *__restrict__ out, int *status) {
+    constexpr int NU = 144, N = 16, KP = 6;
+    __shared__ __align__(128) uint8_t Uh[NU * 16], Ul[NU * 16], Wh[KP * N * 16], Wl[KP * N * 16];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) tmem_alloc(&tmem_base_s, 32);
+    if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    for (int u = tid; u < NU; u += 128) {
+        uint32_t h[4], l[4];
+        for (int e = 0; e < 4; ++e) split2_bf16(U[u * 8 + 2 * e], U[u * 8 + 2 * e + 1], h[e], l[e]);
+        *reinterpret_cast<uint4 *>(Uh + u * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4 *>(Ul + u * 16) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+    for (int idx = tid; idx < KP * N; idx += 128) {
+        const int n = idx % N, kp = idx / N;
+        uint32_t h[4], l[4];
+        for (int e = 0; e < 4; ++e) split2_bf16(W[n * 48 + kp * 8 + 2 * e], W[n * 48 + kp * 8 + 2 * e + 1], h[e], l[e]);
+        *reinterpret_cast<uint4 *>(Wh + (kp * N + n) * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4 *>(Wl + (kp * N + n) * 16) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    if (tid == 0) {
+        const uint32_t idesc = make_idesc_bf16(128, N);
+        bool acc = false;
+        for (int pass = 0; pass < 3; ++pass)
+            for (int k = 0; k < 3; ++k) {
+                const uint32_t a_addr = smem_u32(pass == 1 ? Ul : Uh) + (2 * k) * 16;           // panel 2k of row 0 = unit 2k
+                const uint32_t b_addr = smem_u32(pass == 2 ? Wl : Wh) + (2 * k) * (N * 16);
+                mma_bf16(tmem, make_desc(a_addr, /*LBO: next k-panel = next unit*/ 16, 128), make_desc(b_addr, N * 16, 128), idesc, acc);
+                acc = true;
+            }
+        mma_commit(&bar);
+    }
+    const bool ok = mbar_wait(&bar, 0, 1u << 22);
+    tc_fence_after();
+    if (!ok) {
+        if (tid == 0) atomicExch(status, 1);
+    } else {
+        uint32_t v[16];
+        tmem_ld16(tmem + ((uint32_t)(32 * warp) << 16), v);
+        tmem_ld_wait();
+        for (int j = 0; j < 16; ++j) out[(32 * warp + lane) * N + j] = __uint_as_float(v[j]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 32);
+}
+
+static int run_toeplitz() {
+    std::vector<float> U(144 * 8), W(16 * 48), out(128 * 16, 0.f);
+    srand(77);
+    for (auto &v : U) v = (rand() / (float)RAND_MAX) * 2.f - 1.f;
+    for (auto &v : W) v = ((rand() / (float)RAND_MAX) * 2.f - 1.f) / 7.f;
+    float *dU, *dW, *dO;
+    int *dS, st = 0;
+    cudaMalloc(&dU, U.size() * 4); cudaMalloc(&dW, W.size() * 4); cudaMalloc(&dO, out.size() * 4); cudaMalloc(&dS, 4);
+    cudaMemcpy(dU, U.data(), U.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dW, W.data(), W.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemset(dS, 0, 4);
+    probe_toeplitz<<<1, 128>>>(dU, dW, dO, dS);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("toeplitz: CUDA ERROR %s\n", cudaGetErrorString(e)); return 2; }
+    cudaMemcpy(out.data(), dO, out.size() * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(&st, dS, 4, cudaMemcpyDeviceToHost);
+    double maxerr = 0, maxref = 0;
+    for (int m = 0; m < 128; ++m)
+        for (int n = 0; n < 16; ++n) {
+            double s = 0;
+            for (int j = 0; j < 6; ++j)
+                for (int el = 0; el < 8; ++el) s += (double)U[(m + j) * 8 + el] * W[n * 48 + j * 8 + el];
+            maxerr = fmax(maxerr, fabs(s - out[m * 16 + n]));
+            maxref = fmax(maxref, fabs(s));
+        }
+    const bool good = st == 0 && maxerr / maxref < 2e-5;
+    printf("toeplitz (LBO = 16 B, overlapping k-panels) N=16 K=48: timeout=%d max|err|/max|ref| = %.3e %s\n", st, maxerr / maxref,
+           good ? "OK" : "MISMATCH");
+    return good ? 0 : 1;
+}
+
 int main() {
     int bad = 0;
+    bad += run_toeplitz();
     // which LBO/SBO assignment is right (variant 0 expected), single pass first
     for (int variant = 0; variant < 2; ++variant) bad += run_case<64, 64>(1, variant, 1) && variant == 0;
     for (int dil : {1, 3, 9}) {
