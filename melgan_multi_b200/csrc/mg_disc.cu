@@ -50,6 +50,18 @@ __global__ void __launch_bounds__(128) disc_pack_kernel(DiscPackArgs a, uint8_t 
         const int cog = sh.cout / sh.groups, grp = row / cog, col = row % cog;
         for (int j = threadIdx.x; j < inner; j += blockDim.x)  // j = ci*41 + tap -> [grp][ci][tap][col]
             fw[((size_t)grp * inner + j) * cog + col] = scale * vr[j];
+        if (l <= 3) {  // split-bf16 Toeplitz copy for the tcgen05 kernel (layout: mg_layout.h d_gtc_index), zeros included
+            __nv_bfloat16 *gt = reinterpret_cast<__nv_bfloat16 *>(blob + d_gtc_start() + d_gtc_offset(l) + (size_t)grp * d_gtc_group_bytes());
+            for (int s = threadIdx.x; s < kDgPanels * 64; s += blockDim.x) {
+                const int ci = s & 3, pos = (s >> 2) & 1, e = (s >> 3) & 1, r = (s >> 4) & 3, kp = s >> 6;
+                const int q = 2 * kp + pos - 1 - e, k = 4 * q + r;
+                const float wv = (q >= 0 && k <= 40) ? scale * vr[ci * 41 + k] : 0.f;
+                __nv_bfloat16 hi, lo;
+                tc::split_bf16(wv, hi, lo);
+                gt[d_gtc_index(kp, r, e * 16 + col, pos, ci)] = hi;
+                gt[d_gtc_index(kp, r, 32 + e * 16 + col, pos, ci)] = lo;
+            }
+        }
     } else if (l == 5) {
         __nv_bfloat16 *tcw = reinterpret_cast<__nv_bfloat16 *>(blob + d_tc_start());
         for (int j = threadIdx.x; j < inner; j += blockDim.x) {
@@ -283,6 +295,8 @@ int launch_msd_forward(const void *packed, const float *y, int Bt, int L, float 
     int lens[3 * kDiscLayers];
     msd_lengths(L, lens);
     const int L1 = (L + 4 - 4) / 2 + 1, L2 = (L1 + 4 - 4) / 4 + 1;
+    const char *gp = getenv("MG_DISC_GROUP");
+    const bool group_tc = !(gp && strcmp(gp, "simt") == 0);
     MG_CUDA_TRY(cudaEventRecord(ss.fork, s));
     for (int sc = 0; sc < 3; ++sc) {
         cudaStream_t q = sc == 0 ? s : ss.st[sc - 1];  // scale 0 (the largest) stays on the caller's stream
@@ -297,9 +311,16 @@ int launch_msd_forward(const void *packed, const float *y, int Bt, int L, float 
         else if (sc == 1) disc_pre_kernel<1><<<gpre, 256, 0, q>>>(y, f[0], fw, L, L1, L2);
         else disc_pre_kernel<2><<<gpre, 256, 0, q>>>(y, f[0], fw, L, L1, L2);
         MG_CUDA_TRY(cudaGetLastError());
-        if ((rc = launch_group<16, 4>(f[0], f[1], fw + d_weight_offset(1), fw + d_bias_offset(1), Bt, 16, 64, ln[0], ln[1], q))) return rc;
-        if ((rc = launch_group<16, 4>(f[1], f[2], fw + d_weight_offset(2), fw + d_bias_offset(2), Bt, 64, 256, ln[1], ln[2], q))) return rc;
-        if ((rc = launch_group<16, 4>(f[2], f[3], fw + d_weight_offset(3), fw + d_bias_offset(3), Bt, 256, 1024, ln[2], ln[3], q))) return rc;
+        for (int l = 1; l <= 3; ++l) {  // stride-4 grouped convs: tcgen05 (MG_DISC_GROUP=simt: the fp32 SIMT second implementation)
+            const DLayer d = d_layer(l);
+            if (group_tc)
+                rc = launch_disc_group_tc(f[l - 1], f[l], blob + d_gtc_start() + d_gtc_offset(l), fw + d_bias_offset(l), Bt, d.cin,
+                                          d.cout, ln[l - 1], ln[l], status, q);
+            else
+                rc = launch_group<16, 4>(f[l - 1], f[l], fw + d_weight_offset(l), fw + d_bias_offset(l), Bt, d.cin, d.cout, ln[l - 1],
+                                         ln[l], q);
+            if (rc) return rc;
+        }
         if ((rc = launch_group<4, 1>(f[3], f[4], fw + d_weight_offset(4), fw + d_bias_offset(4), Bt, 1024, 1024, ln[3], ln[4], q))) return rc;
         if ((rc = launch_disc_post1_tc(f[4], f[5], blob + d_tc_start(), fw + d_bias_offset(5), Bt, ln[4], status, q))) return rc;
         dim3 gp2((ln[5] + 31) / 32, Bt);

@@ -1,0 +1,165 @@
+// Discriminator grouped convs on the tensor cores: Conv1d(k41, stride 4, pad 20, 4 input / 16 output channels per group)
+// + LeakyReLU, layers 1..3 of models.py:78-81,89-95 (groups 4 / 16 / 64), tcgen05 + TMEM, split-bf16.
+//
+// Toeplitz view.  Tap k = 4q + r of output t reads input position 4(t + q - 5) + r, so with the input of one group
+// de-interleaved by phase r into channels-last rows  U_r[u][ci] = x[ci][4u + r]  (8 B per u in bf16), one output is
+//     out[co][t] = sum_r sum_q sum_ci  U_r[t + q - 5][ci] * w[co][ci][4q + r].
+// A 16-byte unit of U_r holds two consecutive u (x 4 ci) = one 8-element k-panel, and rows of an UMMA operand are
+// 16 B = 2 u apart, so TMEM lane m of a tile is the output PAIR t = t0 + 2m + e (e = 0, 1) and both parities read the
+// same A rows:  unit (m + kp) of U_r  x  weights of q = 2 kp + pos - 1 - e  (7 panels cover q = -2..11, zeros outside
+// 0..10; mg_layout.h d_gtc_index).  One K = 16 instruction contracts panel kp of phases r and r + 1 (LBO = the pitch
+// between phase buffers), with N = 64 columns = [w hi | w lo] x parity x 16 co:
+//     pass 0:  A = hi(U),  B = [w hi | w lo]  (N = 64)        pass 1:  A = lo(U),  B = w hi  (N = 32, same columns)
+// = 28 instructions per (group, 256 outputs); the epilogue adds the hi and lo column blocks (fp32-grade: ~4e-6).
+// CTA = 2 groups x 256 outputs of one batch item, 93 KB of shared memory -> two CTAs per SM overlap each other's
+// load / convert, MMA and epilogue phases.  Weights (28 KB per group, contiguous in the packed blob) arrive by bulk TMA.
+#include "mg_common.cuh"
+#include "mg_tc.cuh"
+
+namespace mg {
+using namespace tc;
+
+namespace dg {
+constexpr int NGRP = 2;                       // groups per CTA
+constexpr int TILE = 256;                     // outputs per CTA (128 TMEM lanes x 2 parities)
+constexpr int UNITS = 128 + kDgPanels - 1;    // 16-byte units per phase buffer
+constexpr int XP = UNITS * 16;                // phase-buffer pitch: 536 words = 24 (mod 32) -> conflict-free 8-byte stores
+constexpr int NPOS = UNITS * 8;               // input positions per channel per tile
+constexpr int WBYTES = 28672;                 // d_gtc_group_bytes()
+constexpr int XBYTES = NGRP * 2 * 4 * XP;     // [group][half][phase r][unit][pos 2][ci 4] bf16
+constexpr int NCONV = 256, NT = NCONV + 32;
+constexpr int SMEM_BYTES = NGRP * WBYTES + XBYTES + (1 + NGRP) * 8 + 16;
+static_assert(WBYTES == (int)d_gtc_group_bytes(), "weight block");
+}  // namespace dg
+
+__global__ void __launch_bounds__(dg::NT, 2)
+disc_group_tc_kernel(const float *__restrict__ x, float *__restrict__ out, const uint8_t *__restrict__ wtc,
+                     const float *__restrict__ bias, int Cin, int Cout, int Lin, int Lout, int *__restrict__ status) {
+    using namespace dg;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *wsm = smem, *xsm = smem + NGRP * WBYTES;
+    uint64_t *wbar = reinterpret_cast<uint64_t *>(xsm + XBYTES);
+    uint64_t *done = wbar + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done + NGRP);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int t0 = blockIdx.x * TILE, g0 = blockIdx.y * NGRP, b = blockIdx.z;
+
+    if (warp == 0) tmem_alloc(tmem_slot, NGRP * 64);
+    if (tid == 32) {
+        mbar_init(wbar, 1);
+        for (int g = 0; g < NGRP; ++g) mbar_init(&done[g], 1);
+        fence_mbar_init();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == NCONV / 32) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(wbar, NGRP * WBYTES);
+            bulk_g2s(wsm, wtc + (size_t)g0 * WBYTES, NGRP * WBYTES, wbar);
+        }
+    } else {
+        // U_r[u][ci] of both groups, hi / lo split: item = (group, offset pp from the first position 4 (t0 - 6))
+        const int p0 = 4 * (t0 - 6);
+#pragma unroll 1
+        for (int i = tid; i < NGRP * NPOS; i += NCONV) {
+            const int g = i >= NPOS, pp = i - g * NPOS, p = p0 + pp;
+            const bool in = p >= 0 && p < Lin;
+            const float *xp = x + ((size_t)b * Cin + (g0 + g) * 4) * Lin + (in ? p : 0);
+            float f[4];
+#pragma unroll
+            for (int ci = 0; ci < 4; ++ci) f[ci] = in ? __ldg(xp + (size_t)ci * Lin) : 0.f;
+            uint32_t h0, h1, l0, l1;
+            split2_bf16(f[0], f[1], h0, l0);
+            split2_bf16(f[2], f[3], h1, l1);
+            uint8_t *dst = xsm + ((g * 2) * 4 + (pp & 3)) * XP + (pp >> 2) * 8;
+            *reinterpret_cast<uint2 *>(dst) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2 *>(dst + 4 * XP) = make_uint2(l0, l1);
+        }
+        fence_proxy_async();
+    }
+    __syncthreads();
+
+    if (warp == NCONV / 32) {
+        // ================= MMA issuer (warp-uniform, one elected lane issues) =================
+        bool ok = mbar_wait(wbar, 0);
+        tc_fence_after();
+        const uint32_t idesc64 = make_idesc_bf16(128, 64), idesc32 = make_idesc_bf16(128, 32);
+        const uint64_t adesc_t = desc_template(XP, 128), bdesc_t = desc_template(64 * 16, 128);
+        const uint32_t x_addr = smem_u32(xsm), w_addr = smem_u32(wsm);
+#pragma unroll 1
+        for (int g = 0; g < NGRP; ++g) {
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                const uint64_t a0 = desc_at(adesc_t, x_addr + (g * 2 + pass) * 4 * XP);
+                const uint64_t b0 = desc_at(bdesc_t, w_addr + g * WBYTES);
+#pragma unroll
+                for (int kp = 0; kp < kDgPanels; ++kp) {
+#pragma unroll
+                    for (int rp = 0; rp < 2; ++rp) {
+                        const uint64_t adesc = a0 + (uint64_t)((2 * rp * XP + 16 * kp) >> 4);
+                        const uint64_t bdesc = b0 + (uint64_t)(((kp * 2 + rp) * 2048) >> 4);
+                        if (elect_one()) mma_bf16(tmem + g * 64, adesc, bdesc, pass ? idesc32 : idesc64, (pass | kp | rp) != 0);
+                    }
+                }
+            }
+            if (elect_one()) mma_commit(&done[g]);
+        }
+        if (!ok && lane == 0) atomicExch(status, 31);
+    } else {
+        // ================= epilogue: lane m <-> outputs t0 + 2m, t0 + 2m + 1; warp half <-> 8 of the 16 co =================
+        const int q = warp & 3, ch = warp >> 2;
+        const int t = t0 + 2 * (q * 32 + lane);
+        const bool pair = (Lout & 1) == 0;
+#pragma unroll 1
+        for (int g = 0; g < NGRP; ++g) {
+            if (!mbar_wait(&done[g], 0)) { if (lane == 0) atomicExch(status, 32); break; }
+            tc_fence_after();
+            const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + g * 64 + ch * 8;
+            uint32_t h0[8], h1[8], l0[8], l1[8];
+            tmem_ld8(ta, h0);
+            tmem_ld8(ta + 16, h1);
+            tmem_ld8(ta + 32, l0);
+            tmem_ld8(ta + 48, l1);
+            tmem_ld_wait();
+            const int co0 = (g0 + g) * 16 + ch * 8;
+            float *op = out + ((size_t)b * Cout + co0) * Lout + t;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float bv = __ldg(bias + co0 + j);
+                const float v0 = lrelu(__uint_as_float(h0[j]) + __uint_as_float(l0[j]) + bv);
+                const float v1 = lrelu(__uint_as_float(h1[j]) + __uint_as_float(l1[j]) + bv);
+                float *o = op + (size_t)j * Lout;
+                if (pair && t + 1 < Lout) {
+                    *reinterpret_cast<float2 *>(o) = make_float2(v0, v1);
+                } else {
+                    if (t < Lout) o[0] = v0;
+                    if (t + 1 < Lout) o[1] = v1;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, NGRP * 64);
+}
+
+// x [Bt][Cin][Lin] -> out [Bt][Cout][Lout] = lrelu(grouped conv), layer l in 1..3;  wtc = blob + d_gtc_start() + d_gtc_offset(l)
+int launch_disc_group_tc(const float *x, float *out, const uint8_t *wtc, const float *bias, int Bt, int Cin, int Cout,
+                         int Lin, int Lout, int *status, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        MG_CUDA_TRY(cudaFuncSetAttribute(disc_group_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dg::SMEM_BYTES));
+        configured = true;
+    }
+    if (Bt > 65535) return set_error(MG_ERR_INVALID_ARGUMENT, "discriminator batch %d exceeds 65535", Bt);
+    dim3 grid((Lout + dg::TILE - 1) / dg::TILE, (Cin / 4) / dg::NGRP, Bt);
+    disc_group_tc_kernel<<<grid, dg::NT, dg::SMEM_BYTES, s>>>(x, out, wtc, bias, Cin, Cout, Lin, Lout, status);
+    MG_CUDA_TRY(cudaGetLastError());
+    return MG_OK;
+}
+
+}  // namespace mg

@@ -163,7 +163,24 @@ MG_HD constexpr size_t d_bias_offset(int l) {
 MG_HD constexpr size_t d_fp32_floats() { return d_bias_offset(kDiscLayers); }
 MG_HD constexpr size_t d_tc_start() { return ((d_fp32_floats() * 4 + 255) / 256) * 256; }  // conv_post1, conv_tc_weight_index layout
 MG_HD constexpr size_t d_tc_bytes() { return (size_t)1024 * 1024 * 5 * 4; }
-MG_HD constexpr size_t d_blob_bytes() { return d_tc_start() + d_tc_bytes(); }
+// Tensor-core copy of the stride-4 grouped convs (layers 1..3), one 28 KB block per group (mg_disc_tc.cu):
+//   tap k = 4q + r reads input position 4(t + q - 5) + r, so per input phase r the conv is a Toeplitz contraction over
+//   (q, ci).  K is cut into 7 panels of 8 = 2 consecutive q x 4 ci; one block row n = [hi/lo half][output parity e][co 16]
+//   holds w[co][ci][4q + r] with q = 2*kp + pos - 1 - e (zero outside 0 <= k <= 40): both output parities of a tile read
+//   the same A operand.  Order [kp 7][r pair 2][r & 1][n 64][8 bf16] = one B operand (N = 64, K = 16) per (kp, r pair).
+constexpr int kDgPanels = 7;
+MG_HD constexpr size_t d_gtc_group_bytes() { return (size_t)kDgPanels * 2 * 2 * 64 * 16; }
+MG_HD constexpr size_t d_gtc_index(int kp, int r, int n, int pos, int ci) {  // bf16 element index inside a group block
+    return ((((size_t)(kp * 2 + (r >> 1)) * 2 + (r & 1)) * 64 + n) * 8) + pos * 4 + ci;
+}
+MG_HD constexpr size_t d_gtc_start() { return d_tc_start() + d_tc_bytes(); }
+MG_HD constexpr size_t d_gtc_offset(int l) {  // bytes from d_gtc_start(), l = 1..3
+    size_t o = 0;
+    for (int i = 1; i < l; ++i) o += (size_t)d_layer(i).groups * d_gtc_group_bytes();
+    return o;
+}
+MG_HD constexpr size_t d_gtc_bytes() { return d_gtc_offset(4); }
+MG_HD constexpr size_t d_blob_bytes() { return d_gtc_start() + d_gtc_bytes(); }
 MG_HD constexpr size_t msd_packed_bytes() { return 3 * d_blob_bytes(); }
 
 // Activation workspace (floats per batch item per mel frame): conv_pre out, stage 0..2 outs.
