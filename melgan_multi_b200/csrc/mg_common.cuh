@@ -49,6 +49,8 @@ int launch_disc_post1_tc(const float *x, float *y, const uint8_t *wtc, const flo
                          cudaStream_t s);
 int launch_disc_group_tc(const float *x, float *out, const uint8_t *wtc, const float *bias, int Bt, int Cin, int Cout,
                          int Lin, int Lout, int *status, cudaStream_t s);
+int launch_disc_group4_tc(const float *x, float *out, const uint8_t *wtc, const float *bias, int Bt, int L, int *status,
+                          cudaStream_t s);
 int launch_disc_pack(const float *const *v, const float *const *g, const float *const *bias, void *packed, cudaStream_t s);
 void msd_lengths(int L, int *lens);
 int launch_msd_forward(const void *packed, const float *y, int Bt, int L, float *const *fmaps, int *status, cudaStream_t s);

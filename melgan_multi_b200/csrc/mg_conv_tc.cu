@@ -17,8 +17,9 @@
 namespace mg {
 using namespace tc;
 
-template <int CIN_, int COUT_, int NTAP_, int KCA_, bool LRELU_OUT_>
+template <int CIN_, int COUT_, int NTAP_, int KCA_, bool LRELU_OUT_, int MINB_ = 1>
 struct ConvCfg {
+    static constexpr int MINB = MINB_;                      // CTAs per SM the shared-memory footprint is sized for
     static constexpr int CIN = CIN_, COUT = COUT_, NTAP = NTAP_, PAD = NTAP_ / 2, KCA = KCA_;
     static constexpr bool LRELU_OUT = LRELU_OUT_;
     static constexpr int N = 256;                          // output channels per CTA
@@ -33,13 +34,13 @@ struct ConvCfg {
     static constexpr int NT = NCONV + 64;
     static constexpr int SMEM_BYTES = NSA * ASLOT + NSB * BSLOT + (2 * NSA + 2 * NSB + 1) * 8 + 16;
     static_assert(CIN % KCA == 0 && KCA % 16 == 0 && COUT % N == 0, "shape");
-    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+    static_assert(MINB * (SMEM_BYTES + 1024) <= 228 * 1024 && MINB * N <= 512, "shared memory / TMEM budget");
 };
 
 // packed weights for this kernel: conv_tc_weight_index() in mg_layout.h
 
 template <class Cfg>
-__global__ void __launch_bounds__(Cfg::NT, 1)
+__global__ void __launch_bounds__(Cfg::NT, Cfg::MINB)
 conv_rows_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const uint8_t *__restrict__ wtc,
                     const float *__restrict__ bias, int L, int B, int *__restrict__ status) {
     constexpr int CIN = Cfg::CIN, COUT = Cfg::COUT, NTAP = Cfg::NTAP, PAD = Cfg::PAD, KCA = Cfg::KCA, N = Cfg::N;
@@ -194,7 +195,9 @@ static int launch_conv_rows(const float *x, float *y, const uint8_t *wtc, const 
 }
 
 using PreCfg = ConvCfg<80, 512, 7, 80, false>;          // generator conv_pre
-using Post1Cfg = ConvCfg<1024, 1024, 5, 64, true>;       // discriminator conv_post1 (+ LeakyReLU)
+// discriminator conv_post1 (+ LeakyReLU): 32-channel A slots -> 100 KB, two CTAs per SM (each owns half of TMEM), so the
+// three scales' tiles (132 + 68 + 20 CTAs at 8192 samples) are all resident at once and overlap each other's phases
+using Post1Cfg = ConvCfg<1024, 1024, 5, 32, true, 2>;
 
 // mel [B][80][T] -> y [B][512][T]   (Generator.conv_pre)
 int launch_gen_pre_tc(const float *mel, float *y, const float *packed, int B, int T, int *status, cudaStream_t s) {

@@ -61,6 +61,17 @@ __global__ void __launch_bounds__(128) disc_pack_kernel(DiscPackArgs a, uint8_t 
                 gt[d_gtc_index(kp, r, e * 16 + col, pos, ci)] = hi;
                 gt[d_gtc_index(kp, r, 32 + e * 16 + col, pos, ci)] = lo;
             }
+        } else {  // layer 4 (stride 1): 8-outputs-per-lane Toeplitz copy, mg_layout.h d_g4tc_index
+            __nv_bfloat16 *gt = reinterpret_cast<__nv_bfloat16 *>(blob + d_g4tc_start() + (size_t)grp * d_g4tc_group_bytes());
+            for (int s = threadIdx.x; s < kDg4Panels * 4 * 64; s += blockDim.x) {
+                const int i = s & 7, e = (s >> 3) & 7, ci = (s >> 6) & 3, kp = s >> 8;
+                const int k = 8 * kp + i - e;
+                const float wv = (k >= 0 && k <= 40) ? scale * vr[ci * 41 + k] : 0.f;
+                __nv_bfloat16 hi, lo;
+                tc::split_bf16(wv, hi, lo);
+                gt[d_g4tc_index(kp, ci, e * 4 + col, i)] = hi;
+                gt[d_g4tc_index(kp, ci, 32 + e * 4 + col, i)] = lo;
+            }
         }
     } else if (l == 5) {
         __nv_bfloat16 *tcw = reinterpret_cast<__nv_bfloat16 *>(blob + d_tc_start());
@@ -210,28 +221,33 @@ __global__ void __launch_bounds__(128) disc_group_kernel(const float *__restrict
 }
 
 // conv_post2 (1024 -> 1, k3, pad 1), no activation.  x [Bt][1024][L] -> out [Bt][1][L]
-// CTA = 32 positions of one item (lane = position: coalesced 128-byte rows); 16 warps split the 1024 input channels.
-__global__ void __launch_bounds__(512) disc_post2_kernel(const float *__restrict__ x, float *__restrict__ out,
+// The op is a 16.8 MB read for 4 K outputs (scale 0), so the grid is cut fine: CTA = 8 positions of one item (one 32-byte
+// sector per channel row); a warp load covers 4 channels x 8 positions, 8 warps split the 1024 channels.  The partial
+// sums are combined in a fixed order (shuffles, then warp 0 over the 8 per-warp partials): bit-reproducible.
+__global__ void __launch_bounds__(256) disc_post2_kernel(const float *__restrict__ x, float *__restrict__ out,
                                                          const float *__restrict__ w, const float *__restrict__ bias, int L) {
-    __shared__ float part[16][32];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int t = blockIdx.x * 32 + lane, b = blockIdx.y;
+    __shared__ float part[8][8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, cl = lane >> 3, pos = lane & 7;
+    const int t = blockIdx.x * 8 + pos, b = blockIdx.y;
     const float *xb = x + (size_t)b * 1024 * L;
     float acc = 0.f;
     if (t < L) {
 #pragma unroll 8
-        for (int ci = warp * 64; ci < warp * 64 + 64; ++ci) {
+        for (int j = 0; j < 32; ++j) {
+            const int ci = warp * 128 + j * 4 + cl;
             const float *xr = xb + (size_t)ci * L + t;
             const float xm = t >= 1 ? __ldg(xr - 1) : 0.f, xc = __ldg(xr), xp = t + 1 < L ? __ldg(xr + 1) : 0.f;
             acc = fmaf(__ldg(w + ci * 3), xm, fmaf(__ldg(w + ci * 3 + 1), xc, fmaf(__ldg(w + ci * 3 + 2), xp, acc)));
         }
     }
-    part[warp][lane] = acc;
+    acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+    if (lane < 8) part[warp][lane] = acc;
     __syncthreads();
-    if (warp == 0 && t < L) {
+    if (warp == 0 && lane < 8 && t < L) {
         float s = __ldg(bias);
 #pragma unroll
-        for (int q = 0; q < 16; ++q) s += part[q][lane];
+        for (int q = 0; q < 8; ++q) s += part[q][lane];
         out[(size_t)b * L + t] = s;
     }
 }
@@ -321,10 +337,14 @@ int launch_msd_forward(const void *packed, const float *y, int Bt, int L, float 
                                          ln[l], q);
             if (rc) return rc;
         }
-        if ((rc = launch_group<4, 1>(f[3], f[4], fw + d_weight_offset(4), fw + d_bias_offset(4), Bt, 1024, 1024, ln[3], ln[4], q))) return rc;
+        if (group_tc)
+            rc = launch_disc_group4_tc(f[3], f[4], blob + d_g4tc_start(), fw + d_bias_offset(4), Bt, ln[4], status, q);
+        else
+            rc = launch_group<4, 1>(f[3], f[4], fw + d_weight_offset(4), fw + d_bias_offset(4), Bt, 1024, 1024, ln[3], ln[4], q);
+        if (rc) return rc;
         if ((rc = launch_disc_post1_tc(f[4], f[5], blob + d_tc_start(), fw + d_bias_offset(5), Bt, ln[4], status, q))) return rc;
-        dim3 gp2((ln[5] + 31) / 32, Bt);
-        disc_post2_kernel<<<gp2, 512, 0, q>>>(f[5], f[6], fw + d_weight_offset(6), fw + d_bias_offset(6), ln[5]);
+        dim3 gp2((ln[5] + 7) / 8, Bt);
+        disc_post2_kernel<<<gp2, 256, 0, q>>>(f[5], f[6], fw + d_weight_offset(6), fw + d_bias_offset(6), ln[5]);
         MG_CUDA_TRY(cudaGetLastError());
         if (sc > 0) {
             MG_CUDA_TRY(cudaEventRecord(ss.join[sc - 1], q));

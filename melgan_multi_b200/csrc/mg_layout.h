@@ -180,7 +180,18 @@ MG_HD constexpr size_t d_gtc_offset(int l) {  // bytes from d_gtc_start(), l = 1
     return o;
 }
 MG_HD constexpr size_t d_gtc_bytes() { return d_gtc_offset(4); }
-MG_HD constexpr size_t d_blob_bytes() { return d_gtc_start() + d_gtc_bytes(); }
+// Tensor-core copy of the stride-1 grouped conv (layer 4: 256 groups of 4 -> 4 channels), 24 KB per group: one TMEM lane
+// owns a block of 8 consecutive outputs t = 8 m + e, a 16-byte unit of the A operand is 8 consecutive positions of ONE
+// input channel, and element i of k-panel kp (of channel ci) multiplies w[co][ci][tap = 8 kp + i - e] (zero outside 0..40):
+//   [kp 6][ci pair 2][ci & 1][n 64 = half 2 x e 8 x co 4][8 bf16] = one B operand (N = 64, K = 16) per (kp, ci pair).
+constexpr int kDg4Panels = 6;
+MG_HD constexpr size_t d_g4tc_group_bytes() { return (size_t)kDg4Panels * 2 * 2 * 64 * 16; }
+MG_HD constexpr size_t d_g4tc_index(int kp, int ci, int n, int i) {  // bf16 element index inside a group block
+    return ((((size_t)(kp * 2 + (ci >> 1)) * 2 + (ci & 1)) * 64 + n) * 8) + i;
+}
+MG_HD constexpr size_t d_g4tc_start() { return d_gtc_start() + d_gtc_bytes(); }
+MG_HD constexpr size_t d_g4tc_bytes() { return (size_t)d_layer(4).groups * d_g4tc_group_bytes(); }
+MG_HD constexpr size_t d_blob_bytes() { return d_g4tc_start() + d_g4tc_bytes(); }
 MG_HD constexpr size_t msd_packed_bytes() { return 3 * d_blob_bytes(); }
 
 // Activation workspace (floats per batch item per mel frame): conv_pre out, stage 0..2 outs.

@@ -36,7 +36,8 @@ struct RbCfg {
     static constexpr bool POST = POST_;  // fuse LeakyReLU -> conv_post -> tanh into the final epilogue (last stage)
     static constexpr int TCOLS = NBLK * 2 * C;  // TMEM columns (power of two: 256 or 512)
     static constexpr int P = 128 * NBLK;
-    static constexpr int SLACK = 16;      // zero rows either side of X (dilation-9 taps reach 9 rows out)
+    // zero rows either side of X (dilation-9 taps reach 9 rows out); 12 lets two C = 128 single-block CTAs share an SM
+    static constexpr int SLACK = (C_ == 128 && NBLK_ == 1) ? 12 : 16;
     static constexpr int HALO = 16 + (POST ? 3 : 0);  // 1+1+3+1+9+1 (+3 for the fused k7 conv_post)
     static constexpr int PVALID = P - 2 * HALO;
     static constexpr int ROWS = P + 2 * SLACK;
@@ -407,6 +408,8 @@ int launch_resblock_tc(const float *x, float *y, const float *packed, int stage,
     switch (stage) {
         //                                       C  NBLK NSTAGE NWG MINB
         case 0: return launch_resblock<RbCfg<256, 1, 4, 4, 1>>(x, y, packed, stage, B, L, status, trace, s);
+        // (C = 128 as two single-block CTAs per SM, RbCfg<128, 1, 2, 2, 2>: measured 244 us vs 213 us at config 2 -- the
+        //  25 % halo recompute and the two-slot weight rings cost more than the overlap buys)
         case 1: return launch_resblock<RbCfg<128, 2, 4, 4, 1>>(x, y, packed, stage, B, L, status, trace, s);
         // (3 CTAs/SM with half-size tiles was measured slower for C = 64 / 32: the extra halo recompute outweighs the overlap)
         case 2: return launch_resblock<RbCfg<64, 2, 2, 2, 2>>(x, y, packed, stage, B, L, status, trace, s);
