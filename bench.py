@@ -389,7 +389,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 80 * T * 4 * world,
                     "d2h_bytes_per_step": B * 256 * T * 4 * world, "ms_per_step": 1e3 * e2e_s / K,
                     "api": "mg_gen_engine_forward (host buffers, pinned)", "output_abs_sum": checksum},
-            "gpu_launches": K * world * engine.lib().mg_gen_forward_launches(),
+            "gpu_launches": K * world * engine.lib().mg_gen_forward_launches() * engine.lib().mg_gen_forward_slices(B, T),
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         }))
     if world > 1:

@@ -141,15 +141,19 @@ int mg_gen_engine_load_state(mg_gen_engine *e, const float *const *v, const floa
                              const float *const *bias);
 /* mel_host [B,80,T] -> audio_host [B,1,256T]; synchronous (returns when audio_host is filled).
  * Pinned host memory is used as given; pageable memory is staged through an internal pinned
- * buffer. */
+ * buffer.  The copies are cut with the batch slices (mg_gen_forward_slices): a slice's audio goes
+ * back to the host while the other slices are still computing. */
 int mg_gen_engine_forward(mg_gen_engine *e, const float *mel_host, float *audio_host, int B, int T);
-/* Device time of the kernels of the last forward, in milliseconds (CUDA events). */
+/* Device time of the last forward in milliseconds (CUDA events on the engine's stream around the sliced
+ * upload -> kernels -> download sequence). */
 int mg_gen_engine_last_kernel_ms(mg_gen_engine *e, float *ms);
 void mg_gen_engine_destroy(mg_gen_engine *e);
 
-/* Number of kernel launches one mg_gen_forward enqueues (for bench.py's gpu_launches; at most 16) and the
- * name of the i-th one. */
+/* Number of kernels in the generator's chain (at most 16) and the name of the i-th one.  mg_gen_forward cuts
+ * the batch into mg_gen_forward_slices(B, T) contiguous slices whose chains run concurrently on forked streams
+ * (joined back into `stream` before it returns), so one forward enqueues slices x launches kernels. */
 int mg_gen_forward_launches(void);
+int mg_gen_forward_slices(int B, int T);
 const char *mg_gen_kernel_name(int i);
 
 #ifdef __cplusplus

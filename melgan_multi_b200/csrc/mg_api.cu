@@ -30,13 +30,20 @@ static int *status_ptr(void *workspace, int B, int T) {
     return reinterpret_cast<int *>(reinterpret_cast<float *>(workspace) + ws_offset(6, (size_t)B, (size_t)T));
 }
 
+// mel_host / audio_host: optional pinned host buffers (the engine entry point); the copies ride on the batch slices' streams
 static int run_generator(const float *packed, const float *mel, float *audio, int B, int T, float *ws, cudaStream_t s,
-                         cudaEvent_t *ev) {
-    if (!use_tc()) return launch_generator_simt(packed, mel, audio, B, T, ws, s, ev);
+                         cudaEvent_t *ev, const float *mel_host = nullptr, float *audio_host = nullptr) {
+    if (!use_tc()) {
+        const size_t nin = (size_t)B * T * kMelBins * sizeof(float), nout = (size_t)B * T * 256 * sizeof(float);
+        if (mel_host) MG_CUDA_TRY(cudaMemcpyAsync(const_cast<float *>(mel), mel_host, nin, cudaMemcpyHostToDevice, s));
+        int rc = launch_generator_simt(packed, mel, audio, B, T, ws, s, ev);
+        if (rc == MG_OK && audio_host) MG_CUDA_TRY(cudaMemcpyAsync(audio_host, audio, nout, cudaMemcpyDeviceToHost, s));
+        return rc;
+    }
     int *st = status_ptr(ws, B, T);
     MG_CUDA_TRY(cudaMemsetAsync(st, 0, sizeof(int), s));
     const char *up = getenv("MG_UP_PATH");
-    return launch_generator_tc(packed, mel, audio, B, T, ws, st, !(up && strcmp(up, "simt") == 0), s, ev);
+    return launch_generator_tc(packed, mel, audio, B, T, ws, st, !(up && strcmp(up, "simt") == 0), s, ev, mel_host, audio_host);
 }
 
 static int check_shape(const char *fn, int B, int T) {
@@ -134,6 +141,8 @@ int mg_gen_stage_output(const void *workspace, int which, float *out, int B, int
 }
 
 int mg_gen_forward_launches(void) { return use_tc() ? generator_tc_num_launches() : generator_simt_num_launches(); }
+
+int mg_gen_forward_slices(int B, int T) { return (use_tc() && B >= 1 && T >= 1) ? generator_tc_slices(B, T) : 1; }
 
 int mg_gen_check_status(const void *workspace, int B, int T, void *stream) {
     int rc = check_shape("mg_gen_check_status", B, T);
@@ -252,6 +261,7 @@ struct mg_gen_engine {
     float *raw = nullptr;  // device staging for raw v/g/bias
     float *mel = nullptr, *audio = nullptr, *ws = nullptr;
     float *pin_in = nullptr, *pin_out = nullptr;
+    int *pin_status = nullptr;
     size_t cap_frames = 0;  // B*T capacity
     bool loaded = false;
     float last_ms = 0.f;
@@ -324,15 +334,19 @@ int mg_gen_engine_forward(mg_gen_engine *e, const float *mel_host, float *audio_
     cudaGetLastError();  // clear "invalid value" some drivers raise for pageable pointers
     const float *src = mel_host;
     if (!in_pinned) { memcpy(e->pin_in, mel_host, nin); src = e->pin_in; }
-    MG_CUDA_TRY(cudaMemcpyAsync(e->mel, src, nin, cudaMemcpyHostToDevice, e->stream));
+    if (!e->pin_status) MG_CUDA_TRY(cudaMallocHost(&e->pin_status, sizeof(int)));
     MG_CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
-    rc = run_generator(e->packed, e->mel, e->audio, B, T, e->ws, e->stream, nullptr);
+    // upload, kernels and download are enqueued per batch slice (launch_generator_tc); one synchronisation at the end
+    rc = run_generator(e->packed, e->mel, e->audio, B, T, e->ws, e->stream, nullptr, src, out_pinned ? audio_host : e->pin_out);
     if (rc) return rc;
     MG_CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
-    MG_CUDA_TRY(cudaMemcpyAsync(out_pinned ? audio_host : e->pin_out, e->audio, nout, cudaMemcpyDeviceToHost, e->stream));
+    *e->pin_status = 0;
+    if (use_tc())
+        MG_CUDA_TRY(cudaMemcpyAsync(e->pin_status, status_ptr(e->ws, B, T), sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     MG_CUDA_TRY(cudaStreamSynchronize(e->stream));
     if (!out_pinned) memcpy(audio_host, e->pin_out, nout);
-    if ((rc = mg_gen_check_status(e->ws, B, T, e->stream))) return rc;
+    if (*e->pin_status)
+        return set_error(MG_ERR_CUDA, "mg_gen_engine_forward: tensor-core pipeline wait timed out (code %d)", *e->pin_status);
     MG_CUDA_TRY(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
     return MG_OK;
 }
@@ -347,6 +361,7 @@ void mg_gen_engine_destroy(mg_gen_engine *e) {
     if (!e) return;
     engine_free_io(e);
     cudaFree(e->packed); cudaFree(e->raw);
+    if (e->pin_status) cudaFreeHost(e->pin_status);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->stream) cudaStreamDestroy(e->stream);

@@ -42,8 +42,9 @@ int launch_generator_simt(const float *packed, const float *mel, float *audio, i
                           cudaStream_t s, cudaEvent_t *ev = nullptr);
 int generator_simt_num_launches();
 int generator_tc_num_launches();
+int generator_tc_slices(int B, int T);  // batch slices (concurrent kernel chains) one forward is cut into
 int launch_generator_tc(const float *packed, const float *mel, float *audio, int B, int T, float *ws, int *status, bool up_tc,
-                        cudaStream_t s, cudaEvent_t *ev = nullptr);
+                        cudaStream_t s, cudaEvent_t *ev = nullptr, const float *mel_host = nullptr, float *audio_host = nullptr);
 int launch_gen_pre_tc(const float *mel, float *y, const float *packed, int B, int T, int *status, cudaStream_t s);
 int launch_disc_post1_tc(const float *x, float *y, const uint8_t *wtc, const float *bias, int Bt, int L, int *status,
                          cudaStream_t s);

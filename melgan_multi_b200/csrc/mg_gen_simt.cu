@@ -401,14 +401,12 @@ static int launch_stage(const float *x, float *y, const float *packed, int stage
 int generator_simt_num_launches() { return 5; }
 int generator_tc_num_launches() { return 9; }
 
-// Tensor-core pipeline: conv_pre (fp32 SIMT, 0.5% of the FLOPs) -> 4 x [ConvT (tcgen05) -> ResBlock (tcgen05)], the last
-// ResBlock with LeakyReLU -> conv_post -> tanh fused into its epilogue.  (up_tc = false swaps in the SIMT ConvT kernels.)
-int launch_generator_tc(const float *packed, const float *mel, float *audio, int B, int T, float *ws, int *status, bool up_tc,
-                        cudaStream_t s, cudaEvent_t *ev) {
+// Tensor-core pipeline of one contiguous slice of the batch: conv_pre -> 4 x [ConvT (tcgen05) -> ResBlock (tcgen05)], the
+// last ResBlock with LeakyReLU -> conv_post -> tanh fused into its epilogue.  (up_tc = false swaps in the SIMT ConvT / pre.)
+// a0, a[0..2], u: this slice's part of the workspace buffers.
+static int generator_tc_chain(const float *packed, const float *mel, float *audio, int B, int T, float *a0, float *const *a,
+                              float *u, int *status, bool up_tc, cudaStream_t s, cudaEvent_t *ev) {
 #define MG_MARK(i) do { if (ev) MG_CUDA_TRY(cudaEventRecord(ev[i], s)); } while (0)
-    float *a0 = ws + ws_offset(0, B, T);
-    float *a[4] = {ws + ws_offset(1, B, T), ws + ws_offset(2, B, T), ws + ws_offset(3, B, T), ws + ws_offset(4, B, T)};
-    float *u = ws + ws_offset(5, B, T);  // ConvT output of the current stage (largest: B*8192*T floats)
     int rc;
     MG_MARK(0);
     if (up_tc) {
@@ -437,7 +435,81 @@ int launch_generator_tc(const float *packed, const float *mel, float *audio, int
     if ((rc = launch_resblock_tc(u, audio, packed, 4, B, 256 * T, status, s))) return rc;
     MG_MARK(9);
 #undef MG_MARK
-    (void)a;
+    return MG_OK;
+}
+
+// Side streams for batch slices (forked from / joined into the caller's stream with events: the call stays asynchronous
+// and stream-ordered for the caller).  Per host thread, like the rest of the library's state.
+struct SliceStreams {
+    static constexpr int kMax = 8;
+    cudaStream_t st[kMax - 1] = {};
+    cudaEvent_t fork = nullptr, join[kMax - 1] = {};
+    bool ready = false;
+    int init() {
+        if (ready) return MG_OK;
+        for (int i = 0; i < kMax - 1; ++i) {
+            MG_CUDA_TRY(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+            MG_CUDA_TRY(cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming));
+        }
+        MG_CUDA_TRY(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+        ready = true;
+        return MG_OK;
+    }
+};
+
+// Whole generator.  The batch items are independent and every kernel's grid is a whole number of tiles per item (or per
+// 128 virtual rows), so the batch is cut into `slices` contiguous parts whose nine-kernel chains run on forked streams:
+// the block scheduler fills the SMs one chain's partial last wave leaves idle (stage 0 at config 2 is 192 one-per-SM
+// tiles on 148 SMs) with the other chain's tiles.  Same kernels, same per-item arithmetic: results are bit-identical
+// to the single-chain order.  ev != nullptr (per-kernel timing) keeps everything on one stream.
+int generator_tc_slices(int B, int T) {
+    static const int forced = [] {  // MG_GEN_SLICES=n pins the slice count (experiments); default: chosen from the shape
+        const char *e = getenv("MG_GEN_SLICES");
+        const int v = e ? atoi(e) : 0;
+        return v < 0 ? 0 : v > SliceStreams::kMax ? SliceStreams::kMax : v;
+    }();
+    // slicing pays while a slice still fills the machine: >= 512 mel frames per slice (stage-0 tiles ~ frames / 11)
+    int slices = forced ? forced : 4;
+    while (slices > 1 && ((!forced && (long long)B * T < 512ll * slices) || B < slices)) --slices;
+    return slices;
+}
+
+// mel_host / audio_host (both or neither; pinned): the host-buffer entry point's copies, cut the same way -- each slice's
+// stream uploads its mel slice before its chain and downloads its audio slice after it, so all but the last download
+// overlap the other chains' kernels.
+int launch_generator_tc(const float *packed, const float *mel, float *audio, int B, int T, float *ws, int *status, bool up_tc,
+                        cudaStream_t s, cudaEvent_t *ev, const float *mel_host, float *audio_host) {
+    const int slices = ev ? 1 : generator_tc_slices(B, T);
+    float *base[6];
+    for (int i = 0; i < 6; ++i) base[i] = ws + ws_offset(i, B, T);
+    const size_t per_item[6] = {(size_t)512 * T, (size_t)256 * 8 * T, (size_t)128 * 64 * T, (size_t)64 * 128 * T, 0, (size_t)8192 * T};
+    const size_t mel_item = (size_t)kMelBins * T, audio_item = (size_t)256 * T;
+    static thread_local SliceStreams ss;
+    int rc = MG_OK;
+    if (slices > 1) {
+        if ((rc = ss.init())) return rc;
+        MG_CUDA_TRY(cudaEventRecord(ss.fork, s));
+    }
+    for (int k = 0, b0 = 0; k < slices; ++k) {
+        const int nb = B / slices + (k < B % slices);
+        cudaStream_t q = k == 0 ? s : ss.st[k - 1];
+        if (k > 0) MG_CUDA_TRY(cudaStreamWaitEvent(q, ss.fork, 0));
+        if (mel_host)
+            MG_CUDA_TRY(cudaMemcpyAsync(const_cast<float *>(mel) + b0 * mel_item, mel_host + b0 * mel_item, nb * mel_item * sizeof(float),
+                                        cudaMemcpyHostToDevice, q));
+        float *a[3] = {base[1] + b0 * per_item[1], base[2] + b0 * per_item[2], base[3] + b0 * per_item[3]};
+        rc = generator_tc_chain(packed, mel + b0 * mel_item, audio + b0 * audio_item, nb, T, base[0] + b0 * per_item[0], a,
+                                base[5] + b0 * per_item[5], status, up_tc, q, ev);
+        if (rc) return rc;
+        if (audio_host)
+            MG_CUDA_TRY(cudaMemcpyAsync(audio_host + b0 * audio_item, audio + b0 * audio_item, nb * audio_item * sizeof(float),
+                                        cudaMemcpyDeviceToHost, q));
+        if (k > 0) {
+            MG_CUDA_TRY(cudaEventRecord(ss.join[k - 1], q));
+            MG_CUDA_TRY(cudaStreamWaitEvent(s, ss.join[k - 1], 0));
+        }
+        b0 += nb;
+    }
     return MG_OK;
 }
 

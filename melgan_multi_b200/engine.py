@@ -56,6 +56,8 @@ def lib():
         L.mg_gen_stage_output.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                           ctypes.c_int, ctypes.c_void_p]
         L.mg_gen_forward_launches.restype = ctypes.c_int
+        L.mg_gen_forward_slices.restype = ctypes.c_int
+        L.mg_gen_forward_slices.argtypes = [ctypes.c_int, ctypes.c_int]
         L.mg_gen_kernel_name.restype = ctypes.c_char_p
         L.mg_gen_kernel_name.argtypes = [ctypes.c_int]
         L.mg_msd_packed_bytes.restype = ctypes.c_size_t
