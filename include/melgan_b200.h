@@ -149,6 +149,21 @@ int mg_gen_engine_forward(mg_gen_engine *e, const float *mel_host, float *audio_
 int mg_gen_engine_last_kernel_ms(mg_gen_engine *e, float *ms);
 void mg_gen_engine_destroy(mg_gen_engine *e);
 
+/* ---- fused loss reductions (reference: feature_loss / discriminator_loss / generator_loss, models.py:138-167) ----
+ * A loss is a table of `count` (<= 24) rows; out[i] = mean over the n[i] elements of
+ *   mode 0: |a[i] - b[i]|   (one feature-map pair of feature_loss, models.py:142)
+ *   mode 1: (1 - a[i])^2    (real term of discriminator_loss :151, generator_loss :165)
+ *   mode 2: a[i]^2          (generated term of discriminator_loss :152)
+ * (b[i] is ignored for modes 1, 2).  All rows are reduced by one launch plus a fixed-order combine (bit-reproducible);
+ * `workspace` holds the per-CTA partial sums.  The caller scales / sums the row means (x10 for feature_loss).
+ * mg_loss_backward writes grad_a[i] (and grad_b[i] for mode 0; either may be NULL) = grad_out[i] * d out[i] / d input;
+ * grad_out is a DEVICE array of `count` floats. */
+size_t mg_loss_workspace_bytes(const long long *n, int count);
+int mg_loss_forward(const float *const *a, const float *const *b, const long long *n, const int *mode, int count,
+                    float *out, void *workspace, size_t workspace_bytes, void *stream);
+int mg_loss_backward(const float *const *a, const float *const *b, const long long *n, const int *mode, int count,
+                     const float *grad_out, float *const *grad_a, float *const *grad_b, void *stream);
+
 /* Number of kernels in the generator's chain (at most 16) and the name of the i-th one.  mg_gen_forward cuts
  * the batch into mg_gen_forward_slices(B, T) contiguous slices whose chains run concurrently on forked streams
  * (joined back into `stream` before it returns), so one forward enqueues slices x launches kernels. */

@@ -140,6 +140,25 @@ int mg_gen_stage_output(const void *workspace, int which, float *out, int B, int
     return MG_OK;
 }
 
+size_t mg_loss_workspace_bytes(const long long *n, int count) {
+    if (!n || count < 1) return 0;
+    return (size_t)loss_num_ctas(n, count) * sizeof(float);
+}
+
+int mg_loss_forward(const float *const *a, const float *const *b, const long long *n, const int *mode, int count,
+                    float *out, void *workspace, size_t workspace_bytes, void *stream) {
+    if (!out || !workspace) return set_error(MG_ERR_INVALID_ARGUMENT, "mg_loss_forward: null argument");
+    if (n && count >= 1 && workspace_bytes < mg_loss_workspace_bytes(n, count))
+        return set_error(MG_ERR_WORKSPACE_TOO_SMALL, "mg_loss_forward: workspace too small");
+    return launch_loss_forward(a, b, n, mode, count, out, (float *)workspace, (cudaStream_t)stream);
+}
+
+int mg_loss_backward(const float *const *a, const float *const *b, const long long *n, const int *mode, int count,
+                     const float *grad_out, float *const *grad_a, float *const *grad_b, void *stream) {
+    if (!grad_out) return set_error(MG_ERR_INVALID_ARGUMENT, "mg_loss_backward: null grad_out");
+    return launch_loss_backward(a, b, n, mode, count, grad_out, grad_a, grad_b, (cudaStream_t)stream);
+}
+
 int mg_gen_forward_launches(void) { return use_tc() ? generator_tc_num_launches() : generator_simt_num_launches(); }
 
 int mg_gen_forward_slices(int B, int T) { return (use_tc() && B >= 1 && T >= 1) ? generator_tc_slices(B, T) : 1; }

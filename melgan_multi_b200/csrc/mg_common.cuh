@@ -54,6 +54,11 @@ int launch_disc_group4_tc(const float *x, float *out, const uint8_t *wtc, const 
                           cudaStream_t s);
 int launch_disc_pack(const float *const *v, const float *const *g, const float *const *bias, void *packed, cudaStream_t s);
 void msd_lengths(int L, int *lens);
+long long loss_num_ctas(const long long *n, int count);
+int launch_loss_forward(const float *const *a, const float *const *b, const long long *n, const int *mode, int count, float *out,
+                        float *partial, cudaStream_t s);
+int launch_loss_backward(const float *const *a, const float *const *b, const long long *n, const int *mode, int count,
+                         const float *gout, float *const *ga, float *const *gb, cudaStream_t s);
 int launch_msd_forward(const void *packed, const float *y, int Bt, int L, float *const *fmaps, int *status, cudaStream_t s);
 int launch_convt_tc(const float *x, float *y, const float *packed, int stage, int B, int Lin, int *status, cudaStream_t s);
 int launch_resblock_tc(const float *x, float *y, const float *packed, int stage, int B, int L, int *status, cudaStream_t s,

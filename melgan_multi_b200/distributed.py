@@ -119,3 +119,47 @@ def apply_gradient_allreduce(module):
 
     module.register_forward_hook(set_needs_reduction)
     return module
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Long-utterance inference sharded over ranks along TIME (BASELINE config 5).  Not in the reference:
+# its inference script runs one utterance on one device.  The generator's receptive field is +-7 mel frames, so a rank
+# that owns frames [lo, hi) reads [lo - 8, hi + 8) (clipped to the utterance) and keeps the middle: no data-path
+# collective, the mel (320 B/frame) is simply replicated; only the optional gather of the audio talks to other ranks.
+HALO_FRAMES = 8
+
+
+def utterance_shard(T, world_size, rank, halo=HALO_FRAMES):
+    """Frames rank `rank` owns and reads: (lo, hi, a, b) with owned [lo, hi) and read window [a, b).  Contiguous, balanced
+    to one frame, empty (lo == hi) for ranks beyond T."""
+    if T < 1 or world_size < 1 or not 0 <= rank < world_size:
+        raise ValueError("utterance_shard(T=%r, world_size=%r, rank=%r)" % (T, world_size, rank))
+    base, extra = divmod(T, world_size)
+    lo = rank * base + min(rank, extra)
+    hi = lo + base + (rank < extra)
+    return lo, hi, max(0, lo - halo), min(T, hi + halo)
+
+
+def generate_sharded(generator, mel, rank=None, world_size=None, gather=True, group=None):
+    """mel [1, 80, T] (replicated on every rank) -> this rank's audio slice [1, 1, 256 * (hi - lo)]; with gather=True every
+    rank returns the whole utterance [1, 1, 256 * T] (one all_gather of equal-size padded slices over NCCL)."""
+    if rank is None:
+        rank = dist.get_rank(group)
+    if world_size is None:
+        world_size = dist.get_world_size(group)
+    T = mel.shape[2]
+    lo, hi, a, b = utterance_shard(T, world_size, rank)
+    if hi > lo:
+        with torch.no_grad():
+            part = generator(mel[:, :, a:b].contiguous())[:, :, (lo - a) * 256:(hi - a) * 256]
+    else:
+        part = mel.new_zeros((1, 1, 0))
+    if not gather or world_size == 1:
+        return part
+    width = 256 * ((T + world_size - 1) // world_size)
+    padded = mel.new_zeros((1, 1, width))
+    padded[:, :, :part.shape[2]] = part
+    parts = [torch.empty_like(padded) for _ in range(world_size)]
+    dist.all_gather(parts, padded, group=group)
+    sizes = [utterance_shard(T, world_size, r)[1] - utterance_shard(T, world_size, r)[0] for r in range(world_size)]
+    return torch.cat([p[:, :, :256 * n] for p, n in zip(parts, sizes)], dim=2)

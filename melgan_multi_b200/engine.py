@@ -68,6 +68,14 @@ def lib():
         L.mg_msd_forward.restype = ctypes.c_int
         L.mg_msd_forward.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                      ctypes.c_void_p, ctypes.c_void_p]
+        L.mg_loss_workspace_bytes.restype = ctypes.c_size_t
+        L.mg_loss_workspace_bytes.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.mg_loss_forward.restype = ctypes.c_int
+        L.mg_loss_forward.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+        L.mg_loss_backward.restype = ctypes.c_int
+        L.mg_loss_backward.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.mg_msd_check_status.restype = ctypes.c_int
         L.mg_msd_check_status.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.mg_gen_engine_create.restype = ctypes.c_int
@@ -222,6 +230,56 @@ def msd_lengths(L):
     lens = (ctypes.c_int * 21)()
     check(lib().mg_msd_lengths(int(L), lens))
     return [[lens[s * 7 + l] for l in range(7)] for s in range(3)]
+
+
+LOSS_L1, LOSS_ONE_MINUS_SQ, LOSS_SQ = 0, 1, 2  # row modes of mg_loss_forward (include/melgan_b200.h)
+
+
+def _loss_tables(a, b, modes):
+    import torch
+    dev = a[0].device
+    if dev.type != "cuda":
+        raise EngineError("the fused loss kernels run on CUDA tensors only")
+    keep_a, keep_b = [], []
+    for t, u, m in zip(a, b, modes):
+        if t.dtype != torch.float32 or t.device != dev or (m == LOSS_L1 and (u is None or u.shape != t.shape or u.device != dev)):
+            raise EngineError("loss rows must be fp32 tensors of equal shape on one CUDA device")
+        keep_a.append(t.contiguous())
+        keep_b.append(u.contiguous() if m == LOSS_L1 else None)
+    n = (ctypes.c_longlong * len(a))(*[t.numel() for t in keep_a])
+    md = (ctypes.c_int * len(a))(*modes)
+    pa = _ptr_array([t.data_ptr() for t in keep_a])
+    pb = _ptr_array([u.data_ptr() if u is not None else 0 for u in keep_b])
+    return dev, keep_a, keep_b, n, md, pa, pb
+
+
+def loss_forward(a, b, modes):
+    """Row means of a fused loss table (mg_loss_forward): a, b lists of CUDA tensors, modes list of LOSS_*; returns a
+    float32 CUDA tensor [len(a)].  One reduction launch + one fixed-order combine, no host sync."""
+    import torch
+    dev, keep_a, keep_b, n, md, pa, pb = _loss_tables(a, b, modes)
+    out = torch.empty(len(a), dtype=torch.float32, device=dev)
+    nbytes = lib().mg_loss_workspace_bytes(n, len(a))
+    ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream().cuda_stream
+        check(lib().mg_loss_forward(pa, pb, n, md, len(a), out.data_ptr(), ws.data_ptr(), nbytes, stream))
+    return out
+
+
+def loss_backward(a, b, modes, grad_out, need_b):
+    """Gradients of the row means w.r.t. a (and b where need_b[i] and the row is an L1 pair), scaled by grad_out [rows]."""
+    import torch
+    dev, keep_a, keep_b, n, md, pa, pb = _loss_tables(a, b, modes)
+    ga = [torch.empty_like(t) for t in keep_a]
+    gb = [torch.empty_like(u) if (u is not None and nb) else None for u, nb in zip(keep_b, need_b)]
+    pga = _ptr_array([t.data_ptr() for t in ga])
+    pgb = _ptr_array([t.data_ptr() if t is not None else 0 for t in gb])
+    grad_out = grad_out.to(device=dev, dtype=torch.float32).contiguous()
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream().cuda_stream
+        check(lib().mg_loss_backward(pa, pb, n, md, len(a), grad_out.data_ptr(), pga, pgb, stream))
+    return ga, gb
 
 
 class DiscriminatorDevice:

@@ -8,15 +8,16 @@ registration order (so reference checkpoints and Adam state load), an
 all-reduce wrapper (distributed.py:90-142) hooks them unchanged.
 
 What runs where
-  * ``Generator.forward`` (models.py:61-71 in the reference): five hand-written sm_100a kernels in
-    libmelgan_b200.so -- conv_pre, then one fused kernel per (LeakyReLU -> ConvTranspose1d ->
-    ResBlock) stage, the last one also doing LeakyReLU -> conv_post -> tanh -- plus one launch
-    that folds weight-norm for all 30 layers whenever the parameters changed.  CUDA only; a CPU
-    tensor raises (the reference's CPU path lives in oracle/ as test infrastructure).
+  * ``Generator.forward`` (models.py:61-71 in the reference): nine hand-written sm_100a tcgen05 kernels in
+    libmelgan_b200.so -- conv_pre, then LeakyReLU -> ConvTranspose1d and the fused six-conv ResBlock of each stage,
+    the last one also doing LeakyReLU -> conv_post -> tanh -- plus one launch that folds weight-norm for all 30 layers
+    whenever the parameters changed.  CUDA only; a CPU tensor raises (the reference's CPU path lives in oracle/ as
+    test infrastructure).
   * ``MultiScaleDiscriminator.forward`` (models.py:119-135, Discriminator.forward :87-103) on CUDA: real and generated
     audio are stacked into one batch and run through hand-written kernels -- AvgPool chain fused into each scale's
-    conv_pre, grouped k41 convs in fp32 SIMT, conv_post1 (88% of the FLOPs) on tcgen05 -- after one launch that folds
-    weight-norm for the 21 layers.
+    conv_pre, grouped k41 convs and conv_post1 on tcgen05 -- after one launch that folds weight-norm for the 21 layers.
+  * ``feature_loss`` / ``generator_loss`` / ``discriminator_loss`` (models.py:138-167) on CUDA tensors: every term of a
+    loss is a row of one fused reduction launch (forward) and one gradient launch (backward).
   * Backward passes (generator and discriminators) are NOT native yet: they run as recomputation through stock
     PyTorch ops so that train.py keeps working.  Open row in DESIGN.md, never part of a benchmark or parity claim.
 """
@@ -282,30 +283,62 @@ class MultiScaleDiscriminator(nn.Module):
         return y_d_rs, y_d_gs, fmap_rs, fmap_gs
 
 
+class _LossRows(torch.autograd.Function):
+    """Row means of a loss table on the fused kernels (csrc/mg_loss.cu): forward = one reduction launch over every row +
+    a fixed-order combine, backward = one launch writing every input gradient.  Inputs: rows of (a, b) CUDA tensors
+    (b ignored unless the row is an L1 pair)."""
+
+    @staticmethod
+    def forward(ctx, modes, *tensors):
+        k = len(modes)
+        a, b = list(tensors[:k]), list(tensors[k:])
+        ctx.modes, ctx.k = modes, k
+        ctx.save_for_backward(*[t.detach() for t in tensors])
+        return _engine.loss_forward(a, b, list(modes))
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        k, modes = ctx.k, ctx.modes
+        saved = ctx.saved_tensors
+        a, b = list(saved[:k]), list(saved[k:])
+        need_b = [ctx.needs_input_grad[1 + k + i] and modes[i] == _engine.LOSS_L1 for i in range(k)]
+        ga, gb = _engine.loss_backward(a, b, list(modes), grad_out, need_b)
+        ga = [g if ctx.needs_input_grad[1 + i] else None for i, g in enumerate(ga)]
+        return (None, *[g.view_as(t) if g is not None else None for g, t in zip(ga, a)],
+                *[g.view_as(t) if g is not None else None for g, t in zip(gb, b)])
+
+
+def _row_means(a, b, modes):
+    """CUDA tensors: the fused kernels.  CPU tensors (the reference's own CPU use, tests without a GPU): plain torch math
+    with the same definitions -- host-side logic, not a fallback of the CUDA path (a CUDA tensor never takes it)."""
+    if a[0].is_cuda:
+        b = [u if u is not None else t for t, u in zip(a, b)]  # placeholder rows keep the argument list rectangular
+        return _LossRows.apply(tuple(modes), *a, *b)
+    out = []
+    for t, u, m in zip(a, b, modes):
+        out.append((t - u).abs().mean() if m == _engine.LOSS_L1 else ((1 - t) ** 2).mean() if m == _engine.LOSS_ONE_MINUS_SQ
+                   else (t ** 2).mean())
+    return torch.stack(out)
+
+
 def feature_loss(fmap_r, fmap_g):
     """10 * sum over the 21 feature-map pairs of mean |r - g| (reference models.py:138-144)."""
-    total = 0
-    for maps_r, maps_g in zip(fmap_r, fmap_g):
-        for r, g in zip(maps_r, maps_g):
-            total = total + (r - g).abs().mean()
-    return total * 10
+    rs = [r for maps in fmap_r for r in maps]
+    gs = [g for maps in fmap_g for g in maps]
+    return _row_means(rs, gs, [_engine.LOSS_L1] * len(rs)).sum() * 10
 
 
 def discriminator_loss(disc_real_outputs, disc_generated_outputs):
-    """LSGAN discriminator loss; returns (loss, real terms, generated terms) like models.py:147-159."""
-    total, r_losses, g_losses = 0, [], []
-    for dr, dg in zip(disc_real_outputs, disc_generated_outputs):
-        r_term = ((1 - dr) ** 2).mean()
-        g_term = (dg ** 2).mean()
-        total = total + r_term + g_term
-        r_losses.append(r_term.item())
-        g_losses.append(g_term.item())
-    return total, r_losses, g_losses
+    """LSGAN discriminator loss; returns (loss, real terms, generated terms) like models.py:147-159 (the two lists are
+    Python floats, as in the reference -- read back with ONE host sync instead of six)."""
+    k = len(disc_real_outputs)
+    rows = list(disc_real_outputs) + list(disc_generated_outputs)
+    means = _row_means(rows, [None] * (2 * k), [_engine.LOSS_ONE_MINUS_SQ] * k + [_engine.LOSS_SQ] * k)
+    vals = means.detach().tolist()
+    return means.sum(), vals[:k], vals[k:]
 
 
 def generator_loss(disc_generated_outputs):
     """LSGAN generator loss (reference models.py:162-167)."""
-    total = 0
-    for dg in disc_generated_outputs:
-        total = total + ((1 - dg) ** 2).mean()
-    return total
+    rows = list(disc_generated_outputs)
+    return _row_means(rows, [None] * len(rows), [_engine.LOSS_ONE_MINUS_SQ] * len(rows)).sum()

@@ -91,6 +91,36 @@ def test_losses_on_native_outputs_match_reference(golden, msd_module):
     np.testing.assert_allclose([dl.item()] + rl + gl, golden[tag + "_discriminator_loss"], rtol=1e-4)
 
 
+def test_fused_losses_match_torch_formulas_and_gradients():
+    """csrc/mg_loss.cu against the reference's formulas (models.py:138-167) in plain torch, values and input gradients;
+    ragged sizes exercise the vector/tail split and multi-CTA rows."""
+    from melgan_multi_b200 import models
+    gen = torch.Generator(device="cpu").manual_seed(7)
+    shapes = [(2, 16, 4097), (2, 64, 1025), (2, 1024, 17), (2, 1, 17), (3, 5, 33333)]
+    fr = [[torch.randn(s, generator=gen).cuda().requires_grad_(True) for s in shapes]]
+    fg = [[torch.randn(s, generator=gen).cuda().requires_grad_(True) for s in shapes]]
+    dr = [torch.randn(4, n, generator=gen).cuda().requires_grad_(True) for n in (128, 65, 17)]
+    dg = [torch.randn(4, n, generator=gen).cuda().requires_grad_(True) for n in (128, 65, 17)]
+    loss = models.feature_loss(fr, fg) + models.generator_loss(dg)
+    dl, rl, gl = models.discriminator_loss(dr, dg)
+    (loss + dl).backward()
+    got = [t.grad.clone() for t in fr[0] + fg[0] + dr + dg]
+    for t in fr[0] + fg[0] + dr + dg:
+        t.grad = None
+    ref = sum((r - g).abs().mean() for r, g in zip(fr[0], fg[0])) * 10 + sum(((1 - g) ** 2).mean() for g in dg)
+    ref_r = [((1 - r) ** 2).mean() for r in dr]
+    ref_g = [(g ** 2).mean() for g in dg]
+    ref_dl = sum(ref_r) + sum(ref_g)
+    (ref + ref_dl).backward()
+    assert abs(loss.item() / ref.item() - 1) < 1e-5 and abs(dl.item() / ref_dl.item() - 1) < 1e-5
+    np.testing.assert_allclose(rl + gl, [v.item() for v in ref_r + ref_g], rtol=1e-5)
+    for g, t in zip(got, fr[0] + fg[0] + dr + dg):
+        assert torch.allclose(g, t.grad, rtol=1e-5, atol=1e-9)
+    # bit-reproducible (fixed-order combine of the per-CTA partial sums)
+    with torch.no_grad():
+        assert models.feature_loss(fr, fg).item() == models.feature_loss(fr, fg).item()
+
+
 def test_msd_backward_reaches_parameters_and_input(msd_module):
     """train.py:117 backpropagates the generator loss THROUGH the discriminators into y_hat (and into D's leaves)."""
     msd_module.zero_grad()

@@ -140,3 +140,47 @@ def test_batch_sharded_inference_equals_unsharded(tmp_path):
     whole = torch_port.generator_forward(ws, bs, torch.from_numpy(synth.mel_input(4, 6, 11))).numpy()
     sharded = np.load(os.path.join(tmp_path, "sharded.npy"))
     np.testing.assert_allclose(sharded, whole, rtol=0, atol=1e-6)
+
+
+def test_utterance_shard_partitions_time_axis():
+    from melgan_multi_b200.distributed import HALO_FRAMES, utterance_shard
+    for T in (1, 2, 7, 1000, 1001):
+        for world in (1, 2, 3, 8):
+            cover = []
+            for r in range(world):
+                lo, hi, a, b = utterance_shard(T, world, r)
+                assert 0 <= a <= lo <= hi <= b <= T
+                assert (lo - a == HALO_FRAMES or a == 0) and (b - hi == HALO_FRAMES or b == T)
+                cover += list(range(lo, hi))
+            assert cover == list(range(T))
+            sizes = [utterance_shard(T, world, r)[1] - utterance_shard(T, world, r)[0] for r in range(world)]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _utt_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from melgan_multi_b200 import distributed as mgd
+    from melgan_multi_b200 import synth
+    from oracle import torch_port
+    torch.set_num_threads(2)
+    ws, bs = torch_port.fold_state(synth.generator_state(1234))
+    mel = torch.from_numpy(synth.mel_input(1, 37, 5))  # replicated input: every rank builds it from the seed
+    audio = mgd.generate_sharded(lambda m: torch_port.generator_forward(ws, bs, m), mel)
+    np.save(os.path.join(out_dir, "utt%d.npy" % rank), audio.numpy())
+    dist.destroy_process_group()
+
+
+def test_time_sharded_utterance_equals_whole(tmp_path):
+    """One long utterance split along time over 2 ranks (8-frame halo, no data-path collective, one all_gather of the
+    audio): every rank ends up with the whole-utterance result."""
+    world, port = 2, _free_port()
+    mp.spawn(_utt_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    from melgan_multi_b200 import synth
+    from oracle import torch_port
+    ws, bs = torch_port.fold_state(synth.generator_state(1234))
+    whole = torch_port.generator_forward(ws, bs, torch.from_numpy(synth.mel_input(1, 37, 5))).numpy()
+    for r in range(world):
+        got = np.load(os.path.join(tmp_path, "utt%d.npy" % r))
+        assert got.shape == whole.shape
+        assert np.abs(got - whole).max() <= 2e-6 * np.abs(whole).max()

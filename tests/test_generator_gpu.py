@@ -178,3 +178,31 @@ def test_streaming_long_utterance_equals_whole(host_engine):
     chunks = list(host_engine.stream(mel, chunk_frames=96))
     assert len(chunks) == 11 and sum(c.shape[2] for c in chunks) == 256000
     np.testing.assert_allclose(np.concatenate(chunks, axis=2), whole, rtol=0, atol=1e-6)
+
+
+def test_time_sharded_utterance_equals_whole(gen_module):
+    """one utterance cut along time for N ranks (each reads its frames +- 8): the concatenation of the
+    ranks' slices equals the whole-utterance forward.  The ranks are emulated on one GPU (no collective on this path)."""
+    from melgan_multi_b200 import distributed as mgd
+    mel = torch.from_numpy(synth.mel_input(1, 203, 9)).cuda()
+    with torch.no_grad():
+        whole = gen_module(mel)
+        for world in (2, 3, 8):
+            parts = [mgd.generate_sharded(gen_module, mel, rank=r, world_size=world, gather=False) for r in range(world)]
+            got = torch.cat(parts, dim=2)
+            assert got.shape == whole.shape
+            assert (got - whole).abs().max().item() <= 1e-6
+
+
+def test_batch_slices_are_bit_identical_to_single_chain(gen_module, path):
+    """launch_generator_tc cuts large batches into concurrent slices (forked streams); the arithmetic per item is the
+    same, so a sliced forward equals the per-item forwards bit for bit."""
+    if path != "tc":
+        pytest.skip("batch slicing is a feature of the tensor-core pipeline")
+    assert engine.lib().mg_gen_forward_slices(64, 32) == 4 and engine.lib().mg_gen_forward_slices(1, 1000) == 1
+    x = torch.from_numpy(synth.mel_input(40, 32, 3)).cuda()  # 1280 frames -> 2 slices
+    assert engine.lib().mg_gen_forward_slices(40, 32) == 2
+    with torch.no_grad():
+        y = gen_module(x)
+        for i in (0, 19, 20, 39):
+            assert torch.equal(y[i:i + 1], gen_module(x[i:i + 1]))
