@@ -34,7 +34,8 @@ static_assert(WBYTES == (int)d_gtc_group_bytes(), "weight block");
 
 __global__ void __launch_bounds__(dg::NT, 2)
 disc_group_tc_kernel(const float *__restrict__ x, float *__restrict__ out, const uint8_t *__restrict__ wtc,
-                     const float *__restrict__ bias, int Cin, int Cout, int Lin, int Lout, int *__restrict__ status) {
+                     const float *__restrict__ bias, int Bt, int Cin, int Cout, int Lin, int Lout, int rp, int ni,
+                     int *__restrict__ status) {
     using namespace dg;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *wsm = smem, *xsm = smem + NGRP * WBYTES;
@@ -43,7 +44,9 @@ disc_group_tc_kernel(const float *__restrict__ x, float *__restrict__ out, const
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done + NGRP);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int t0 = blockIdx.x * TILE, g0 = blockIdx.y * NGRP, b = blockIdx.z;
+    // lanes are VIRTUAL when the sequence is short: ni items share the tile at a pitch of rp lanes / units (an item's
+    // ceil(Lout/2) output pairs + 6 halo units); ni == 1 (rp = 2^30): blockIdx.x walks the 256-output tiles of one item
+    const int t0 = blockIdx.x * TILE, g0 = blockIdx.y * NGRP, b0 = blockIdx.z * ni;
 
     if (warp == 0) tmem_alloc(tmem_slot, NGRP * 64);
     if (tid == 32) {
@@ -70,9 +73,10 @@ disc_group_tc_kernel(const float *__restrict__ x, float *__restrict__ out, const
             float f[3][4];
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                const int i = i0 + k * NCONV, g = i >= NPOS, p = p0 + i - g * NPOS;
-                const bool in = i < NGRP * NPOS && p >= 0 && p < Lin;
-                const float *xp = x + ((size_t)b * Cin + (g0 + g) * 4) * Lin + (in ? p : 0);
+                const int i = i0 + k * NCONV, g = i >= NPOS, pp = i - g * NPOS;
+                const int j = (pp >> 3) / rp, p = p0 + pp - 8 * j * rp, b = b0 + j;  // a unit = 8 consecutive positions
+                const bool in = i < NGRP * NPOS && b < Bt && p >= 0 && p < Lin;
+                const float *xp = x + ((size_t)(in ? b : 0) * Cin + (g0 + g) * 4) * Lin + (in ? p : 0);
 #pragma unroll
                 for (int ci = 0; ci < 4; ++ci) f[k][ci] = in ? __ldg(xp + (size_t)ci * Lin) : 0.f;
             }
@@ -109,10 +113,10 @@ disc_group_tc_kernel(const float *__restrict__ x, float *__restrict__ out, const
 #pragma unroll
                 for (int kp = 0; kp < kDgPanels; ++kp) {
 #pragma unroll
-                    for (int rp = 0; rp < 2; ++rp) {
-                        const uint64_t adesc = a0 + (uint64_t)((2 * rp * XP + 16 * kp) >> 4);
-                        const uint64_t bdesc = b0 + (uint64_t)(((kp * 2 + rp) * 2048) >> 4);
-                        if (elect_one()) mma_bf16(tmem + g * 64, adesc, bdesc, pass ? idesc32 : idesc64, (pass | kp | rp) != 0);
+                    for (int rq = 0; rq < 2; ++rq) {  // phase pair (r = 2 rq, 2 rq + 1)
+                        const uint64_t adesc = a0 + (uint64_t)((2 * rq * XP + 16 * kp) >> 4);
+                        const uint64_t bdesc = b0 + (uint64_t)(((kp * 2 + rq) * 2048) >> 4);
+                        if (elect_one()) mma_bf16(tmem + g * 64, adesc, bdesc, pass ? idesc32 : idesc64, (pass | kp | rq) != 0);
                     }
                 }
             }
@@ -122,7 +126,8 @@ disc_group_tc_kernel(const float *__restrict__ x, float *__restrict__ out, const
     } else {
         // ================= epilogue: lane m <-> outputs t0 + 2m, t0 + 2m + 1; warp half <-> 8 of the 16 co =================
         const int q = warp & 3, ch = warp >> 2;
-        const int t = t0 + 2 * (q * 32 + lane);
+        const int m = q * 32 + lane, jm = m / rp, b = b0 + jm;
+        const int t = (jm < ni && b < Bt) ? t0 + 2 * (m - jm * rp) : Lout;  // lanes of the inter-item gap store nothing
         const bool pair = (Lout & 1) == 0;
 #pragma unroll 1
         for (int g = 0; g < NGRP; ++g) {
@@ -136,7 +141,7 @@ disc_group_tc_kernel(const float *__restrict__ x, float *__restrict__ out, const
             tmem_ld8(ta + 48, l1);
             tmem_ld_wait();
             const int co0 = (g0 + g) * 16 + ch * 8;
-            float *op = out + ((size_t)b * Cout + co0) * Lout + t;
+            float *op = out + ((size_t)(t < Lout ? b : 0) * Cout + co0) * Lout + t;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const float bv = __ldg(bias + co0 + j);
@@ -165,9 +170,12 @@ int launch_disc_group_tc(const float *x, float *out, const uint8_t *wtc, const f
         MG_CUDA_TRY(cudaFuncSetAttribute(disc_group_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dg::SMEM_BYTES));
         configured = true;
     }
-    if (Bt > 65535) return set_error(MG_ERR_INVALID_ARGUMENT, "discriminator batch %d exceeds 65535", Bt);
-    dim3 grid((Lout + dg::TILE - 1) / dg::TILE, (Cin / 4) / dg::NGRP, Bt);
-    disc_group_tc_kernel<<<grid, dg::NT, dg::SMEM_BYTES, s>>>(x, out, wtc, bias, Cin, Cout, Lin, Lout, status);
+    int rp = (Lout + 1) / 2 + kDgPanels - 1, ni = dg::UNITS / rp;
+    if (ni <= 1) { ni = 1; rp = 1 << 30; }
+    const int zb = (Bt + ni - 1) / ni;
+    if (zb > 65535) return set_error(MG_ERR_INVALID_ARGUMENT, "discriminator batch %d exceeds the grid", Bt);
+    dim3 grid(ni > 1 ? 1 : (Lout + dg::TILE - 1) / dg::TILE, (Cin / 4) / dg::NGRP, zb);
+    disc_group_tc_kernel<<<grid, dg::NT, dg::SMEM_BYTES, s>>>(x, out, wtc, bias, Bt, Cin, Cout, Lin, Lout, rp, ni, status);
     MG_CUDA_TRY(cudaGetLastError());
     return MG_OK;
 }
