@@ -413,6 +413,9 @@ int launch_resblock_tc(const float *x, float *y, const float *packed, int stage,
         case 1: return launch_resblock<RbCfg<128, 2, 4, 4, 1>>(x, y, packed, stage, B, L, status, trace, s);
         // (3 CTAs/SM with half-size tiles was measured slower for C = 64 / 32: the extra halo recompute outweighs the overlap)
         case 2: return launch_resblock<RbCfg<64, 2, 2, 2, 2>>(x, y, packed, stage, B, L, status, trace, s);
+        // (C = 32 with the two A = hi(x) passes merged into one N = 64 MMA against [w hi | w lo] -- 4C TMEM columns per
+        //  block, so NBLK = 2: measured 184 us vs 142 us; this stage is bound by its epilogue, which then reads twice the
+        //  accumulator columns, not by the A-operand re-reads the merge saves)
         case 3: return launch_resblock<RbCfg<32, 4, 4, 2, 2>>(x, y, packed, stage, B, L, status, trace, s);
         // stage 4 = ResBlock 3 with LeakyReLU -> conv_post -> tanh fused: y is the audio [B][1][L]
         case 4: return launch_resblock<RbCfg<32, 4, 4, 2, 2, true>>(x, y, packed, 3, B, L, status, trace, s);

@@ -49,7 +49,53 @@ def generator_stage_outputs(gen, x):
     return [t.detach().numpy() for t in taps], torch.tanh(h).detach().numpy()
 
 
+TRAIN_CASE = dict(B=2, T=4, mel_seed=21, audio_seed=22)  # one train.py:108-129 step on a 1024-sample segment
+
+
+def grad_digest(named_params):
+    d = {}
+    for n, p in named_params:
+        g = p.grad.detach().double().reshape(-1)
+        d[n + "/l2"] = np.array(float(g.norm()))
+        d[n + "/sum"] = np.array(float(g.sum()))
+        d[n + "/head"] = g[:16].numpy().copy()
+    return d
+
+
+def train_step_golden():
+    """Losses and parameter-gradient digests of ONE reference training step (train.py:108-129, without the optimizer
+    updates): generator step through the discriminators, then the discriminator step on the detached audio."""
+    c = TRAIN_CASE
+    gen = load_state(ref_models.Generator(), synth.generator_state(1234)).train()
+    msd = load_state(ref_models.MultiScaleDiscriminator(), synth.discriminator_state(4321)).train()
+    x = torch.from_numpy(synth.mel_input(c["B"], c["T"], c["mel_seed"]))
+    y = torch.from_numpy(synth.audio_input(c["B"], 256 * c["T"], c["audio_seed"]))
+    out = {}
+    y_ghat = gen(x)
+    dr, dg, fr, fg = msd(y, y_ghat)
+    loss_gen = ref_models.generator_loss(dg) + ref_models.feature_loss(fr, fg)
+    loss_gen.backward()
+    out["loss_gen"] = np.array(loss_gen.item())
+    for k, v in grad_digest(gen.named_parameters()).items():
+        out["gstep/G/" + k] = v
+    for k, v in grad_digest(msd.named_parameters()).items():
+        out["gstep/D/" + k] = v
+    msd.zero_grad()
+    dr, dg, _, _ = msd(y, y_ghat.detach())
+    loss_disc, _, _ = ref_models.discriminator_loss(dr, dg)
+    loss_disc.backward()
+    out["loss_disc"] = np.array(loss_disc.item())
+    for k, v in grad_digest(msd.named_parameters()).items():
+        out["dstep/D/" + k] = v
+    path = os.path.join(HERE, "train_step_grads.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, "%.2f MB" % (os.path.getsize(path) / 1e6), len(out), "arrays")
+
+
 def main():
+    if "--train-step" in sys.argv:  # only the training-step fixture (leaves reference_outputs.npz untouched)
+        torch.set_num_threads(os.cpu_count())
+        return train_step_golden()
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count())
     out = {}

@@ -150,3 +150,64 @@ def test_cabi_argument_errors_are_reported_not_thrown():
                             ctypes.c_void_p(256), 16, None) == -4  # MG_ERR_WORKSPACE_TOO_SMALL
     assert L.mg_gen_kernel_name(0) == b"conv_pre" and L.mg_gen_kernel_name(99) == b""
     assert L.mg_gen_forward_launches() == 9
+
+
+def _train_case():
+    return dict(B=2, T=4, mel_seed=21, audio_seed=22)  # tests/golden/make_golden.py TRAIN_CASE
+
+
+def check_grad_digest(golden_grads, prefix, named_params, rtol):
+    """Every parameter's gradient against the reference digest (L2 norm, sum, first 16 values)."""
+    worst = 0.0
+    for n, p in named_params:
+        g = p.grad.detach().double().reshape(-1).cpu()
+        l2 = float(golden_grads[prefix + n + "/l2"])
+        scale = max(l2, 1e-12)
+        assert abs(float(g.norm()) - l2) <= rtol * scale, (prefix, n, float(g.norm()), l2)
+        assert abs(float(g.sum()) - float(golden_grads[prefix + n + "/sum"])) <= rtol * scale * max(1.0, g.numel() ** 0.5), (prefix, n)
+        head = golden_grads[prefix + n + "/head"]
+        err = np.abs(g[:16].numpy() - head).max()
+        assert err <= rtol * max(np.abs(head).max(), scale / max(1.0, g.numel() ** 0.5)), (prefix, n, err)
+        worst = max(worst, abs(float(g.norm()) - l2) / scale)
+    return worst
+
+
+def test_backward_restatement_matches_reference_gradients():
+    """The stock-op graphs the autograd path differentiates (Generator._torch_forward / MultiScaleDiscriminator.
+    _torch_forward + the loss formulas), run on CPU through one train.py:108-129 step, against the gradient digests of
+    the unmodified reference (tests/golden/train_step_grads.npz)."""
+    import os
+    from melgan_multi_b200 import models
+    gg = np.load(os.path.join(os.path.dirname(__file__), "golden", "train_step_grads.npz"))
+    c = _train_case()
+    gen = models.Generator()
+    gen.load_state_dict({k: torch.from_numpy(v) for k, v in synth.generator_state(1234).items()})
+    msd = models.MultiScaleDiscriminator()
+    msd.load_state_dict({k: torch.from_numpy(v) for k, v in synth.discriminator_state(4321).items()})
+    x = torch.from_numpy(synth.mel_input(c["B"], c["T"], c["mel_seed"]))
+    y = torch.from_numpy(synth.audio_input(c["B"], 256 * c["T"], c["audio_seed"]))
+
+    def leaves(m):
+        vs, gs_, bs = m._param_triplets()
+        return [t for trip in zip(vs, gs_, bs) for t in trip]
+
+    def disc(y_, y_hat):
+        B = y_.shape[0]
+        outs = msd._torch_forward(torch.cat([y_, y_hat]), leaves(msd))
+        fm = [outs[7 * s:7 * s + 7] for s in range(3)]
+        return ([sc[6][:B].flatten(1) for sc in fm], [sc[6][B:].flatten(1) for sc in fm],
+                [[f[:B] for f in sc] for sc in fm], [[f[B:] for f in sc] for sc in fm])
+
+    y_ghat = gen._torch_forward(x, leaves(gen))
+    dr, dg, fr, fg = disc(y, y_ghat)
+    loss_gen = models.generator_loss(dg) + models.feature_loss(fr, fg)
+    loss_gen.backward()
+    assert abs(loss_gen.item() / float(gg["loss_gen"]) - 1) < 1e-5
+    check_grad_digest(gg, "gstep/G/", gen.named_parameters(), 2e-4)
+    check_grad_digest(gg, "gstep/D/", msd.named_parameters(), 2e-4)
+    msd.zero_grad()
+    dr, dg, _, _ = disc(y, y_ghat.detach())
+    loss_disc, _, _ = models.discriminator_loss(dr, dg)
+    loss_disc.backward()
+    assert abs(loss_disc.item() / float(gg["loss_disc"]) - 1) < 1e-5
+    check_grad_digest(gg, "dstep/D/", msd.named_parameters(), 2e-4)

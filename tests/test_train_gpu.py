@@ -1,0 +1,52 @@
+"""GPU: one training step (train.py:108-129) through the drop-in modules -- native forwards (generator, discriminators,
+fused losses and their fused backward), stock-op recomputation for the conv backward -- against the losses and
+parameter-gradient digests of the unmodified reference (tests/golden/train_step_grads.npz).  Convs of the recomputed
+backward run in strict fp32 here so that the comparison is tight; the forward is the tcgen05 split-bf16 path."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from melgan_multi_b200 import synth
+from test_host import _train_case, check_grad_digest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def strict_fp32():
+    old = torch.backends.cudnn.conv.fp32_precision
+    torch.backends.cudnn.conv.fp32_precision = "ieee"
+    yield
+    torch.backends.cudnn.conv.fp32_precision = old
+
+
+def test_train_step_losses_and_gradients_match_reference(strict_fp32):
+    from melgan_multi_b200 import models
+    gg = np.load(os.path.join(os.path.dirname(__file__), "golden", "train_step_grads.npz"))
+    c = _train_case()
+    gen = models.Generator()
+    gen.load_state_dict({k: torch.from_numpy(v) for k, v in synth.generator_state(1234).items()})
+    msd = models.MultiScaleDiscriminator()
+    msd.load_state_dict({k: torch.from_numpy(v) for k, v in synth.discriminator_state(4321).items()})
+    gen, msd = gen.cuda().train(), msd.cuda().train()
+    x = torch.from_numpy(synth.mel_input(c["B"], c["T"], c["mel_seed"])).cuda()
+    y = torch.from_numpy(synth.audio_input(c["B"], 256 * c["T"], c["audio_seed"])).cuda()
+
+    y_ghat = gen(x)
+    dr, dg, fr, fg = msd(y, y_ghat)
+    loss_gen = models.generator_loss(dg) + models.feature_loss(fr, fg)
+    loss_gen.backward()
+    assert abs(loss_gen.item() / float(gg["loss_gen"]) - 1) < 1e-4
+    w1 = check_grad_digest(gg, "gstep/G/", gen.named_parameters(), 1e-3)
+    w2 = check_grad_digest(gg, "gstep/D/", msd.named_parameters(), 1e-3)
+    msd.zero_grad()
+    dr, dg, _, _ = msd(y, y_ghat.detach())
+    loss_disc, rl, gl = models.discriminator_loss(dr, dg)
+    loss_disc.backward()
+    assert abs(loss_disc.item() / float(gg["loss_disc"]) - 1) < 1e-4
+    assert abs(sum(rl) + sum(gl) - loss_disc.item()) < 1e-5
+    w3 = check_grad_digest(gg, "dstep/D/", msd.named_parameters(), 1e-3)
+    msd._dev.check_status()
+    print("worst relative gradient-norm error:", max(w1, w2, w3))
