@@ -149,6 +149,18 @@ int mg_gen_engine_forward(mg_gen_engine *e, const float *mel_host, float *audio_
 int mg_gen_engine_last_kernel_ms(mg_gen_engine *e, float *ms);
 void mg_gen_engine_destroy(mg_gen_engine *e);
 
+/* ---- discriminator backward pieces (autograd of Discriminator.forward, models.py:87-103) ------------------------
+ * Gradients of ONE grouped conv (layer 1..4: k41, pad 20, 4 input channels per group, stride 4/4/4/1) of discriminator
+ * `scale` of the packed MSD blob, each a single launch (cuDNN runs one kernel per group):
+ *   dz [Bt][Cout][Lout]: upstream gradient already multiplied by LeakyReLU'(layer output);  x [Bt][Cin][Lin]: layer input
+ *   dx [Bt][Cin][Lin] (NULL: skip), dw [Cout][4][41] + db [Cout] (dw NULL: skip both) -- dw is the gradient of the FOLDED
+ *   weight; mg_msd_wn_backward turns the 21 layers' dw into (d weight_v, d weight_g) in one launch (dw[i] NULL: skip). */
+size_t mg_msd_grouped_backward_workspace_bytes(int layer, int Bt, int Lout);
+int mg_msd_grouped_backward(const void *packed, int scale, int layer, const float *dz, const float *x, float *dx, float *dw,
+                            float *db, void *workspace, size_t workspace_bytes, int Bt, int Lin, int Lout, void *stream);
+int mg_msd_wn_backward(const float *const *v, const float *const *g, const float *const *dw, float *const *dv,
+                       float *const *dg, void *stream);
+
 /* ---- fused loss reductions (reference: feature_loss / discriminator_loss / generator_loss, models.py:138-167) ----
  * A loss is a table of `count` (<= 24) rows; out[i] = mean over the n[i] elements of
  *   mode 0: |a[i] - b[i]|   (one feature-map pair of feature_loss, models.py:142)

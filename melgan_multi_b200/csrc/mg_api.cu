@@ -140,6 +140,31 @@ int mg_gen_stage_output(const void *workspace, int which, float *out, int B, int
     return MG_OK;
 }
 
+size_t mg_msd_grouped_backward_workspace_bytes(int layer, int Bt, int Lout) {
+    if (layer < 1 || layer > 4 || Bt < 1 || Lout < 1) return 0;
+    return grouped_bwd_workspace_bytes(layer, Bt, Lout);
+}
+
+int mg_msd_grouped_backward(const void *packed, int scale, int layer, const float *dz, const float *x, float *dx, float *dw,
+                            float *db, void *workspace, size_t workspace_bytes, int Bt, int Lin, int Lout, void *stream) {
+    if (!packed || !dz || scale < 0 || scale > 2 || layer < 1 || layer > 4 || Bt < 1 || Lin < 1 || Lout < 1)
+        return set_error(MG_ERR_INVALID_ARGUMENT, "mg_msd_grouped_backward: bad argument");
+    const DLayer d = d_layer(layer);
+    if (Lout != (Lin + 2 * d.pad - d.k) / d.stride + 1)
+        return set_error(MG_ERR_INVALID_ARGUMENT, "mg_msd_grouped_backward: Lout %d does not follow from Lin %d", Lout, Lin);
+    if (dw && (!x || !db || !workspace || workspace_bytes < grouped_bwd_workspace_bytes(layer, Bt, Lout)))
+        return set_error(MG_ERR_WORKSPACE_TOO_SMALL, "mg_msd_grouped_backward: dw needs x, db and a workspace of %zu bytes",
+                         grouped_bwd_workspace_bytes(layer, Bt, Lout));
+    const uint8_t *blob = reinterpret_cast<const uint8_t *>(packed) + (size_t)scale * d_blob_bytes();
+    return launch_disc_grouped_backward(blob, layer, dz, x, dx, dw, db, (float *)workspace, Bt, Lin, Lout, (cudaStream_t)stream);
+}
+
+int mg_msd_wn_backward(const float *const *v, const float *const *g, const float *const *dw, float *const *dv,
+                       float *const *dg, void *stream) {
+    if (!v || !g || !dw || !dv || !dg) return set_error(MG_ERR_INVALID_ARGUMENT, "mg_msd_wn_backward: null argument");
+    return launch_disc_wn_backward(v, g, dw, dv, dg, (cudaStream_t)stream);
+}
+
 size_t mg_loss_workspace_bytes(const long long *n, int count) {
     if (!n || count < 1) return 0;
     return (size_t)loss_num_ctas(n, count) * sizeof(float);

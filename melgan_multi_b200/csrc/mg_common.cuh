@@ -54,6 +54,11 @@ int launch_disc_group4_tc(const float *x, float *out, const uint8_t *wtc, const 
                           cudaStream_t s);
 int launch_disc_pack(const float *const *v, const float *const *g, const float *const *bias, void *packed, cudaStream_t s);
 void msd_lengths(int L, int *lens);
+size_t grouped_bwd_workspace_bytes(int l, int Bt, int Lout);
+int launch_disc_grouped_backward(const void *blob, int l, const float *dz, const float *x, float *dx, float *dw, float *db,
+                                 float *ws, int Bt, int Lin, int Lout, cudaStream_t s);
+int launch_disc_wn_backward(const float *const *v, const float *const *g, const float *const *dw, float *const *dv,
+                            float *const *dg, cudaStream_t s);
 long long loss_num_ctas(const long long *n, int count);
 int launch_loss_forward(const float *const *a, const float *const *b, const long long *n, const int *mode, int count, float *out,
                         float *partial, cudaStream_t s);

@@ -1,0 +1,239 @@
+// Backward of the discriminators' grouped convs (layers 1..4 of models.py:78-82: k41, pad 20, 4 input channels per group,
+// stride 4/4/4/1) and of weight-norm for all 21 discriminator layers.  cuDNN runs a grouped conv's backward as one small
+// kernel per group (thousands of launches per step: 29 ms of a 32 ms training step at BASELINE config 3); here each
+// gradient is one launch.  fp32 SIMT: the FLOPs are small (1.4 GF per layer), the dense layers' backward stays on
+// cuDNN (aten::convolution_backward) for now.
+//
+//   dz [Bt][Cout][Lout]  = upstream gradient already multiplied by LeakyReLU'(output)
+//   dx [Bt][Cin][Lin]    = sum_co sum_{k: 4t + k - 20 = p} dz[co][t] w[co][ci][k]            (grouped_dx_kernel)
+//   dw [Cout][4][41]     = sum_b sum_t dz[co][t] x[ci][S t + k - 20],  db[co] = sum dz       (grouped_dw_kernel + combine)
+#include "mg_common.cuh"
+
+namespace mg {
+
+// ------------------------------------------------------------------------------------------------------------------
+// dx.  CTA = (tile of 256 input positions, group, item); thread = 2 positions x 4 input channels.
+// w: packed fp32 [group][ci 4][tap 41][co COG] (d_weight_offset(l)).
+template <int COG, int S>
+__global__ void __launch_bounds__(128) grouped_dx_kernel(const float *__restrict__ dz, float *__restrict__ dx,
+                                                         const float *__restrict__ w, int Cin, int Cout, int Lin, int Lout) {
+    constexpr int TP = 256, NT_ = TP / S + 41 / S + 2;  // dz positions a tile can touch
+    __shared__ float ws[4 * 41 * COG];
+    __shared__ float zs[COG * NT_];
+    const int p0 = blockIdx.x * TP, g = blockIdx.y, b = blockIdx.z;
+    for (int i = threadIdx.x; i < 4 * 41 * COG; i += 128) ws[i] = w[(size_t)g * 4 * 41 * COG + i];
+    // t of position p, tap k: (p + 20 - k) / S; over the tile t ranges from floor((p0 + 20 - 40) / S) upwards
+    const int tb = (p0 - 20) >= 0 ? (p0 - 20) / S : -((20 - p0 + S - 1) / S);
+    for (int i = threadIdx.x; i < COG * NT_; i += 128) {
+        const int co = i / NT_, t = tb + i % NT_;
+        zs[i] = (t >= 0 && t < Lout) ? dz[((size_t)b * Cout + g * COG + co) * Lout + t] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int p = p0 + threadIdx.x + 128 * h;
+        if (p >= Lin) continue;
+        const int k0 = (p + 20) % S, tq = (p + 20) / S;  // tap k0 + S q reads t = tq - q
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+        for (int co = 0; co < COG; ++co) {
+            const float *zr = zs + co * NT_ + (tq - tb);
+#pragma unroll
+            for (int q = 0; q < (40 / S) + 1; ++q) {
+                const int k = k0 + S * q;
+                if (k <= 40) {
+                    const float z = zr[-q];
+#pragma unroll
+                    for (int ci = 0; ci < 4; ++ci) acc[ci] = fmaf(z, ws[(ci * 41 + k) * COG + co], acc[ci]);
+                }
+            }
+        }
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) dx[((size_t)b * Cin + g * 4 + ci) * Lin + p] = acc[ci];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// dw, db partial sums.  CTA = (chunk of (item, 128-output tile) pairs, group); thread (ci, k) owns the COG outputs
+// dw[.][ci][k]; threads 164 .. 164 + COG - 1 own db.  partial: [chunk][group][164 * COG + COG].
+template <int COG, int S>
+__global__ void __launch_bounds__(192) grouped_dw_kernel(const float *__restrict__ dz, const float *__restrict__ x,
+                                                         float *__restrict__ partial, int Bt, int Cin, int Cout, int Lin, int Lout,
+                                                         int tiles_per_item, int tiles_per_chunk) {
+    constexpr int TT = 128, XW = S * TT + 40;
+    __shared__ __align__(16) float zs[TT * COG];  // [t][co]
+    __shared__ float xs[4 * XW];                   // [ci][position - (S t0 - 20)]
+    const int g = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+    const int ci = tid / 41, k = tid - 41 * ci;    // valid for tid < 164
+    float acc[COG];
+#pragma unroll
+    for (int c = 0; c < COG; ++c) acc[c] = 0.f;
+    float bacc = 0.f;
+    const int total = Bt * tiles_per_item;
+    const int first = chunk * tiles_per_chunk, last = min(total, first + tiles_per_chunk);
+#pragma unroll 1
+    for (int tile = first; tile < last; ++tile) {
+        const int b = tile / tiles_per_item, t0 = (tile - b * tiles_per_item) * TT;
+        __syncthreads();
+        for (int i = tid; i < TT * COG; i += 192) {
+            const int co = i / TT, t = i - co * TT;  // coalesced along t
+            zs[t * COG + co] = (t0 + t < Lout) ? dz[((size_t)b * Cout + g * COG + co) * Lout + t0 + t] : 0.f;
+        }
+        for (int i = tid; i < 4 * XW; i += 192) {
+            const int c = i / XW, p = S * t0 - 20 + (i - c * XW);
+            xs[i] = (p >= 0 && p < Lin) ? x[((size_t)b * Cin + g * 4 + c) * Lin + p] : 0.f;
+        }
+        __syncthreads();
+        if (tid < 164) {
+            const float *xr = xs + ci * XW + k;
+#pragma unroll 4
+            for (int t = 0; t < TT; ++t) {
+                const float xv = xr[S * t];
+#pragma unroll
+                for (int c4 = 0; c4 < COG / 4; ++c4) {
+                    const float4 z = *reinterpret_cast<const float4 *>(zs + t * COG + 4 * c4);
+                    acc[4 * c4 + 0] = fmaf(z.x, xv, acc[4 * c4 + 0]);
+                    acc[4 * c4 + 1] = fmaf(z.y, xv, acc[4 * c4 + 1]);
+                    acc[4 * c4 + 2] = fmaf(z.z, xv, acc[4 * c4 + 2]);
+                    acc[4 * c4 + 3] = fmaf(z.w, xv, acc[4 * c4 + 3]);
+                }
+            }
+        } else if (tid < 164 + COG) {
+            for (int t = 0; t < TT; ++t) bacc += zs[t * COG + (tid - 164)];
+        }
+    }
+    float *out = partial + ((size_t)chunk * gridDim.y + g) * (165 * COG);
+    if (tid < 164) {
+#pragma unroll
+        for (int c = 0; c < COG; ++c) out[tid * COG + c] = acc[c];
+    } else if (tid < 164 + COG) {
+        out[164 * COG + (tid - 164)] = bacc;
+    }
+}
+
+// fixed-order combination of the chunk partials -> dw [Cout][4][41] (the weight_v layout), db [Cout]
+template <int COG>
+__global__ void __launch_bounds__(256) grouped_dw_combine_kernel(const float *__restrict__ partial, float *__restrict__ dw,
+                                                                 float *__restrict__ db, int groups, int chunks) {
+    const int per_group = 165 * COG;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= groups * per_group) return;
+    const int g = i / per_group, r = i - g * per_group;
+    float s = 0.f;
+    for (int c = 0; c < chunks; ++c) s += partial[((size_t)c * groups + g) * per_group + r];
+    if (r < 164 * COG) {
+        const int cik = r / COG, co = r - cik * COG;  // cik = ci * 41 + k
+        dw[((size_t)(g * COG + co)) * 164 + cik] = s;
+    } else {
+        db[g * COG + (r - 164 * COG)] = s;
+    }
+}
+
+struct GroupedBwdPlan {
+    int tiles_per_item, tiles_per_chunk, chunks;
+};
+static GroupedBwdPlan grouped_plan(int groups, int Bt, int Lout) {
+    GroupedBwdPlan p;
+    p.tiles_per_item = (Lout + 127) / 128;
+    const int total = Bt * p.tiles_per_item;
+    int want = (592 + groups - 1) / groups;  // ~4 CTAs per SM over all groups
+    if (want > total) want = total;
+    if (want < 1) want = 1;
+    p.tiles_per_chunk = (total + want - 1) / want;
+    p.chunks = (total + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
+    return p;
+}
+
+size_t grouped_bwd_workspace_bytes(int l, int Bt, int Lout) {
+    const DLayer d = d_layer(l);
+    const int cog = d.cout / d.groups;
+    return (size_t)grouped_plan(d.groups, Bt, Lout).chunks * d.groups * 165 * cog * sizeof(float);
+}
+
+template <int COG, int S>
+static int grouped_backward(const float *w, const float *dz, const float *x, float *dx, float *dw, float *db, float *ws, int Bt,
+                            int Cin, int Cout, int Lin, int Lout, cudaStream_t s) {
+    const int groups = Cin / 4;
+    if (dx) {
+        dim3 grid((Lin + 255) / 256, groups, Bt);
+        grouped_dx_kernel<COG, S><<<grid, 128, 0, s>>>(dz, dx, w, Cin, Cout, Lin, Lout);
+        MG_CUDA_TRY(cudaGetLastError());
+    }
+    if (dw) {
+        const GroupedBwdPlan p = grouped_plan(groups, Bt, Lout);
+        dim3 grid(p.chunks, groups);
+        grouped_dw_kernel<COG, S><<<grid, 192, 0, s>>>(dz, x, ws, Bt, Cin, Cout, Lin, Lout, p.tiles_per_item, p.tiles_per_chunk);
+        MG_CUDA_TRY(cudaGetLastError());
+        const int n = groups * 165 * COG;
+        grouped_dw_combine_kernel<COG><<<(n + 255) / 256, 256, 0, s>>>(ws, dw, db, groups, p.chunks);
+        MG_CUDA_TRY(cudaGetLastError());
+    }
+    return MG_OK;
+}
+
+// blob: one discriminator's packed weights (scale sc of the MSD blob); layer l in 1..4
+int launch_disc_grouped_backward(const void *blob, int l, const float *dz, const float *x, float *dx, float *dw, float *db,
+                                 float *ws, int Bt, int Lin, int Lout, cudaStream_t s) {
+    const DLayer d = d_layer(l);
+    const float *w = reinterpret_cast<const float *>(blob) + d_weight_offset(l);
+    if (Bt > 65535) return set_error(MG_ERR_INVALID_ARGUMENT, "discriminator batch %d exceeds 65535", Bt);
+    if (l == 4) return grouped_backward<4, 1>(w, dz, x, dx, dw, db, ws, Bt, d.cin, d.cout, Lin, Lout, s);
+    return grouped_backward<16, 4>(w, dz, x, dx, dw, db, ws, Bt, d.cin, d.cout, Lin, Lout, s);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// weight-norm backward for all 21 layers in one launch (one CTA per norm row, like disc_pack_kernel):
+//   w = g v / |v|   =>   dg = <dw, v> / |v|,   dv = (g / |v|) (dw - <dw, v> v / |v|^2)
+struct DiscWnArgs {
+    const float *v[3 * kDiscLayers];
+    const float *g[3 * kDiscLayers];
+    const float *dw[3 * kDiscLayers];
+    float *dv[3 * kDiscLayers];
+    float *dg[3 * kDiscLayers];
+};
+
+__global__ void __launch_bounds__(128) disc_wn_backward_kernel(const __grid_constant__ DiscWnArgs a) {
+    int grow = blockIdx.x;
+    const int d = grow / kDiscRows;
+    grow -= d * kDiscRows;
+    int l = 0;
+#pragma unroll 1
+    while (grow >= d_layer(l).cout) { grow -= d_layer(l).cout; ++l; }
+    const DLayer sh = d_layer(l);
+    const int inner = (sh.cin / sh.groups) * sh.k, idx = d * kDiscLayers + l;
+    if (!a.dw[idx]) return;
+    const float *vr = a.v[idx] + (size_t)grow * inner, *dwr = a.dw[idx] + (size_t)grow * inner;
+    float ss = 0.f, dot = 0.f;
+    for (int j = threadIdx.x; j < inner; j += 128) {
+        ss = fmaf(vr[j], vr[j], ss);
+        dot = fmaf(dwr[j], vr[j], dot);
+    }
+    __shared__ float red[2][4];
+    for (int o = 16; o > 0; o >>= 1) {
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = ss; red[1][threadIdx.x >> 5] = dot; }
+    __syncthreads();
+    ss = (red[0][0] + red[0][1]) + (red[0][2] + red[0][3]);
+    dot = (red[1][0] + red[1][1]) + (red[1][2] + red[1][3]);
+    const float inv = rsqrtf(ss), gv = a.g[idx][grow];
+    const float sc = gv * inv, proj = dot / ss;
+    float *dvr = a.dv[idx] + (size_t)grow * inner;
+    for (int j = threadIdx.x; j < inner; j += 128) dvr[j] = sc * (dwr[j] - proj * vr[j]);
+    if (threadIdx.x == 0) a.dg[idx][grow] = dot * inv;
+}
+
+int launch_disc_wn_backward(const float *const *v, const float *const *g, const float *const *dw, float *const *dv,
+                            float *const *dg, cudaStream_t s) {
+    DiscWnArgs a;
+    for (int i = 0; i < 3 * kDiscLayers; ++i) {
+        if (!v[i] || !g[i] || (dw[i] && (!dv[i] || !dg[i]))) return set_error(MG_ERR_INVALID_ARGUMENT, "mg_msd_wn_backward: null tensor %d", i);
+        a.v[i] = v[i]; a.g[i] = g[i]; a.dw[i] = dw[i]; a.dv[i] = dv[i]; a.dg[i] = dg[i];
+    }
+    disc_wn_backward_kernel<<<3 * kDiscRows, 128, 0, s>>>(a);
+    MG_CUDA_TRY(cudaGetLastError());
+    return MG_OK;
+}
+
+}  // namespace mg

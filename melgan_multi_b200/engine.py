@@ -68,6 +68,13 @@ def lib():
         L.mg_msd_forward.restype = ctypes.c_int
         L.mg_msd_forward.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                      ctypes.c_void_p, ctypes.c_void_p]
+        L.mg_msd_grouped_backward_workspace_bytes.restype = ctypes.c_size_t
+        L.mg_msd_grouped_backward_workspace_bytes.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        L.mg_msd_grouped_backward.restype = ctypes.c_int
+        L.mg_msd_grouped_backward.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 6 + [
+            ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        L.mg_msd_wn_backward.restype = ctypes.c_int
+        L.mg_msd_wn_backward.argtypes = [ctypes.c_void_p] * 6
         L.mg_loss_workspace_bytes.restype = ctypes.c_size_t
         L.mg_loss_workspace_bytes.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.mg_loss_forward.restype = ctypes.c_int
@@ -335,6 +342,41 @@ class DiscriminatorDevice:
             stream = torch.cuda.current_stream().cuda_stream
             check(lib().mg_msd_forward(self.packed.data_ptr(), y.data_ptr(), Bt, L, ptrs, self.status.data_ptr(), stream))
         return fmaps
+
+    def grouped_backward(self, scale, layer, dz, x, need_dx=True):
+        """Gradients of grouped conv `layer` (1..4) of discriminator `scale`: dz [Bt, Cout, Lout] (already multiplied by
+        LeakyReLU'), x [Bt, Cin, Lin] the layer input -> (dx or None, dw [Cout, 4, 41] w.r.t. the folded weight, db)."""
+        torch = self.torch
+        dz, x = dz.contiguous(), x.contiguous()
+        Bt, cout, Lout = dz.shape
+        _, cin, Lin = x.shape
+        dx = torch.empty_like(x) if need_dx else None
+        dw = torch.empty((cout, 4, 41), dtype=torch.float32, device=self.device)
+        db = torch.empty(cout, dtype=torch.float32, device=self.device)
+        nbytes = lib().mg_msd_grouped_backward_workspace_bytes(layer, Bt, Lout)
+        ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            check(lib().mg_msd_grouped_backward(self.packed.data_ptr(), scale, layer, dz.data_ptr(), x.data_ptr(),
+                                                dx.data_ptr() if need_dx else None, dw.data_ptr(), db.data_ptr(),
+                                                ws.data_ptr(), nbytes, Bt, Lin, Lout, stream))
+        return dx, dw, db
+
+    def wn_backward(self, vs, gs, dws):
+        """(d weight_v, d weight_g) of the 21 layers from the gradients of their folded weights (None: layer skipped)."""
+        torch = self.torch
+        vs = [t.detach().contiguous() for t in vs]
+        gs = [t.detach().contiguous() for t in gs]
+        dws = [t.contiguous() if t is not None else None for t in dws]
+        dvs = [torch.empty_like(v) if d is not None else None for v, d in zip(vs, dws)]
+        dgs = [torch.empty_like(g) if d is not None else None for g, d in zip(gs, dws)]
+
+        def arr(ts):
+            return _ptr_array([t.data_ptr() if t is not None else None for t in ts])
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            check(lib().mg_msd_wn_backward(arr(vs), arr(gs), arr(dws), arr(dvs), arr(dgs), stream))
+        return dvs, dgs
 
     def check_status(self):
         torch = self.torch

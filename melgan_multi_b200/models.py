@@ -18,8 +18,9 @@ What runs where
     conv_pre, grouped k41 convs and conv_post1 on tcgen05 -- after one launch that folds weight-norm for the 21 layers.
   * ``feature_loss`` / ``generator_loss`` / ``discriminator_loss`` (models.py:138-167) on CUDA tensors: every term of a
     loss is a row of one fused reduction launch (forward) and one gradient launch (backward).
-  * Backward passes (generator and discriminators) are NOT native yet: they run as recomputation through stock
-    PyTorch ops so that train.py keeps working.  Open row in DESIGN.md, never part of a benchmark or parity claim.
+  * Backward: the generator's runs as recomputation through stock PyTorch ops; the discriminators' walks the saved
+    feature maps layer by layer with hand-written kernels for the grouped convs and weight-norm and
+    aten::convolution_backward for the three dense layers.  Open row in DESIGN.md (native tcgen05 dgrad / wgrad).
 """
 import torch
 import torch.nn as nn
@@ -186,31 +187,67 @@ class Discriminator(nn.Module):
 
 
 class _MSDFunction(torch.autograd.Function):
-    """Forward on the fused sm_100a kernels (real and generated stacked as one batch); backward by recomputation through
-    stock PyTorch ops (open row: native backward).  Inputs: stacked audio [2B,1,L], then 21 x (weight_v, weight_g, bias);
-    outputs: the 21 feature maps, scale-major."""
+    """Forward on the fused sm_100a kernels (real and generated stacked as one batch).  Backward layer by layer on the
+    saved feature maps, without recomputing the forward: the grouped k41 convs (layers 1..4) and weight-norm on the
+    hand-written kernels of csrc/mg_disc_bwd.cu (cuDNN launches one kernel per group for them), the dense layers
+    (conv_pre, conv_post1, conv_post2) through aten::convolution_backward (open row: native tcgen05 dgrad/wgrad).
+    Inputs: stacked audio [2B,1,L], then 21 x (weight_v, weight_g, bias); outputs: the 21 feature maps, scale-major."""
 
     @staticmethod
     def forward(ctx, msd, y2, *params):
         ctx.msd = msd
-        ctx.save_for_backward(y2, *params)
         fmaps = msd._engine_forward(y2)
-        return tuple(f for sc in fmaps for f in sc)
+        flat = tuple(f for sc in fmaps for f in sc)
+        ctx.save_for_backward(y2, *params, *flat)
+        return flat
 
     @staticmethod
     def backward(ctx, *grads):
-        msd = ctx.msd
-        y2, *params = ctx.saved_tensors
-        with torch.enable_grad():
-            y_ = y2.detach().requires_grad_(ctx.needs_input_grad[1])
-            leaves = [p.detach().requires_grad_(True) for p in params]
-            outs = msd._torch_forward(y_, leaves)
-            pairs = [(o, g) for o, g in zip(outs, grads) if g is not None]
-            wanted = ([y_] if ctx.needs_input_grad[1] else []) + leaves
-            gs = torch.autograd.grad([o for o, _ in pairs], wanted, [g for _, g in pairs], allow_unused=True)
-        gs = list(gs)
-        gy = gs.pop(0) if ctx.needs_input_grad[1] else None
-        return (None, gy, *gs)
+        msd, dev = ctx.msd, ctx.msd._dev
+        saved = ctx.saved_tensors
+        n = 3 * len(DISCRIMINATOR_LAYERS)
+        y2, params, fm = saved[0], saved[1:1 + 3 * n], saved[1 + 3 * n:]
+        need_y = ctx.needs_input_grad[1]
+        dws, dbs, g_in = [None] * n, [None] * n, []
+        x0, pooled = y2, [y2]
+        for s in range(3):
+            if s > 0:
+                x0 = msd.meanpools[s - 1](x0)
+                pooled.append(x0)
+            inputs = [x0] + list(fm[7 * s:7 * s + 6])
+            g = None
+            for l in range(6, -1, -1):
+                i = 7 * s + l
+                go = grads[i]
+                gt = go if g is None else g if go is None else g + go
+                if gt is None:
+                    continue
+                out = fm[i]
+                dz = (torch.where(out > 0, gt, gt * 0.01) if l < 6 else gt).contiguous()
+                need_dx = l > 0 or need_y
+                _n, _cin, cout, _k, stride, groups, pad = DISCRIMINATOR_LAYERS[l]
+                if groups > 1:
+                    g, dws[i], dbs[i] = dev.grouped_backward(s, l, dz, inputs[l], need_dx)
+                else:
+                    w = torch._weight_norm(params[3 * i], params[3 * i + 1], 0)
+                    g, dws[i], dbs[i] = torch.ops.aten.convolution_backward(
+                        dz, inputs[l], w, [cout], [stride], [pad], [1], False, [0], 1, [need_dx, True, True])
+            g_in.append(g)
+        gy = None
+        if need_y:  # AvgPool chain (models.py:114-117,125-127): linear, so its backward is differentiated on zeros
+            for s in (2, 1):
+                if g_in[s] is None:
+                    continue
+                with torch.enable_grad():
+                    a = torch.zeros_like(pooled[s - 1]).requires_grad_(True)
+                    (ga,) = torch.autograd.grad(msd.meanpools[s - 1](a), a, g_in[s])
+                g_in[s - 1] = ga if g_in[s - 1] is None else g_in[s - 1] + ga
+            gy = g_in[0]
+        dvs, dgs = dev.wn_backward([params[3 * i] for i in range(n)], [params[3 * i + 1] for i in range(n)], dws)
+        out = []
+        for i in range(n):
+            out += [dvs[i], dgs[i], dbs[i]]
+        return (None, gy, *out)
 
 
 class MultiScaleDiscriminator(nn.Module):

@@ -148,3 +148,32 @@ def test_msd_is_deterministic_and_batch_items_are_independent(msd_module):
         for j in range(7):
             assert torch.equal(a[2][i][j], b[2][i][j]) and torch.equal(a[3][i][j], b[3][i][j])
             assert torch.equal(a[2][i][j][1:2], one[2][i][j]) and torch.equal(a[3][i][j][1:2], one[3][i][j])
+
+
+@pytest.mark.parametrize("layer,Bt,Lin", [(1, 3, 1025), (1, 2, 4096), (2, 2, 257), (3, 2, 65), (3, 5, 300), (4, 3, 17), (4, 2, 130)])
+def test_grouped_conv_backward_matches_torch(msd_module, layer, Bt, Lin):
+    """csrc/mg_disc_bwd.cu (dx, dw, db of the grouped k41 convs) against autograd of F.conv1d in strict fp32; ragged
+    lengths cover the stride-4 phase logic at both edges and partial tiles."""
+    import torch.nn.functional as F
+    from melgan_multi_b200.synth import DISCRIMINATOR_LAYERS
+    old = torch.backends.cudnn.conv.fp32_precision
+    torch.backends.cudnn.conv.fp32_precision = "ieee"
+    try:
+        with torch.no_grad():
+            msd_module(torch.zeros(1, 1, 64).cuda(), torch.zeros(1, 1, 64).cuda())  # makes sure the weights are packed
+        scale = 1
+        _n, cin, cout, k, stride, groups, pad = DISCRIMINATOR_LAYERS[layer]
+        conv = msd_module.discriminators[scale].layers()[layer]
+        w = torch._weight_norm(conv.weight_v, conv.weight_g, 0).detach().requires_grad_(True)
+        gen = torch.Generator(device="cpu").manual_seed(100 * layer + Lin)
+        x = torch.randn(Bt, cin, Lin, generator=gen).cuda().requires_grad_(True)
+        out = F.conv1d(x, w, None, stride, pad, 1, groups)
+        dz = torch.randn(out.shape, generator=gen).cuda()
+        rdx, rdw = torch.autograd.grad(out, (x, w), dz)
+        dx, dw, db = msd_module._dev.grouped_backward(scale, layer, dz, x.detach())
+        for got, ref in ((dx, rdx), (dw, rdw), (db, dz.sum(dim=(0, 2)))):
+            m, l2 = rel_errors(got.cpu().numpy(), ref.cpu().numpy())
+            assert m < 2e-5 and l2 < 2e-5, (m, l2)
+        assert msd_module._dev.grouped_backward(scale, layer, dz, x.detach(), need_dx=False)[0] is None
+    finally:
+        torch.backends.cudnn.conv.fp32_precision = old
