@@ -53,6 +53,62 @@ __global__ void __launch_bounds__(128) grouped_dx_kernel(const float *__restrict
     }
 }
 
+// Stride-4 specialisation (layers 1..3: 16 output channels per group).  The four positions p = 4j .. 4j+3 read the same dz
+// values (t = j + 5 - q) through taps k = 4q + (p & 3), so a thread owns a quad of positions x 4 input channels and one
+// float4 of four consecutive taps feeds 4 FMAs per dz load: 16 FMAs per 5 shared-memory loads (the generic kernel: 4).
+__global__ void __launch_bounds__(128) grouped_dx4_kernel(const float *__restrict__ dz, float *__restrict__ dx,
+                                                          const float *__restrict__ w, int Cin, int Cout, int Lin, int Lout) {
+    constexpr int COG = 16, TP = 512, NT_ = TP / 4 + 12, KP = 44;  // taps padded to 44 per (co, ci)
+    __shared__ __align__(16) float ws[COG * 4 * KP];               // [co][ci][k]
+    __shared__ float zs[COG * NT_];
+    const int p0 = blockIdx.x * TP, g = blockIdx.y, b = blockIdx.z;
+    for (int i = threadIdx.x; i < COG * 4 * KP; i += 128) {
+        const int co = i / (4 * KP), ci = (i / KP) & 3, k = i % KP;
+        ws[i] = k < 41 ? w[(size_t)g * 4 * 41 * COG + (ci * 41 + k) * COG + co] : 0.f;
+    }
+    const int tb = p0 / 4 - 5;  // dz position of zs column 0: t = j + 5 - q >= p0/4 - 5
+    for (int i = threadIdx.x; i < COG * NT_; i += 128) {
+        const int co = i / NT_, t = tb + i % NT_;
+        zs[i] = (t >= 0 && t < Lout) ? dz[((size_t)b * Cout + g * COG + co) * Lout + t] : 0.f;
+    }
+    __syncthreads();
+    const int j = threadIdx.x, p = p0 + 4 * j;  // quad of positions p .. p + 3
+    if (p >= Lin) return;
+    float acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) acc[r][ci] = 0.f;
+#pragma unroll 1
+    for (int co = 0; co < COG; ++co) {
+        const float *zr = zs + co * NT_ + j + 10;  // column of t = j + 5 (tb = p0/4 - 5): j + 5 - tb + ... = j + 10
+        const float *wr = ws + co * 4 * KP;
+#pragma unroll
+        for (int q = 0; q < 11; ++q) {  // q = 10: only tap 40 is real (41..43 are zero padding)
+            const float z = zr[-q];
+#pragma unroll
+            for (int ci = 0; ci < 4; ++ci) {
+                const float4 wv = *reinterpret_cast<const float4 *>(wr + ci * KP + 4 * q);
+                acc[0][ci] = fmaf(z, wv.x, acc[0][ci]);
+                acc[1][ci] = fmaf(z, wv.y, acc[1][ci]);
+                acc[2][ci] = fmaf(z, wv.z, acc[2][ci]);
+                acc[3][ci] = fmaf(z, wv.w, acc[3][ci]);
+            }
+        }
+    }
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci) {
+        float *o = dx + ((size_t)b * Cin + g * 4 + ci) * Lin + p;
+        if ((Lin & 3) == 0) {
+            *reinterpret_cast<float4 *>(o) = make_float4(acc[0][ci], acc[1][ci], acc[2][ci], acc[3][ci]);
+        } else {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (p + r < Lin) o[r] = acc[r][ci];
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // dw, db partial sums.  CTA = (chunk of (item, 128-output tile) pairs, group); thread (ci, k) owns the COG outputs
 // dw[.][ci][k]; threads 164 .. 164 + COG - 1 own db.  partial: [chunk][group][164 * COG + COG].
@@ -155,8 +211,13 @@ static int grouped_backward(const float *w, const float *dz, const float *x, flo
                             int Cin, int Cout, int Lin, int Lout, cudaStream_t s) {
     const int groups = Cin / 4;
     if (dx) {
-        dim3 grid((Lin + 255) / 256, groups, Bt);
-        grouped_dx_kernel<COG, S><<<grid, 128, 0, s>>>(dz, dx, w, Cin, Cout, Lin, Lout);
+        if (S == 4 && COG == 16) {
+            dim3 grid((Lin + 511) / 512, groups, Bt);
+            grouped_dx4_kernel<<<grid, 128, 0, s>>>(dz, dx, w, Cin, Cout, Lin, Lout);
+        } else {
+            dim3 grid((Lin + 255) / 256, groups, Bt);
+            grouped_dx_kernel<COG, S><<<grid, 128, 0, s>>>(dz, dx, w, Cin, Cout, Lin, Lout);
+        }
         MG_CUDA_TRY(cudaGetLastError());
     }
     if (dw) {
