@@ -207,7 +207,7 @@ def run_reference(args):
     val = args.steps * sample_B * T_FRAMES * 256 / dt
     sample = "B=%d of the 64 x 80x32 mel segments per step, PyTorch-CPU (oneDNN) port of the reference forward, %d threads" % (
         sample_B, cores)
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -217,7 +217,26 @@ def run_reference(args):
     }))
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout must carry exactly ONE JSON line, but libraries write there too (NCCL prints its version banner to fd 1
+    whatever NCCL_DEBUG_FILE says): keep a private copy of the real stdout for the result and point fd 1 at stderr."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    _JSON_OUT.write(json.dumps(obj) + "\n")
+    _JSON_OUT.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -376,7 +395,7 @@ def main():
                          "oracle/torch_port.py = the reference forward on PyTorch-CPU/oneDNN, all threads" % (iters, med)}
 
     if rank == 0:
-        print(json.dumps({
+        emit(({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": ("f32 in/out; products as 3 split-bf16 tcgen05 passes with fp32 accumulation (fp32-equivalent, ~1e-5)"

@@ -161,6 +161,16 @@ int mg_msd_grouped_backward(const void *packed, int scale, int layer, const floa
 int mg_msd_wn_backward(const float *const *v, const float *const *g, const float *const *dw, float *const *dv,
                        float *const *dg, void *stream);
 
+/* ---- multi-tensor Adam (the optimizer step either side of the path: train.py:51-52,118,129) -------------------------
+ * One launch updates `count` parameter tensors.  p, g, m, v: DEVICE arrays of `count` device pointers (parameter,
+ * gradient, exp_avg, exp_avg_sq); n: DEVICE array of element counts; first: DEVICE array of count + 1 ints with
+ * first[i] = sum_{j<i} ceil(n[j] / mg_adam_chunk()), total_ctas = first[count].  `step` is the 1-based step number of
+ * this update.  Arithmetic of torch.optim.Adam (L2 weight decay, no amsgrad). */
+int mg_adam_chunk(void);
+int mg_adam_step(float *const *p, const float *const *g, float *const *m, float *const *v, const long long *n,
+                 const int *first, int count, int total_ctas, float lr, float beta1, float beta2, float eps,
+                 float weight_decay, long long step, void *stream);
+
 /* ---- fused loss reductions (reference: feature_loss / discriminator_loss / generator_loss, models.py:138-167) ----
  * A loss is a table of `count` (<= 24) rows; out[i] = mean over the n[i] elements of
  *   mode 0: |a[i] - b[i]|   (one feature-map pair of feature_loss, models.py:142)

@@ -165,6 +165,14 @@ int mg_msd_wn_backward(const float *const *v, const float *const *g, const float
     return launch_disc_wn_backward(v, g, dw, dv, dg, (cudaStream_t)stream);
 }
 
+int mg_adam_chunk(void) { return 4096; }
+
+int mg_adam_step(float *const *p, const float *const *g, float *const *m, float *const *v, const long long *n,
+                 const int *first, int count, int total_ctas, float lr, float beta1, float beta2, float eps,
+                 float weight_decay, long long step, void *stream) {
+    return launch_adam(p, g, m, v, n, first, count, total_ctas, lr, beta1, beta2, eps, weight_decay, step, (cudaStream_t)stream);
+}
+
 size_t mg_loss_workspace_bytes(const long long *n, int count) {
     if (!n || count < 1) return 0;
     return (size_t)loss_num_ctas(n, count) * sizeof(float);

@@ -59,6 +59,8 @@ int launch_disc_grouped_backward(const void *blob, int l, const float *dz, const
                                  float *ws, int Bt, int Lin, int Lout, cudaStream_t s);
 int launch_disc_wn_backward(const float *const *v, const float *const *g, const float *const *dw, float *const *dv,
                             float *const *dg, cudaStream_t s);
+int launch_adam(float *const *p, const float *const *g, float *const *m, float *const *v, const long long *n, const int *first,
+                int count, int total_ctas, float lr, float b1, float b2, float eps, float wd, long long step, cudaStream_t s);
 long long loss_num_ctas(const long long *n, int count);
 int launch_loss_forward(const float *const *a, const float *const *b, const long long *n, const int *mode, int count, float *out,
                         float *partial, cudaStream_t s);

@@ -75,6 +75,10 @@ def lib():
             ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
         L.mg_msd_wn_backward.restype = ctypes.c_int
         L.mg_msd_wn_backward.argtypes = [ctypes.c_void_p] * 6
+        L.mg_adam_chunk.restype = ctypes.c_int
+        L.mg_adam_step.restype = ctypes.c_int
+        L.mg_adam_step.argtypes = [ctypes.c_void_p] * 6 + [ctypes.c_int, ctypes.c_int] + [ctypes.c_float] * 5 + [
+            ctypes.c_longlong, ctypes.c_void_p]
         L.mg_loss_workspace_bytes.restype = ctypes.c_size_t
         L.mg_loss_workspace_bytes.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.mg_loss_forward.restype = ctypes.c_int

@@ -2,6 +2,7 @@
 discriminators, then D step on the detached audio; Adam on both) at batch 16 x 8192 samples, fp32.
   ours  : drop-in modules -- native forwards (generator, discriminators, fused losses), backward by recomputation
           through stock PyTorch ops (the open row of DESIGN.md section 8)
+  ours_with_multi_tensor_adam : + melgan_multi_b200.optim.Adam (one launch per optimizer step) instead of torch.optim.Adam
   stock : the same modules' stock-PyTorch restatement (_torch_forward) end to end, cuDNN default (TF32) and strict fp32
 Prints step times and the relative difference of the losses of the first step."""
 import json
@@ -57,12 +58,12 @@ def torch_losses():
     return feature_loss, generator_loss, discriminator_loss
 
 
-def run(gen, disc, losses, x, y, steps, warmup):
+def run(gen, disc, losses, x, y, steps, warmup, adam=torch.optim.Adam):
     feature_loss, generator_loss, discriminator_loss = losses
     params_g = [p for p in gen.parameters()]
     params_d = [p for p in disc.parameters()]
-    og = torch.optim.Adam(params_g, 1e-4, betas=(0.5, 0.9))
-    od = torch.optim.Adam(params_d, 1e-4, betas=(0.5, 0.9))
+    og = adam(params_g, 1e-4, betas=(0.5, 0.9))
+    od = adam(params_d, 1e-4, betas=(0.5, 0.9))
     first = None
     times = []
     for it in range(warmup + steps):
@@ -96,8 +97,12 @@ def main():
     y = torch.from_numpy(synth.audio_input(16, 8192, 0)).cuda()
     out = {"config": "BASELINE config 3: B=16, 80x32 mel / 8192-sample segments, fp32, G step + D step + Adam"}
     g, d = build()
-    ms, first = run(g, d, (models.feature_loss, models.generator_loss, models.discriminator_loss), x, y, steps, warmup)
+    ours_losses = (models.feature_loss, models.generator_loss, models.discriminator_loss)
+    ms, first = run(g, d, ours_losses, x, y, steps, warmup)
     out["ours_ms"], out["ours_first_losses"] = ms, first
+    from melgan_multi_b200.optim import Adam
+    g, d = build()
+    out["ours_with_multi_tensor_adam_ms"] = run(g, d, ours_losses, x, y, steps, warmup, adam=Adam)[0]
     for prec in ("tf32", "ieee"):
         torch.backends.cudnn.conv.fp32_precision = prec
         g, d = build()
