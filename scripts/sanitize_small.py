@@ -1,11 +1,13 @@
-"""Tiny generator + discriminator forwards for compute-sanitizer (memcheck / racecheck / synccheck)."""
+"""Tiny generator + discriminator forwards, a sliced generator forward, one training step (fused losses, native
+discriminator backward, multi-tensor Adam) for compute-sanitizer (memcheck / racecheck / synccheck)."""
+import os
 import sys
 
-import numpy as np
 import torch
 
 sys.path.insert(0, ".")
-from melgan_multi_b200 import engine, models, synth
+from melgan_multi_b200 import models, synth
+from melgan_multi_b200.optim import Adam
 
 g = models.Generator()
 g.load_state_dict({k: torch.from_numpy(v) for k, v in synth.generator_state(1234).items()})
@@ -18,5 +20,21 @@ with torch.no_grad():
     g._dev.check_status(1, 3)
     out = d(y, torch.from_numpy(synth.audio_input(1, 768, 1)).cuda())
     d._dev.check_status()
+    if os.environ.get("MG_GEN_SLICES"):  # two batch-slice chains on forked streams
+        y2 = g(torch.from_numpy(synth.mel_input(2, 3, 6)).cuda())
+        g._dev.check_status(2, 3)
+# one train.py:108-129 step on a 512-sample segment
+g.train(); d.train()
+og, od = Adam(g.parameters(), 1e-4, betas=(0.5, 0.9)), Adam(d.parameters(), 1e-4, betas=(0.5, 0.9))
+x = torch.from_numpy(synth.mel_input(1, 2, 7)).cuda()
+yr = torch.from_numpy(synth.audio_input(1, 512, 8)).cuda()
+yh = g(x)
+dr, dg, fr, fg = d(yr, yh)
+loss = models.generator_loss(dg) + models.feature_loss(fr, fg)
+loss.backward(); og.step()
+od.zero_grad()
+dr, dg, _, _ = d(yr, yh.detach())
+ld, _, _ = models.discriminator_loss(dr, dg)
+ld.backward(); od.step()
 torch.cuda.synchronize()
-print("ok", float(y.abs().sum()), float(out[0][0].abs().sum()))
+print("ok", float(y.abs().sum()), float(out[0][0].abs().sum()), float(loss), float(ld))
