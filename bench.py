@@ -330,6 +330,8 @@ def main():
         flops_of["stage%d(up+res)" % i] = up_f[i] + res_f[i]
     flops_of["stage3(up+res+post)"] = up_f[3] + res_f[3] + post_f * frames
     flops_of["res3+post"] = res_f[3] + post_f * frames
+    flops_of["up2+res2"] = up_f[2] + res_f[2]  # stride-2 ConvT fused into the stage kernel
+    flops_of["up3+res3+post"] = up_f[3] + res_f[3] + post_f * frames
     k_flops = [flops_of[n] for n in names]
     tc_path = os.environ.get("MG_GEN_PATH", "tc") != "simt"
     dom = names.index("res1") if tc_path else names.index("stage1(up+res)")
@@ -337,8 +339,9 @@ def main():
     fwd_flops = sum(k_flops)
     packed_bytes = engine.lib().mg_gen_packed_bytes()
     # algorithmic HBM bytes: SURVEY 8(d) per-stage-fused figure; the tc pipeline currently makes one extra
-    # round trip of each ConvT output (written by up_i, re-read by res_i): + 2 * (8+32+32+32) KB per mel frame
-    extra = 2 * (8192 + 32768 + 32768 + 32768) if tc_path else 0
+    # round trip of the stride-8 ConvT outputs (written by up_i, re-read by res_i): + 2 * (8+32) KB per mel frame
+    # (+ 2 * (32+32) KB when the stride-2 ConvTs run as separate kernels, MG_GEN_FUSE_UP=0)
+    extra = 2 * (8192 + 32768 + (0 if "up2+res2" in names else 32768) + (0 if "up3+res3+post" in names else 32768)) if tc_path else 0
     fwd_bytes = (ALG_BYTES_PER_FRAME + extra) * frames + packed_bytes
     fwd_ms = total_ms / K
     traffic = None  # dram bytes per launch of the dominant kernel, from the committed ncu --set full capture

@@ -97,6 +97,10 @@ int mg_gen_convt(const void *packed, int stage, const float *x, float *y, int B,
 /* One ResBlock (models.py:32-40) of stage `stage` (C = 256 >> stage channels) on the tensor-core path:
  * x, y [B, C, L] device fp32, x != y.  Synchronous; parity-test entry point for the tcgen05 kernel. */
 int mg_gen_resblock(const void *packed, int stage, const float *x, float *y, int B, int L, void *stream);
+/* Stage 2 or 3 as the pipeline runs it: LeakyReLU -> ConvTranspose1d(k4, s2) -> ResBlock in ONE kernel
+ * (models.py:64-66); x [B][2C][Lin] is the previous stage's output, y [B][C][2 Lin] (C = 64 / 32).  Synchronous, like
+ * mg_gen_resblock: a per-kernel parity entry point. */
+int mg_gen_upres(const void *packed, int stage, const float *x, float *y, int B, int Lin, void *stream);
 
 /* Diagnostic twin of mg_gen_resblock: also returns 128 clock64 stamps (host buffer) of one interior CTA's
  * epilogue and MMA roles (slot meaning documented at the definition in csrc/mg_api.cu). */

@@ -124,9 +124,15 @@ int mg_gen_forward_timed(const void *packed, const float *mel, float *audio, int
 
 const char *mg_gen_kernel_name(int i) {
     static const char *simt[] = {"conv_pre", "stage0(up+res)", "stage1(up+res)", "stage2(up+res)", "stage3(up+res+post)"};
-    static const char *tcn[] = {"conv_pre", "up0", "res0", "up1", "res1", "up2", "res2", "up3", "res3+post"};
+    static const char *tcn[4][9] = {
+        {"conv_pre", "up0", "res0", "up1", "res1", "up2", "res2", "up3", "res3+post"},
+        {"conv_pre", "up0", "res0", "up1", "res1", "up2+res2", "up3", "res3+post", ""},
+        {"conv_pre", "up0", "res0", "up1", "res1", "up2", "res2", "up3+res3+post", ""},
+        {"conv_pre", "up0", "res0", "up1", "res1", "up2+res2", "up3+res3+post", "", ""}};
     if (i < 0 || i >= mg_gen_forward_launches()) return "";
-    return use_tc() ? tcn[i] : simt[i];
+    const char *up = getenv("MG_UP_PATH");
+    const int fuse = (up && strcmp(up, "simt") == 0) ? 0 : generator_tc_fused_up();
+    return use_tc() ? tcn[fuse & 3][i] : simt[i];
 }
 
 int mg_gen_stage_output(const void *workspace, int which, float *out, int B, int T, void *stream) {
@@ -192,7 +198,11 @@ int mg_loss_backward(const float *const *a, const float *const *b, const long lo
     return launch_loss_backward(a, b, n, mode, count, grad_out, grad_a, grad_b, (cudaStream_t)stream);
 }
 
-int mg_gen_forward_launches(void) { return use_tc() ? generator_tc_num_launches() : generator_simt_num_launches(); }
+int mg_gen_forward_launches(void) {
+    if (!use_tc()) return generator_simt_num_launches();
+    const char *up = getenv("MG_UP_PATH");
+    return (up && strcmp(up, "simt") == 0) ? 9 : generator_tc_num_launches();
+}
 
 int mg_gen_forward_slices(int B, int T) { return (use_tc() && B >= 1 && T >= 1) ? generator_tc_slices(B, T) : 1; }
 
@@ -260,6 +270,24 @@ int mg_gen_resblock(const void *packed, int stage, const float *x, float *y, int
         if (e != cudaSuccess) rc = set_error(MG_ERR_CUDA, "mg_gen_resblock: %s", cudaGetErrorString(e));
         else if (cudaMemcpy(&h, st, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess || h)
             rc = set_error(MG_ERR_CUDA, "mg_gen_resblock: pipeline wait timed out (role code %d)", h);
+    }
+    cudaFree(st);
+    return rc;
+}
+
+int mg_gen_upres(const void *packed, int stage, const float *x, float *y, int B, int Lin, void *stream) {
+    if (!packed || !x || !y || x == y || (stage != 2 && stage != 3) || B < 1 || Lin < 1)
+        return set_error(MG_ERR_INVALID_ARGUMENT, "mg_gen_upres: bad argument");
+    int *st = nullptr;
+    MG_CUDA_TRY(cudaMalloc(&st, sizeof(int)));
+    cudaMemsetAsync(st, 0, sizeof(int), (cudaStream_t)stream);
+    int rc = launch_resblock_tc(x, y, (const float *)packed, 10 + stage, B, 2 * Lin, st, (cudaStream_t)stream);
+    int h = 0;
+    if (rc == MG_OK) {
+        cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+        if (e != cudaSuccess) rc = set_error(MG_ERR_CUDA, "mg_gen_upres: %s", cudaGetErrorString(e));
+        else if (cudaMemcpy(&h, st, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess || h)
+            rc = set_error(MG_ERR_CUDA, "mg_gen_upres: pipeline wait timed out (role code %d)", h);
     }
     cudaFree(st);
     return rc;

@@ -42,6 +42,7 @@ int launch_generator_simt(const float *packed, const float *mel, float *audio, i
                           cudaStream_t s, cudaEvent_t *ev = nullptr);
 int generator_simt_num_launches();
 int generator_tc_num_launches();
+int generator_tc_fused_up();  // bit 0: stage 2, bit 1: stage 3 run their stride-2 ConvT inside the ResBlock kernel
 int generator_tc_slices(int B, int T);  // batch slices (concurrent kernel chains) one forward is cut into
 int launch_generator_tc(const float *packed, const float *mel, float *audio, int B, int T, float *ws, int *status, bool up_tc,
                         cudaStream_t s, cudaEvent_t *ev = nullptr, const float *mel_host = nullptr, float *audio_host = nullptr);

@@ -399,7 +399,20 @@ static int launch_stage(const float *x, float *y, const float *packed, int stage
 }
 
 int generator_simt_num_launches() { return 5; }
-int generator_tc_num_launches() { return 9; }
+// Which stride-2 stages run their ConvT inside the ResBlock kernel: bit 0 = stage 2, bit 1 = stage 3.  Default: stage 3
+// only (measured at config 2: up3 + res3 194 -> 176 us fused, up2 + res2 221 -> 241 us: at C = 64 the extra serial phases
+// of the fused tile cost more than the separate ConvT kernel).  MG_GEN_FUSE_UP = 0 / 2 / 3 / 23 overrides (A/B runs).
+int generator_tc_fused_up() {
+    static const int mask = [] {
+        const char *e = getenv("MG_GEN_FUSE_UP");
+        if (!e) return 2;
+        int m = 0;
+        for (; *e; ++e) m |= (*e == '2') ? 1 : (*e == '3') ? 2 : 0;
+        return m;
+    }();
+    return mask;
+}
+int generator_tc_num_launches() { return 9 - (generator_tc_fused_up() & 1) - ((generator_tc_fused_up() >> 1) & 1); }
 
 // Tensor-core pipeline of one contiguous slice of the batch: conv_pre -> 4 x [ConvT (tcgen05) -> ResBlock (tcgen05)], the
 // last ResBlock with LeakyReLU -> conv_post -> tanh fused into its epilogue.  (up_tc = false swaps in the SIMT ConvT / pre.)
@@ -425,15 +438,27 @@ static int generator_tc_chain(const float *packed, const float *mel, float *audi
     MG_MARK(4);
     if ((rc = launch_resblock_tc(u, a[1], packed, 1, B, 64 * T, status, s))) return rc;
     MG_MARK(5);
-    if ((rc = up_tc ? launch_convt_tc(a[1], u, packed, 2, B, 64 * T, status, s) : launch_stage<Up2>(a[1], u, packed, 2, B, 64 * T, s))) return rc;
-    MG_MARK(6);
-    if ((rc = launch_resblock_tc(u, a[2], packed, 2, B, 128 * T, status, s))) return rc;
-    MG_MARK(7);
-    if ((rc = up_tc ? launch_convt_tc(a[2], u, packed, 3, B, 128 * T, status, s) : launch_stage<Up3>(a[2], u, packed, 3, B, 128 * T, s))) return rc;
-    MG_MARK(8);
-    // stage 4 = ResBlock 3 with LeakyReLU -> conv_post -> tanh fused into its final epilogue: writes the audio
-    if ((rc = launch_resblock_tc(u, audio, packed, 4, B, 256 * T, status, s))) return rc;
-    MG_MARK(9);
+    // stages 2 and 3 can run LeakyReLU -> ConvT(k4, s2) -> ResBlock (-> conv_post -> tanh) as ONE kernel reading the previous
+    // stage's output, so that the ConvT output never goes to HBM (generator_tc_fused_up(): bit 0 = stage 2, bit 1 = stage 3)
+    const int fuse = up_tc ? generator_tc_fused_up() : 0;
+    int m = 6;
+    if (fuse & 1) {
+        if ((rc = launch_resblock_tc(a[1], a[2], packed, 12, B, 128 * T, status, s))) return rc;
+    } else {
+        if ((rc = up_tc ? launch_convt_tc(a[1], u, packed, 2, B, 64 * T, status, s) : launch_stage<Up2>(a[1], u, packed, 2, B, 64 * T, s))) return rc;
+        MG_MARK(m); ++m;
+        if ((rc = launch_resblock_tc(u, a[2], packed, 2, B, 128 * T, status, s))) return rc;
+    }
+    MG_MARK(m); ++m;
+    if (fuse & 2) {
+        if ((rc = launch_resblock_tc(a[2], audio, packed, 14, B, 256 * T, status, s))) return rc;
+    } else {
+        if ((rc = up_tc ? launch_convt_tc(a[2], u, packed, 3, B, 128 * T, status, s) : launch_stage<Up3>(a[2], u, packed, 3, B, 128 * T, s))) return rc;
+        MG_MARK(m); ++m;
+        // stage 4 = ResBlock 3 with LeakyReLU -> conv_post -> tanh fused into its final epilogue: writes the audio
+        if ((rc = launch_resblock_tc(u, audio, packed, 4, B, 256 * T, status, s))) return rc;
+    }
+    MG_MARK(m);
 #undef MG_MARK
     return MG_OK;
 }

@@ -119,7 +119,19 @@ MG_HD constexpr size_t conv_tc_weight_index(int CIN, int NTAP, int co, int ci, i
 }
 MG_HD constexpr size_t tc_pre_offset() { return tc_up_offset(4); }
 MG_HD constexpr size_t tc_pre_bytes() { return (size_t)kMelBins * kPreCout * kPreK * 4; }
-MG_HD constexpr size_t tc_region_bytes() { return tc_pre_offset() + tc_pre_bytes(); }
+// ---- stride-2 ConvT fused into the ResBlock kernel (stages 2, 3; mg_res_tc.cu, UPF): the four taps W_k[co][ci] are four
+// "conv taps" over the 2C input channels, chunked exactly like a ResBlock conv of C output channels:
+//   [tap k][kslice = ci/KC][half: hi, lo][k-panel = (ci%KC)/8][co][ci%8]   (bf16), chunk = tc_chunk_bytes(C)
+MG_HD constexpr int upf_chunks(int C) { return 4 * (2 * C / tc_kc(C)); }
+MG_HD constexpr size_t upf_bytes(int stage) { return (size_t)upf_chunks(stage_cout(stage)) * tc_chunk_bytes(stage_cout(stage)); }
+MG_HD constexpr size_t tc_upf_offset(int stage) {  // stage 2 or 3; bytes from the start of the TC region
+    return tc_pre_offset() + tc_pre_bytes() + (stage == 3 ? upf_bytes(2) : 0);
+}
+MG_HD constexpr size_t upf_weight_index(int C, int ci, int co, int k, int h) {  // bf16 element index in the stage's block
+    const int KC = tc_kc(C);
+    return ((((size_t)(k * (2 * C / KC) + ci / KC) * 2 + h) * (KC / 8) + (ci % KC) / 8) * C + co) * 8 + (ci % 8);
+}
+MG_HD constexpr size_t tc_region_bytes() { return tc_upf_offset(3) + upf_bytes(3); }
 MG_HD constexpr size_t packed_total_bytes() { return ((packed_float_count() * 4 + 255) / 256) * 256 + tc_region_bytes(); }
 MG_HD constexpr size_t tc_region_start() { return ((packed_float_count() * 4 + 255) / 256) * 256; }  // bytes
 // element (bf16) index of w[co][ci][tap] (half h) inside its conv's TC block

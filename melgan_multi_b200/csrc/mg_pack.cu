@@ -96,6 +96,17 @@ __global__ void __launch_bounds__(128) pack_kernel(PackArgs a, RowTable rt, floa
             tcw[up_weight_index(stage, row, co, k, 0)] = hi;
             tcw[up_weight_index(stage, row, co, k, 1)] = lo;
         }
+        if (stage >= 2) {  // ... and for the ConvT fused into the ResBlock kernel (layout: mg_layout.h, upf_weight_index)
+            __nv_bfloat16 *fw = reinterpret_cast<__nv_bfloat16 *>(reinterpret_cast<char *>(packed) + tc_region_start() +
+                                                                 tc_upf_offset(stage));
+            for (int j = threadIdx.x; j < inner; j += blockDim.x) {
+                const int co = j / sh.k, k = j - co * sh.k;
+                __nv_bfloat16 hi, lo;
+                tc::split_bf16(scale * vr[j], hi, lo);
+                fw[upf_weight_index(sh.cout, row, co, k, 0)] = hi;
+                fw[upf_weight_index(sh.cout, row, co, k, 1)] = lo;
+            }
+        }
     }
     if (threadIdx.x == 0 && row < sh.cout) packed[bias_offset(l) + row] = a.bias[l][row];
 }

@@ -29,8 +29,17 @@ using namespace tc;
 // C channels; NBLK 128-position blocks per CTA (a block needs 2C of the 512 TMEM columns); NSTAGE weight-ring slots;
 // NWG epilogue warpgroups; MINB CTAs per SM.  With MINB = 2 (C <= 64: the per-CTA weight stream is small) one CTA's
 // epilogue / tile load / store overlaps the other CTA's MMAs; C >= 128 needs the whole SM's shared memory for one tile.
-template <int C_, int NBLK_, int NSTAGE_, int NWG_, int MINB_, bool POST_ = false>
+// UPF (stride-2 stages): the stage's LeakyReLU -> ConvTranspose1d(2C -> C, k4, s2, p1) runs inside this kernel first, so
+// the CTA reads the PREVIOUS stage's output [B][2C][L/2] and the ConvT output never goes to HBM.  TMEM lane m of a
+// "ConvT block" owns the output pair (t = o + 2m, o + 2m + 1):
+//     out[2s]     = x[s] W1 + x[s-1] W3        out[2s+1] = x[s+1] W0 + x[s] W2        (s = o/2 + m; taps of models.py:50-51)
+// i.e. four MMAs chains of N = C over the 2C input channels, whose A operand is the same (input-position) buffer read at
+// row offsets 1, 0, 2, 1 -- the even outputs accumulate in the D1 columns of output block 2cb, the odd ones in those of
+// block 2cb + 1.  The pairs are then de-interleaved through shared memory (fp32, in the X region that is not in use
+// yet) so that lane = output position can fill R, and from there on the kernel is the plain ResBlock.
+template <int C_, int NBLK_, int NSTAGE_, int NWG_, int MINB_, bool POST_ = false, bool UPF_ = false>
 struct RbCfg {
+    static constexpr bool UPF = UPF_;
     static constexpr int C = C_;
     static constexpr int NBLK = NBLK_, MINB = MINB_;
     static constexpr bool POST = POST_;  // fuse LeakyReLU -> conv_post -> tanh into the final epilogue (last stage)
@@ -66,6 +75,11 @@ struct RbCfg {
     static constexpr int NH = (C == 128) ? 2 : 1;
     static constexpr int SMEM_BYTES = 2 * XBYTES + NSTAGE * CHUNK + 2 * C * 4 + (2 * NSTAGE + 1 + NH) * 8 + 16;
     static_assert(KSL % NH == 0 && (CW / NH) % 32 == 0 && (NH == 1 || ITEMS == NWG), "hand-off split");
+    // fused ConvT: input rows s = o/2 - 1 .. o/2 + P/2 of 2C channels (2 KP k-panels), NCB blocks of 128 output pairs
+    static constexpr int UROWS = P / 2 + 2, UPITCH = UROWS * 16, NCB = NBLK / 2, UKSL = 2 * C / KC, NUPCH = UPF ? 4 * UKSL : 0;
+    static constexpr int SPITCH = P + 4;  // floats between channels of the fp32 staging buffer [C][P]
+    static_assert(!UPF || (NBLK % 2 == 0 && NH == 1 && 2 * KP * UPITCH <= XBYTES && C * SPITCH * 4 <= 2 * XBYTES && C <= 64),
+                  "fused ConvT must fit the X region");
     static_assert(MINB * (SMEM_BYTES + 1024) <= 228 * 1024, "shared memory budget");
     static_assert(MINB * TCOLS <= 512 && (TCOLS == 128 || TCOLS == 256 || TCOLS == 512), "TMEM budget");
     static_assert(XPITCH / 16 < 16384, "LBO field");
@@ -129,7 +143,8 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
         for (int h = 0; h < Cfg::NH; ++h) mbar_init(&xready[h], NEPI);
         fence_mbar_init();
     }
-    for (int i = tid; i < 2 * Cfg::KP * 2 * SLACK; i += Cfg::NT) {  // zero the slack rows of Xh and Xl
+    // (fused ConvT: the X region first holds the ConvT operand and the staging buffer; its slack rows are zeroed later)
+    for (int i = Cfg::UPF ? 1 << 30 : tid; i < 2 * Cfg::KP * 2 * SLACK; i += Cfg::NT) {  // zero the slack rows of Xh and Xl
         const int r = i % (2 * SLACK), kp = (i / (2 * SLACK)) % Cfg::KP, hl = i / (2 * SLACK * Cfg::KP);
         const int row = r < SLACK ? r : P + r;  // r in [SLACK, 2*SLACK) -> rows P+SLACK .. P+2*SLACK-1
         *reinterpret_cast<uint4 *>((hl ? Xl : Xh) + kp * XPITCH + row * 16) = make_uint4(0, 0, 0, 0);
@@ -149,6 +164,15 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
         if (lane == 0) {
             int s = 0, ph = 0;
             bool ok = true;
+            if constexpr (Cfg::UPF) {  // the fused ConvT's 4 taps x 2 K-slices, in blob order
+                const uint8_t *src = tc_base + tc_upf_offset(stage);
+                for (int i = 0; i < Cfg::NUPCH && ok; ++i) {
+                    if (!mbar_wait(&empty[s], ph ^ 1)) { ok = false; break; }
+                    mbar_arrive_expect_tx(&full[s], CHUNK);
+                    bulk_g2s(ring + s * CHUNK, src + (size_t)i * CHUNK, CHUNK, &full[s]);
+                    if (++s == NSTAGE) { s = 0; ph ^= 1; }
+                }
+            }
             for (int conv = 0; conv < 6 && ok; ++conv) {
                 const int layer = l0 + (conv >> 1) + 3 * (conv & 1);
                 const uint8_t *src = tc_base + tc_res_offset(layer);
@@ -176,6 +200,45 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
         const uint32_t xh_addr = smem_u32(Xh), xl_addr = smem_u32(Xl), ring_addr = smem_u32(ring);
         int s = 0, ph = 0;
         bool ok = true;  // a timed-out wait only raises the status word: control flow stays warp-uniform
+        if constexpr (Cfg::UPF) {
+            // ---- fused ConvT: chunk (tap k, K-slice ks); odd taps feed the even outputs (D1 of block 2cb), even taps the odd ones
+            constexpr int UPITCH = Cfg::UPITCH, UKSL = Cfg::UKSL, NCB = Cfg::NCB;
+            const uint64_t udesc_t = desc_template(UPITCH, 128);
+            ok &= mbar_wait(&xready[0], 0);
+            tc_fence_after();
+#pragma unroll 1
+            for (int ch = 0; ch < Cfg::NUPCH; ++ch) {
+                const int k = ch / UKSL, ks = ch - k * UKSL;
+                ok &= mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint64_t bbase = desc_at(bdesc_t, ring_addr + s * CHUNK);
+                const int rowoff = (k == 0) ? 2 : (k == 3) ? 0 : 1;  // A row i <-> input position o/2 - 1 + i
+                const uint32_t arow = rowoff * 16 + ks * (KC / 8) * UPITCH;
+                const uint64_t ah = desc_at(udesc_t, xh_addr + arow), al = desc_at(udesc_t, xl_addr + arow);
+                const bool first = (k < 2 && ks == 0);
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+#pragma unroll
+                    for (int k16 = 0; k16 < KC / 16; ++k16) {
+                        const uint64_t bdesc = bbase + (uint64_t)(((pass == 2 ? Cfg::HALF : 0) + 2 * k16 * (C * 16)) >> 4);
+#pragma unroll
+                        for (int bi = 0; bi < (NCB + NIW - 1) / NIW; ++bi) {
+                            const int cb = iw + bi * NIW;
+                            if (cb < NCB) {
+                                const uint64_t adesc = (pass == 1 ? al : ah) + (uint64_t)((2 * k16 * UPITCH) >> 4) + (uint64_t)(cb * 128);
+                                const uint32_t dc = (uint32_t)((2 * cb + ((k & 1) ? 0 : 1)) * 2 * C + C);
+                                if (elect_one()) mma_bf16(tmem + dc, adesc, bdesc, idesc, !(first && pass == 0 && k16 == 0));
+                            }
+                        }
+                    }
+                }
+                if (elect_one()) mma_commit(&empty[s]);
+                if (++s == NSTAGE) { s = 0; ph ^= 1; }
+            }
+            if (elect_one()) mma_commit(done);
+            __syncwarp();
+        }
+        constexpr int PH0 = Cfg::UPF ? 1 : 0;  // barrier phases consumed by the fused ConvT
 #pragma unroll 1
         for (int conv = 0; conv < 6; ++conv) {
             const int dil = (conv & 1) ? 1 : (conv == 0 ? 1 : conv == 2 ? 3 : 9);
@@ -186,7 +249,7 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
                 constexpr int KH = Cfg::KSL / Cfg::NH;
                 const int h = ch / (3 * KH), tap = (ch / KH) % 3, ks = h * KH + ch % KH;
                 if (ch % (3 * KH) == 0) {  // first chunk of channel half h: wait until the epilogue has written those channels of X
-                    ok &= mbar_wait(&xready[h], conv & 1);
+                    ok &= mbar_wait(&xready[h], (conv + PH0) & 1);
                     tc_fence_after();
                     if (ch == 0 && iw == 0) MG_TR(64 + 3 * conv);
                 }
@@ -226,9 +289,153 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
 
         if (warp == 0) MG_TR(0);
+        constexpr int NH = Cfg::NH, CH = CW / NH;
+        if constexpr (Cfg::UPF) {
+            constexpr int UROWS = Cfg::UROWS, UPITCH = Cfg::UPITCH, SPITCH = Cfg::SPITCH, NCB = Cfg::NCB;
+            const int Lin = L >> 1, s0 = (o >> 1) - 1;  // A row i <-> input position s0 + i (o is even)
+            // ---- ConvT operand: A <- split(lrelu(x_in)), 2C channels of UROWS = P/2 + 2 input positions.  Every thread owns
+            // one of the first P/2 rows (and 1 / HS of its channels); the two extra rows are 16-channel snippets of the first
+            // threads, loaded in the same round trip as their main rows.
+            constexpr int HS = NEPI / (P / 2), CPT = 2 * C / HS;  // threads per row, channels per thread
+            static_assert(HS >= 1 && NEPI % (P / 2) == 0 && CPT % 32 == 0 && 2 * (2 * C / 16) <= NEPI, "ConvT operand split");
+            {
+                const int i = tid % (P / 2), cpart = (tid / (P / 2)) * CPT;
+                const int sp = s0 + i;
+                const bool inr = (sp >= 0 && sp < Lin);
+                const float *xp = x + (size_t)b * 2 * C * Lin + (inr ? sp : 0);
+                const bool extra = tid < 2 * (2 * C / 16);
+                const int ei = P / 2 + tid / (2 * C / 16), ec0 = (tid % (2 * C / 16)) * 16, esp = s0 + ei;
+                const bool einr = extra && esp >= 0 && esp < Lin;
+                const float *exp_ = x + (size_t)b * 2 * C * Lin + (einr ? esp : 0);
+                float fe[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) fe[j] = einr ? lrelu(__ldg(exp_ + (size_t)(ec0 + j) * Lin)) : 0.f;
+#pragma unroll 1
+                for (int c0 = cpart; c0 < cpart + CPT; c0 += 32) {
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = inr ? lrelu(__ldg(xp + (size_t)(c0 + j) * Lin)) : 0.f;  // all in flight together
+                    store_x16(Xh, Xl, UPITCH, c0, i * 16, f);
+                    store_x16(Xh, Xl, UPITCH, c0 + 16, i * 16, f + 16);
+                }
+                if (extra) store_x16(Xh, Xl, UPITCH, ec0, ei * 16, fe);
+            }
+            fence_proxy_async();
+            mbar_arrive(&xready[0]);  // phase 0: the ConvT MMAs may start
+            if (warp == 0) MG_TR(1);
+            // ---- ConvT epilogue: lane m of ConvT block cb holds the output pair (256 cb + 2m, + 1) in the D1 columns of blocks
+            // 2cb / 2cb + 1; + bias -> fp32 staging [c][p] (float2 per channel: consecutive lanes, consecutive 8 bytes)
+            bool ok0 = mbar_wait(done, 0);
+            if (!ok0 && lane == 0) atomicExch(status, 6);
+            tc_fence_after();
+            float *stg = reinterpret_cast<float *>(Xh);
+            const float *ubias = packed + bias_offset(1 + stage);
+            {
+                constexpr int UITEMS = NCB * (NWG / NCB > 0 ? NWG / NCB : 1);  // (ConvT block, column part) items over the warpgroups
+                constexpr int UPARTS = UITEMS / NCB, UCW = C / UPARTS;
+                static_assert(UCW % 32 == 0 && UITEMS % NWG == 0, "ConvT epilogue split");
+#pragma unroll 1
+                for (int it = wg; it < UITEMS; it += NWG) {
+                    const int cb = it / UPARTS, cbeg = (it % UPARTS) * UCW;
+#pragma unroll 1
+                    for (int c0 = cbeg; c0 < cbeg + UCW; c0 += 32) {
+                        uint32_t ve[32], vo[32];
+                        tmem_ld32(lane_addr + (2 * cb) * 2 * C + C + c0, ve);
+                        tmem_ld32(lane_addr + (2 * cb + 1) * 2 * C + C + c0, vo);
+                        tmem_ld_wait();
+                        float *sp = stg + (size_t)c0 * SPITCH + 256 * cb + 2 * row;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float bj = ubias[c0 + j];
+                            *reinterpret_cast<float2 *>(sp + (size_t)j * SPITCH) =
+                                make_float2(__uint_as_float(ve[j]) + bj, __uint_as_float(vo[j]) + bj);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            named_bar_sync(2, NEPI);
+            tc_fence_after();
+            // ---- R <- x (lane = output position); then X <- split(lrelu(x)) exactly like after a c2 (pend = 0)
+            constexpr bool DIRECT = (ITEMS / NWG) * CW <= 64 && CW == 32;  // the thread's x values fit in registers: no TMEM round trip
+            if constexpr (DIRECT) {
+                float xv[ITEMS / NWG][32];
+#pragma unroll
+                for (int ii = 0; ii < ITEMS / NWG; ++ii) {
+                    const int it = wg + ii * NWG, blk = it / PARTS, cbeg = (it % PARTS) * CW;
+                    const float *sp = stg + 128 * blk + row;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) xv[ii][j] = sp[(size_t)(cbeg + j) * SPITCH];
+                }
+                named_bar_sync(2, NEPI);  // every staging read is done: the region becomes X
+                for (int i = tid; i < 2 * Cfg::KP * 2 * SLACK; i += NEPI) {  // zero the slack rows of Xh and Xl
+                    const int r = i % (2 * SLACK), kp = (i / (2 * SLACK)) % Cfg::KP, hl = i / (2 * SLACK * Cfg::KP);
+                    const int xr = r < SLACK ? r : P + r;
+                    *reinterpret_cast<uint4 *>((hl ? Xl : Xh) + kp * XPITCH + xr * 16) = make_uint4(0, 0, 0, 0);
+                }
+#pragma unroll
+                for (int ii = 0; ii < ITEMS / NWG; ++ii) {
+                    const int it = wg + ii * NWG, blk = it / PARTS, cbeg = (it % PARTS) * CW;
+                    const int p = blk * 128 + row, t = o + p;
+                    const bool inr = (t >= 0 && t < L);
+                    uint32_t w[16];
+                    float f[32];
+#pragma unroll
+                    for (int h16 = 0; h16 < 2; ++h16) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) w[j] = __float_as_uint(xv[ii][16 * h16 + j]);
+                        tmem_st16(lane_addr + blk * 2 * C + cbeg + 16 * h16, w);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = inr ? lrelu(xv[ii][j]) : 0.f;
+                    store_x16(Xh, Xl, XPITCH, cbeg, (p + SLACK) * 16, f);
+                    store_x16(Xh, Xl, XPITCH, cbeg + 16, (p + SLACK) * 16, f + 16);
+                }
+                tmem_st_wait();
+            } else {
+#pragma unroll 1
+            for (int it = wg; it < ITEMS; it += NWG) {
+                const int blk = it / PARTS, cbeg = (it % PARTS) * CW;
+                const float *sp = stg + 128 * blk + row;
+#pragma unroll 1
+                for (int c0 = cbeg; c0 < cbeg + CW; c0 += 16) {
+                    uint32_t w[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) w[j] = __float_as_uint(sp[(size_t)(c0 + j) * SPITCH]);
+                    tmem_st16(lane_addr + blk * 2 * C + c0, w);
+                }
+            }
+            tmem_st_wait();
+            named_bar_sync(2, NEPI);  // every staging read is done: the region becomes X
+            for (int i = tid; i < 2 * Cfg::KP * 2 * SLACK; i += NEPI) {  // zero the slack rows of Xh and Xl
+                const int r = i % (2 * SLACK), kp = (i / (2 * SLACK)) % Cfg::KP, hl = i / (2 * SLACK * Cfg::KP);
+                const int xr = r < SLACK ? r : P + r;
+                *reinterpret_cast<uint4 *>((hl ? Xl : Xh) + kp * XPITCH + xr * 16) = make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll 1
+            for (int it = wg; it < ITEMS; it += NWG) {
+                const int blk = it / PARTS, cbeg = (it % PARTS) * CW;
+                const int p = blk * 128 + row, t = o + p;
+                const bool inr = (t >= 0 && t < L);
+#pragma unroll 1
+                for (int c0 = cbeg; c0 < cbeg + CW; c0 += 32) {
+                    uint32_t v[32];
+                    float f[32];
+                    tmem_ld32(lane_addr + blk * 2 * C + c0, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = inr ? lrelu(__uint_as_float(v[j])) : 0.f;
+                    store_x16(Xh, Xl, XPITCH, c0, (p + SLACK) * 16, f);
+                    store_x16(Xh, Xl, XPITCH, c0 + 16, (p + SLACK) * 16, f + 16);
+                }
+            }
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(&xready[0]);  // phase 1: conv 0 may start
+        } else {
         // ---- load the input tile: R <- x (fp32, exact), X <- split(lrelu(x))
         // an item (blk, part) owns, in every channel half h, the CH = CW/NH columns  h*C/NH + part*CH .. + CH
-        constexpr int NH = Cfg::NH, CH = CW / NH;
 #pragma unroll 1
         for (int it = wg; it < ITEMS; it += NWG) {
             const int blk = it / PARTS, part = it % PARTS;
@@ -260,6 +467,7 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
         fence_proxy_async();
         tc_fence_before();
         for (int h = 0; h < NH; ++h) mbar_arrive(&xready[h]);  // conv 0 may start (phase 0 of both halves)
+        }
         if (warp == 0) MG_TR(1);
 
         bool ok = true;
@@ -276,7 +484,7 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
                 for (int c = tid; c < C; c += NEPI) b1s[c] = __ldg(bias + c);
             }
             named_bar_sync(2, NEPI);
-            if (ok && !mbar_wait(done, conv & 1)) { ok = false; if (lane == 0) atomicExch(status, 4); }
+            if (ok && !mbar_wait(done, (conv + (Cfg::UPF ? 1 : 0)) & 1)) { ok = false; if (lane == 0) atomicExch(status, 4); }
             tc_fence_after();
             if (warp == 0) MG_TR(3 + 3 * conv);
             if (conv == 5) break;
@@ -419,6 +627,11 @@ int launch_resblock_tc(const float *x, float *y, const float *packed, int stage,
         case 3: return launch_resblock<RbCfg<32, 4, 4, 2, 2>>(x, y, packed, stage, B, L, status, trace, s);
         // stage 4 = ResBlock 3 with LeakyReLU -> conv_post -> tanh fused: y is the audio [B][1][L]
         case 4: return launch_resblock<RbCfg<32, 4, 4, 2, 2, true>>(x, y, packed, 3, B, L, status, trace, s);
+        // 12 / 13 / 14 = stages 2 / 3 / 3+post with the stage's stride-2 ConvT fused in: x is the PREVIOUS stage's output
+        // [B][2C][L/2] (L stays the output length)
+        case 12: return launch_resblock<RbCfg<64, 2, 2, 2, 2, false, true>>(x, y, packed, 2, B, L, status, trace, s);
+        case 13: return launch_resblock<RbCfg<32, 4, 4, 2, 2, false, true>>(x, y, packed, 3, B, L, status, trace, s);
+        case 14: return launch_resblock<RbCfg<32, 4, 4, 2, 2, true, true>>(x, y, packed, 3, B, L, status, trace, s);
     }
     return set_error(MG_ERR_INVALID_ARGUMENT, "launch_resblock_tc: stage %d", stage);
 }

@@ -52,6 +52,9 @@ def lib():
         L.mg_gen_resblock.restype = ctypes.c_int
         L.mg_gen_resblock.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                       ctypes.c_int, ctypes.c_void_p]
+        L.mg_gen_upres.restype = ctypes.c_int
+        L.mg_gen_upres.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                   ctypes.c_int, ctypes.c_void_p]
         L.mg_gen_stage_output.restype = ctypes.c_int
         L.mg_gen_stage_output.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                           ctypes.c_int, ctypes.c_void_p]
@@ -220,6 +223,20 @@ class GeneratorDevice:
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream().cuda_stream
             check(lib().mg_gen_resblock(self.packed.data_ptr(), stage, x.data_ptr(), y.data_ptr(), B, L, stream))
+        return y
+
+    def upres(self, stage, x):
+        """Stage 2 or 3 as one kernel: LeakyReLU -> ConvTranspose1d(k4, s2) -> ResBlock on x [B, 512>>stage, Lin];
+        returns [B, 256>>stage, 2 Lin]; synchronous."""
+        torch = self.torch
+        x = x.contiguous()
+        B, C, L = x.shape
+        if stage not in (2, 3) or C != (512 >> stage):
+            raise EngineError("upres: stage 2 / 3 expect 128 / 64 input channels")
+        y = torch.empty((B, 256 >> stage, 2 * L), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            check(lib().mg_gen_upres(self.packed.data_ptr(), stage, x.data_ptr(), y.data_ptr(), B, L, stream))
         return y
 
     def stage_output(self, which, B, T):

@@ -8,9 +8,9 @@ registration order (so reference checkpoints and Adam state load), an
 all-reduce wrapper (distributed.py:90-142) hooks them unchanged.
 
 What runs where
-  * ``Generator.forward`` (models.py:61-71 in the reference): nine hand-written sm_100a tcgen05 kernels in
+  * ``Generator.forward`` (models.py:61-71 in the reference): eight hand-written sm_100a tcgen05 kernels in
     libmelgan_b200.so -- conv_pre, then LeakyReLU -> ConvTranspose1d and the fused six-conv ResBlock of each stage,
-    the last one also doing LeakyReLU -> conv_post -> tanh -- plus one launch that folds weight-norm for all 30 layers
+    the last stage as ONE kernel (its stride-2 ConvT, the ResBlock and LeakyReLU -> conv_post -> tanh) -- plus one launch that folds weight-norm for all 30 layers
     whenever the parameters changed.  CUDA only; a CPU tensor raises (the reference's CPU path lives in oracle/ as
     test infrastructure).
   * ``MultiScaleDiscriminator.forward`` (models.py:119-135, Discriminator.forward :87-103) on CUDA: real and generated

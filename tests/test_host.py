@@ -62,6 +62,7 @@ def test_cabi_library_exports_every_declared_symbol():
     tc_blob = 6 * 12 * (256 * 256 + 128 * 128 + 64 * 64 + 32 * 32)  # split-bf16 copy of the 24 ResBlock convs
     tc_blob += 4 * (512 * 256 * 16 + 256 * 128 * 16 + 128 * 64 * 4 + 64 * 32 * 4)  # ... and of the 4 ConvTranspose1d
     tc_blob += 4 * 80 * 512 * 7  # ... and of conv_pre
+    tc_blob += 4 * (128 * 64 * 4 + 64 * 32 * 4)  # ... and of the stride-2 ConvTs again, in the fused stage kernels' layout
     assert engine.lib().mg_gen_packed_bytes() == (fp32_blob + 255) // 256 * 256 + tc_blob
     assert engine.lib().mg_gen_workspace_bytes(64, 32) == 64 * 32 * (18944 + 2 * 8192) * 4 + 256
     assert engine.lib().mg_gen_workspace_bytes(0, 32) == 0
@@ -168,7 +169,7 @@ def test_cabi_argument_errors_are_reported_not_thrown():
     assert L.mg_gen_forward(ctypes.c_void_p(256), ctypes.c_void_p(256), ctypes.c_void_p(256), 1, 4,
                             ctypes.c_void_p(256), 16, None) == -4  # MG_ERR_WORKSPACE_TOO_SMALL
     assert L.mg_gen_kernel_name(0) == b"conv_pre" and L.mg_gen_kernel_name(99) == b""
-    assert L.mg_gen_forward_launches() == 9
+    assert L.mg_gen_forward_launches() == 8 and L.mg_gen_kernel_name(7) == b"up3+res3+post"
 
 
 def _train_case():

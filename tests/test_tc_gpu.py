@@ -82,6 +82,25 @@ def test_convt_tc_matches_oracle(state, dev, stage, B, L):
     assert m < TOL and l2 < TOL, (stage, B, L, m, l2)
 
 
+@pytest.mark.parametrize("stage,B,Lin", [(2, 2, 500), (2, 1, 1), (2, 1, 64), (2, 3, 129), (2, 1, 2048), (3, 2, 1050), (3, 1, 1),
+                                         (3, 1, 128), (3, 1, 255), (3, 2, 256), (3, 1, 4096)])
+def test_fused_convt_resblock_matches_oracle(state, dev, stage, B, Lin):
+    """Stage 2 / 3 as ONE kernel (LeakyReLU -> ConvT k4 s2 -> ResBlock; what the pipeline runs) against the oracle's
+    conv_transpose1d + ResBlock; odd and tiny lengths cover the pair de-interleave at both sequence ends, long ones the
+    tile borders."""
+    cin = 512 >> stage
+    rs = np.random.RandomState(stage * 777 + Lin + B)
+    x = rs.standard_normal((B, cin, Lin)).astype(np.float32)
+    name = "ups.%d" % stage
+    w = cport.fold_weight_norm(state[name + ".weight_g"], state[name + ".weight_v"])
+    lr = np.where(x > 0, x, x * np.float32(0.01)).astype(np.float32)
+    ref = oracle_resblock(state, stage, cport.conv_transpose1d(lr, w, state[name + ".bias"], 2, 1))
+    y = dev.upres(stage, torch.from_numpy(x).cuda()).cpu().numpy()
+    assert y.shape == ref.shape
+    m, l2 = rel_errors(y, ref)
+    assert m < TOL and l2 < TOL, (stage, B, Lin, m, l2)
+
+
 @pytest.mark.parametrize("case", cases.GEN_CASES)
 def test_tc_pipeline_matches_golden(golden, state, tc_path, case):
     B, T, seed, realistic = case
