@@ -32,13 +32,32 @@ def main():
                 a.record(); g(x); b.record()
             torch.cuda.synchronize()
         ms = sorted(a.elapsed_time(b) for a, b in ev)
+        # the same forward captured once in a CUDA graph and replayed (tests/test_generator_gpu.py checks equality)
+        with torch.no_grad():
+            sx = x.clone()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                g(sx)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                g(sx)
+            for _ in range(5):
+                graph.replay()
+            gev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(50)]
+            torch.cuda.synchronize()
+            for a, b in gev:
+                a.record(); graph.replay(); b.record()
+            torch.cuda.synchronize()
+        gms = sorted(a.elapsed_time(b) for a, b in gev)
         for _ in range(5):
             host.forward(mel_h)
         ts = []
         for _ in range(30):
             t0 = time.perf_counter(); host.forward(mel_h); ts.append(time.perf_counter() - t0)
         ts.sort()
-        out[name] = {"device_ms_median": ms[len(ms) // 2], "device_ms_min": ms[0], "e2e_ms_median": 1e3 * ts[len(ts) // 2],
+        out[name] = {"device_ms_median": ms[len(ms) // 2], "device_ms_min": ms[0], "cuda_graph_replay_ms_median": gms[len(gms) // 2], "e2e_ms_median": 1e3 * ts[len(ts) // 2],
                      "audio_seconds": B * T * 256 / 22050.0, "slices": engine.lib().mg_gen_forward_slices(B, T)}
         host.close()
     print(json.dumps(out, indent=1))

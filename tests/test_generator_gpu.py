@@ -206,3 +206,29 @@ def test_batch_slices_are_bit_identical_to_single_chain(gen_module, path):
         y = gen_module(x)
         for i in (0, 19, 20, 39):
             assert torch.equal(y[i:i + 1], gen_module(x[i:i + 1]))
+
+
+@pytest.mark.parametrize("B,T", [(2, 8), (40, 32)])
+def test_forward_is_cuda_graph_capturable(gen_module, path, B, T):
+    """The whole forward (including the forked batch-slice streams, which join the capture through their events) records
+    into a CUDA graph and replays on new inputs: no host synchronisation or allocation on the library's side."""
+    x = torch.from_numpy(synth.mel_input(B, T, 31)).cuda()
+    static_x = x.clone()
+    with torch.no_grad():
+        ref = gen_module(x).clone()  # warm-up: packs the weights, sizes the workspace, configures the kernels
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            gen_module(static_x)
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            static_y = gen_module(static_x)
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(static_y, ref)
+        x2 = torch.from_numpy(synth.mel_input(B, T, 32)).cuda()
+        static_x.copy_(x2)
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(static_y, gen_module(x2))
