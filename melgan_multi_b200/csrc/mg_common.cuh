@@ -41,6 +41,8 @@ int launch_pack(const float *const *v, const float *const *g, const float *const
 int launch_generator_simt(const float *packed, const float *mel, float *audio, int B, int T, float *ws,
                           cudaStream_t s, cudaEvent_t *ev = nullptr);
 int generator_simt_num_launches();
+int launch_up_simt(const float *x, float *y, const float *packed, int stage, int B, int Lin, cudaStream_t s);
+int launch_pre_simt(const float *mel, float *y, const float *packed, int B, int T, cudaStream_t s);
 int generator_tc_num_launches();
 int generator_tc_fused_up();  // bit 0: stage 2, bit 1: stage 3 run their stride-2 ConvT inside the ResBlock kernel
 int generator_tc_slices(int B, int T);  // batch slices (concurrent kernel chains) one forward is cut into
