@@ -159,6 +159,9 @@ void mg_gen_engine_destroy(mg_gen_engine *e);
  *   dz [Bt][Cout][Lout]: upstream gradient already multiplied by LeakyReLU'(layer output);  x [Bt][Cin][Lin]: layer input
  *   dx [Bt][Cin][Lin] (NULL: skip), dw [Cout][4][41] + db [Cout] (dw NULL: skip both) -- dw is the gradient of the FOLDED
  *   weight; mg_msd_wn_backward turns the 21 layers' dw into (d weight_v, d weight_g) in one launch (dw[i] NULL: skip). */
+/* dz = (g1 + g2) * LeakyReLU'(out) over n elements (g2 may be NULL): the gradient entering a layer's pre-activation from the
+ * next layer and from the feature-map loss, in one launch (F.leaky_relu backward of models.py:91,94,97 + the add). */
+int mg_lrelu_backward(const float *g1, const float *g2, const float *out, float *dz, long long n, void *stream);
 size_t mg_msd_grouped_backward_workspace_bytes(int layer, int Bt, int Lout);
 int mg_msd_grouped_backward(const void *packed, int scale, int layer, const float *dz, const float *x, float *dx, float *dw,
                             float *db, void *workspace, size_t workspace_bytes, int Bt, int Lin, int Lout, void *stream);

@@ -165,6 +165,10 @@ int mg_msd_grouped_backward(const void *packed, int scale, int layer, const floa
     return launch_disc_grouped_backward(blob, layer, dz, x, dx, dw, db, (float *)workspace, Bt, Lin, Lout, (cudaStream_t)stream);
 }
 
+int mg_lrelu_backward(const float *g1, const float *g2, const float *out, float *dz, long long n, void *stream) {
+    return launch_lrelu_grad(g1, g2, out, dz, n, (cudaStream_t)stream);
+}
+
 int mg_msd_wn_backward(const float *const *v, const float *const *g, const float *const *dw, float *const *dv,
                        float *const *dg, void *stream) {
     if (!v || !g || !dw || !dv || !dg) return set_error(MG_ERR_INVALID_ARGUMENT, "mg_msd_wn_backward: null argument");

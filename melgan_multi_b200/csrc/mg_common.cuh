@@ -57,6 +57,7 @@ int launch_disc_group4_tc(const float *x, float *out, const uint8_t *wtc, const 
                           cudaStream_t s);
 int launch_disc_pack(const float *const *v, const float *const *g, const float *const *bias, void *packed, cudaStream_t s);
 void msd_lengths(int L, int *lens);
+int launch_lrelu_grad(const float *g1, const float *g2, const float *out, float *dz, long long n, cudaStream_t s);
 size_t grouped_bwd_workspace_bytes(int l, int Bt, int Lout);
 int launch_disc_grouped_backward(const void *blob, int l, const float *dz, const float *x, float *dx, float *dw, float *db,
                                  float *ws, int Bt, int Lin, int Lout, cudaStream_t s);

@@ -185,6 +185,42 @@ __global__ void __launch_bounds__(256) grouped_dw_combine_kernel(const float *__
     }
 }
 
+// dz = (g1 + g2) * LeakyReLU'(out): the gradient that reaches a layer's pre-activation from the next layer (g1) and from
+// the feature-map loss (g2, may be null) -- one launch instead of add + compare + scale + select
+__global__ void __launch_bounds__(256) lrelu_grad_kernel(const float *__restrict__ g1, const float *__restrict__ g2,
+                                                         const float *__restrict__ out, float *__restrict__ dz, long long n) {
+    const long long n4 = n >> 2;
+    const bool vec = ((reinterpret_cast<uintptr_t>(g1) | reinterpret_cast<uintptr_t>(g2) | reinterpret_cast<uintptr_t>(out) |
+                       reinterpret_cast<uintptr_t>(dz)) & 15) == 0;
+    const long long stride = (long long)gridDim.x * 256, i0 = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (vec) {
+        for (long long i = i0; i < n4; i += stride) {
+            float4 a = reinterpret_cast<const float4 *>(g1)[i];
+            if (g2) {
+                const float4 b = reinterpret_cast<const float4 *>(g2)[i];
+                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            }
+            const float4 o = reinterpret_cast<const float4 *>(out)[i];
+            reinterpret_cast<float4 *>(dz)[i] = make_float4(o.x > 0.f ? a.x : a.x * kSlope, o.y > 0.f ? a.y : a.y * kSlope,
+                                                            o.z > 0.f ? a.z : a.z * kSlope, o.w > 0.f ? a.w : a.w * kSlope);
+        }
+    }
+    for (long long i = (vec ? 4 * n4 : 0) + i0; i < n; i += stride) {
+        const float a = g1[i] + (g2 ? g2[i] : 0.f);
+        dz[i] = out[i] > 0.f ? a : a * kSlope;
+    }
+}
+
+int launch_lrelu_grad(const float *g1, const float *g2, const float *out, float *dz, long long n, cudaStream_t s) {
+    if (!g1 || !out || !dz || n < 1) return set_error(MG_ERR_INVALID_ARGUMENT, "mg_lrelu_backward: bad argument");
+    long long blocks = (n / 4 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    lrelu_grad_kernel<<<(unsigned)blocks, 256, 0, s>>>(g1, g2, out, dz, n);
+    MG_CUDA_TRY(cudaGetLastError());
+    return MG_OK;
+}
+
 struct GroupedBwdPlan {
     int tiles_per_item, tiles_per_chunk, chunks;
 };

@@ -76,6 +76,8 @@ def lib():
         L.mg_msd_grouped_backward.restype = ctypes.c_int
         L.mg_msd_grouped_backward.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 6 + [
             ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        L.mg_lrelu_backward.restype = ctypes.c_int
+        L.mg_lrelu_backward.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_longlong, ctypes.c_void_p]
         L.mg_msd_wn_backward.restype = ctypes.c_int
         L.mg_msd_wn_backward.argtypes = [ctypes.c_void_p] * 6
         L.mg_adam_chunk.restype = ctypes.c_int
@@ -382,6 +384,21 @@ class DiscriminatorDevice:
                                                 dx.data_ptr() if need_dx else None, dw.data_ptr(), db.data_ptr(),
                                                 ws.data_ptr(), nbytes, Bt, Lin, Lout, stream))
         return dx, dw, db
+
+    def lrelu_backward(self, g1, g2, out):
+        """(g1 + g2) * LeakyReLU'(out) in one launch; g1 or g2 may be None (not both)."""
+        torch = self.torch
+        if g1 is None:
+            g1, g2 = g2, None
+        g1 = g1.contiguous()
+        g2 = g2.contiguous() if g2 is not None else None
+        out = out.contiguous()
+        dz = torch.empty_like(out)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            check(lib().mg_lrelu_backward(g1.data_ptr(), g2.data_ptr() if g2 is not None else None, out.data_ptr(),
+                                          dz.data_ptr(), out.numel(), stream))
+        return dz
 
     def wn_backward(self, vs, gs, dws):
         """(d weight_v, d weight_g) of the 21 layers from the gradients of their folded weights (None: layer skipped)."""

@@ -219,11 +219,12 @@ class _MSDFunction(torch.autograd.Function):
             for l in range(6, -1, -1):
                 i = 7 * s + l
                 go = grads[i]
-                gt = go if g is None else g if go is None else g + go
-                if gt is None:
+                if g is None and go is None:
                     continue
-                out = fm[i]
-                dz = (torch.where(out > 0, gt, gt * 0.01) if l < 6 else gt).contiguous()
+                if l < 6:  # (g + go) * LeakyReLU'(layer output), one launch
+                    dz = dev.lrelu_backward(g, go, fm[i])
+                else:
+                    dz = (go if g is None else g if go is None else g + go).contiguous()
                 need_dx = l > 0 or need_y
                 _n, _cin, cout, _k, stride, groups, pad = DISCRIMINATOR_LAYERS[l]
                 if groups > 1:
