@@ -170,6 +170,23 @@ def test_cabi_argument_errors_are_reported_not_thrown():
                             ctypes.c_void_p(256), 16, None) == -4  # MG_ERR_WORKSPACE_TOO_SMALL
     assert L.mg_gen_kernel_name(0) == b"conv_pre" and L.mg_gen_kernel_name(99) == b""
     assert L.mg_gen_forward_launches() == 8 and L.mg_gen_kernel_name(7) == b"up3+res3+post"
+    # batch slices: config 2 runs as 4 chains, small or single-item batches as one
+    assert [L.mg_gen_forward_slices(b, t) for b, t in ((64, 32), (40, 32), (16, 32), (1, 1000), (0, 5))] == [4, 2, 1, 1, 1]
+    # the training-side entry points validate before touching the device too
+    p = ctypes.c_void_p(256)
+    assert L.mg_gen_upres(p, 1, p, ctypes.c_void_p(512), 1, 4, None) == -1  # only stages 2 and 3 are stride-2
+    n1 = (ctypes.c_longlong * 1)(16)
+    m1 = (ctypes.c_int * 1)(7)
+    a1 = (ctypes.c_void_p * 1)(256)
+    assert L.mg_loss_workspace_bytes(n1, 1) == 4 and L.mg_loss_workspace_bytes(None, 1) == 0
+    assert L.mg_loss_forward(a1, a1, n1, m1, 1, p, p, 4, None) == -1 and b"bad row" in L.mg_last_error_string()  # mode 7
+    assert L.mg_loss_forward(a1, a1, n1, m1, 0, p, p, 4, None) == -1 and L.mg_loss_backward(a1, a1, n1, m1, 1, None, a1, a1, None) == -1
+    assert L.mg_msd_grouped_backward_workspace_bytes(5, 2, 64) == 0 and L.mg_msd_grouped_backward_workspace_bytes(1, 2, 64) > 0
+    assert L.mg_msd_grouped_backward(p, 0, 1, p, p, p, p, p, p, 1 << 30, 2, 1024, 999, None) == -1
+    assert b"does not follow" in L.mg_last_error_string()  # Lout must be the conv's output length for Lin
+    assert L.mg_msd_grouped_backward(p, 0, 1, p, p, p, p, p, p, 8, 2, 1024, 256, None) == -4  # workspace too small
+    assert L.mg_msd_wn_backward(None, None, None, None, None, None) == -1 and L.mg_lrelu_backward(None, None, None, None, 4, None) == -1
+    assert L.mg_adam_chunk() == 4096 and L.mg_adam_step(None, None, None, None, None, None, 1, 1, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1, None) == -1
 
 
 def _train_case():
