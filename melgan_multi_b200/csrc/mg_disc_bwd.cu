@@ -167,6 +167,135 @@ __global__ void __launch_bounds__(192) grouped_dw_kernel(const float *__restrict
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Layer 4 (stride 1, 4 -> 4 channels per group, 256 groups): with only 4 output channels per group the generic kernels
+// spend one shared-memory load per 2-4 FMAs.  Register-tiled along TIME instead:
+//   dx: a thread owns 8 consecutive positions x 4 ci of one group; per co it keeps the 48 dz values those positions touch
+//       (p + 20 - k, k = 0..40) in registers and streams the 164 weights: 1312 FMAs per 12 float4 + 164 scalar loads.
+//   dw: a thread owns (group, ci, block of 8 taps) x 4 co = 32 accumulators and slides an 8-value window of x over t:
+//       32 FMAs per 5 shared-memory loads.
+constexpr int kG1Groups = 8;  // groups per CTA of both kernels
+
+__global__ void __launch_bounds__(128) grouped_dx1_kernel(const float *__restrict__ dz, float *__restrict__ dx,
+                                                          const float *__restrict__ w, int Lin) {
+    constexpr int NG = kG1Groups, TP = 128, ZW = TP + 40, KP = 44, C = 1024;
+    __shared__ __align__(16) float zs[NG * 4 * ZW];   // [group, co][position - (p0 - 20)]
+    __shared__ float ws[NG * 16 * KP];                 // [group][co][ci][k]
+    const int p0 = blockIdx.x * TP, g0 = blockIdx.y * NG, b = blockIdx.z;
+    for (int i = threadIdx.x; i < NG * 16 * KP; i += 128) {
+        const int g = i / (16 * KP), co = (i / (4 * KP)) & 3, ci = (i / KP) & 3, k = i % KP;
+        ws[i] = k < 41 ? w[(size_t)(g0 + g) * 656 + (ci * 41 + k) * 4 + co] : 0.f;  // packed [group][ci][k][co]
+    }
+    for (int i = threadIdx.x; i < NG * 4 * ZW; i += 128) {
+        const int c = i / ZW, t = p0 - 20 + i % ZW;  // stride 1: Lout == Lin
+        zs[i] = (t >= 0 && t < Lin) ? dz[((size_t)b * C + g0 * 4 + c) * Lin + t] : 0.f;
+    }
+    __syncthreads();
+    const int g = threadIdx.x >> 4, pb = threadIdx.x & 15, p = p0 + 8 * pb;
+    float acc[4][8];
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[ci][j] = 0.f;
+#pragma unroll 1
+    for (int co = 0; co < 4; ++co) {
+        float zw[48];  // dz[co][p + j - 20], j = 0..47: position p + jj with tap k reads index jj + 40 - k
+        const float4 *zr = reinterpret_cast<const float4 *>(zs + (g * 4 + co) * ZW + 8 * pb);
+#pragma unroll
+        for (int q = 0; q < 12; ++q) {
+            const float4 v = zr[q];
+            zw[4 * q] = v.x; zw[4 * q + 1] = v.y; zw[4 * q + 2] = v.z; zw[4 * q + 3] = v.w;
+        }
+#pragma unroll 1
+        for (int ci = 0; ci < 4; ++ci) {
+            const float *wr = ws + ((g * 4 + co) * 4 + ci) * KP;
+#pragma unroll
+            for (int k = 0; k < 41; ++k) {
+                const float wv = wr[k];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[ci][j] = fmaf(wv, zw[j + 40 - k], acc[ci][j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci) {
+        float *o = dx + ((size_t)b * C + (g0 + g) * 4 + ci) * Lin + p;
+        if ((Lin & 3) == 0 && p + 8 <= Lin) {
+            *reinterpret_cast<float4 *>(o) = make_float4(acc[ci][0], acc[ci][1], acc[ci][2], acc[ci][3]);
+            *reinterpret_cast<float4 *>(o + 4) = make_float4(acc[ci][4], acc[ci][5], acc[ci][6], acc[ci][7]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (p + j < Lin) o[j] = acc[ci][j];
+        }
+    }
+}
+
+// partial layout per (chunk, group) as in grouped_dw_kernel<4, 1>: [(ci * 41 + k) * 4 + co] then 4 bias sums
+__global__ void __launch_bounds__(192) grouped_dw1_kernel(const float *__restrict__ dz, const float *__restrict__ x,
+                                                          float *__restrict__ partial, int Bt, int L, int tiles_per_item,
+                                                          int tiles_per_chunk) {
+    constexpr int NG = kG1Groups, TT = 128, XW = TT + 48, C = 1024;
+    __shared__ float zs[NG * 4 * TT];  // [group, co][t]
+    __shared__ float xs[NG * 4 * XW];  // [group, ci][position - (t0 - 20)]
+    const int chunk = blockIdx.x, g0 = blockIdx.y * NG, tid = threadIdx.x;
+    const int g = tid / 24, ci = (tid / 6) & 3, tb = tid % 6;  // taps 8 tb .. 8 tb + 7
+    float acc[4][8];
+#pragma unroll
+    for (int co = 0; co < 4; ++co)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[co][j] = 0.f;
+    float bacc[4] = {0.f, 0.f, 0.f, 0.f};
+    const int total = Bt * tiles_per_item;
+    const int first = chunk * tiles_per_chunk, last = min(total, first + tiles_per_chunk);
+#pragma unroll 1
+    for (int tile = first; tile < last; ++tile) {
+        const int b = tile / tiles_per_item, t0 = (tile - b * tiles_per_item) * TT;
+        __syncthreads();
+        for (int i = tid; i < NG * 4 * TT; i += 192) {
+            const int c = i / TT, t = t0 + i % TT;
+            zs[i] = t < L ? dz[((size_t)b * C + g0 * 4 + c) * L + t] : 0.f;
+        }
+        for (int i = tid; i < NG * 4 * XW; i += 192) {
+            const int c = i / XW, p = t0 - 20 + i % XW;
+            xs[i] = (p >= 0 && p < L) ? x[((size_t)b * C + g0 * 4 + c) * L + p] : 0.f;
+        }
+        __syncthreads();
+        const float *zr = zs + g * 4 * TT, *xr = xs + (g * 4 + ci) * XW + 8 * tb;
+        float xw[8];  // x[ci][t + 8 tb + j - 20], slid along t
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xw[j] = xr[j];
+#pragma unroll 8
+        for (int t = 0; t < TT; ++t) {
+            const float z0 = zr[t], z1 = zr[TT + t], z2 = zr[2 * TT + t], z3 = zr[3 * TT + t];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                acc[0][j] = fmaf(z0, xw[j], acc[0][j]);
+                acc[1][j] = fmaf(z1, xw[j], acc[1][j]);
+                acc[2][j] = fmaf(z2, xw[j], acc[2][j]);
+                acc[3][j] = fmaf(z3, xw[j], acc[3][j]);
+            }
+            if (ci == 0 && tb == 0) { bacc[0] += z0; bacc[1] += z1; bacc[2] += z2; bacc[3] += z3; }
+#pragma unroll
+            for (int j = 0; j < 7; ++j) xw[j] = xw[j + 1];
+            xw[7] = xr[t + 8];
+        }
+    }
+    float *out = partial + ((size_t)chunk * 256 + g0 + g) * (165 * 4);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int k = 8 * tb + j;
+        if (k < 41) {
+#pragma unroll
+            for (int co = 0; co < 4; ++co) out[(ci * 41 + k) * 4 + co] = acc[co][j];
+        }
+    }
+    if (ci == 0 && tb == 0) {
+#pragma unroll
+        for (int co = 0; co < 4; ++co) out[164 * 4 + co] = bacc[co];
+    }
+}
+
 // fixed-order combination of the chunk partials -> dw [Cout][4][41] (the weight_v layout), db [Cout]
 template <int COG>
 __global__ void __launch_bounds__(256) grouped_dw_combine_kernel(const float *__restrict__ partial, float *__restrict__ dw,
@@ -236,10 +365,13 @@ static GroupedBwdPlan grouped_plan(int groups, int Bt, int Lout) {
     return p;
 }
 
+// CTAs along the group axis: the layer-4 kernels take kG1Groups groups each
+static int group_blocks(int groups, int cog, int stride) { return (stride == 1 && cog == 4 && groups == 256) ? groups / kG1Groups : groups; }
+
 size_t grouped_bwd_workspace_bytes(int l, int Bt, int Lout) {
     const DLayer d = d_layer(l);
     const int cog = d.cout / d.groups;
-    return (size_t)grouped_plan(d.groups, Bt, Lout).chunks * d.groups * 165 * cog * sizeof(float);
+    return (size_t)grouped_plan(group_blocks(d.groups, cog, d.stride), Bt, Lout).chunks * d.groups * 165 * cog * sizeof(float);
 }
 
 template <int COG, int S>
@@ -250,6 +382,9 @@ static int grouped_backward(const float *w, const float *dz, const float *x, flo
         if (S == 4 && COG == 16) {
             dim3 grid((Lin + 511) / 512, groups, Bt);
             grouped_dx4_kernel<<<grid, 128, 0, s>>>(dz, dx, w, Cin, Cout, Lin, Lout);
+        } else if (S == 1 && COG == 4 && Cin == 1024) {
+            dim3 grid((Lin + 127) / 128, groups / kG1Groups, Bt);
+            grouped_dx1_kernel<<<grid, 128, 0, s>>>(dz, dx, w, Lin);
         } else {
             dim3 grid((Lin + 255) / 256, groups, Bt);
             grouped_dx_kernel<COG, S><<<grid, 128, 0, s>>>(dz, dx, w, Cin, Cout, Lin, Lout);
@@ -257,9 +392,14 @@ static int grouped_backward(const float *w, const float *dz, const float *x, flo
         MG_CUDA_TRY(cudaGetLastError());
     }
     if (dw) {
-        const GroupedBwdPlan p = grouped_plan(groups, Bt, Lout);
-        dim3 grid(p.chunks, groups);
-        grouped_dw_kernel<COG, S><<<grid, 192, 0, s>>>(dz, x, ws, Bt, Cin, Cout, Lin, Lout, p.tiles_per_item, p.tiles_per_chunk);
+        const GroupedBwdPlan p = grouped_plan(group_blocks(groups, COG, S), Bt, Lout);
+        if (S == 1 && COG == 4 && Cin == 1024) {
+            dim3 grid(p.chunks, groups / kG1Groups);
+            grouped_dw1_kernel<<<grid, 192, 0, s>>>(dz, x, ws, Bt, Lin, p.tiles_per_item, p.tiles_per_chunk);
+        } else {
+            dim3 grid(p.chunks, groups);
+            grouped_dw_kernel<COG, S><<<grid, 192, 0, s>>>(dz, x, ws, Bt, Cin, Cout, Lin, Lout, p.tiles_per_item, p.tiles_per_chunk);
+        }
         MG_CUDA_TRY(cudaGetLastError());
         const int n = groups * 165 * COG;
         grouped_dw_combine_kernel<COG><<<(n + 255) / 256, 256, 0, s>>>(ws, dw, db, groups, p.chunks);
