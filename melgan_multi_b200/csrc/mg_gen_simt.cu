@@ -318,60 +318,6 @@ gen_pre_kernel(const float *__restrict__ mel, float *__restrict__ y, const float
         if (t0 + t < T) yr[t] = acc[t];
 }
 
-// LeakyReLU -> conv_post (32->1, k7) -> tanh (models.py:67-69) as its own kernel (tensor-core pipeline).
-// CTA = kPostTile outputs, 4 consecutive outputs per thread (10 activations + 7 weights feed 28 FMAs).
-constexpr int kPostTile = 1024;
-constexpr int kPostXS = kPostTile + 8;
-__global__ void __launch_bounds__(256)
-gen_post_kernel(const float *__restrict__ x, float *__restrict__ audio, const float *__restrict__ packed, int L) {
-    extern __shared__ __align__(16) float post_smem[];
-    float *xs = post_smem;                    // [32][kPostXS], xs[ci][i] = lrelu(x[t0 - 4 + i])
-    float *ws = post_smem + 32 * kPostXS;     // [32][8] (7 taps + pad)
-    const int b = blockIdx.y, t0 = blockIdx.x * kPostTile;
-    for (int i = threadIdx.x; i < 32 * 8; i += 256) ws[i] = (i & 7) < kPostK ? packed[weight_offset(29) + (i >> 3) * kPostK + (i & 7)] : 0.f;
-    const float *xb = x + (size_t)b * 32 * L;
-    for (int idx = threadIdx.x; idx < 32 * (kPostXS / 4); idx += 256) {
-        const int ci = idx / (kPostXS / 4), i4 = (idx - ci * (kPostXS / 4)) * 4;
-        const int t = t0 - 4 + i4;
-        float4 v;
-        if (t >= 0 && t + 3 < L && (L & 3) == 0) {
-            v = *reinterpret_cast<const float4 *>(xb + (size_t)ci * L + t);
-        } else {
-            v.x = (t >= 0 && t < L) ? xb[(size_t)ci * L + t] : 0.f;
-            v.y = (t + 1 >= 0 && t + 1 < L) ? xb[(size_t)ci * L + t + 1] : 0.f;
-            v.z = (t + 2 >= 0 && t + 2 < L) ? xb[(size_t)ci * L + t + 2] : 0.f;
-            v.w = (t + 3 >= 0 && t + 3 < L) ? xb[(size_t)ci * L + t + 3] : 0.f;
-        }
-        *reinterpret_cast<float4 *>(xs + ci * kPostXS + i4) = make_float4(lrelu(v.x), lrelu(v.y), lrelu(v.z), lrelu(v.w));
-    }
-    __syncthreads();
-    const float bias = packed[bias_offset(29)];
-    const int i0 = threadIdx.x * 4;  // outputs t0 + i0 .. + 3 need xs[i0 + 1 .. i0 + 10]
-    float acc[4] = {bias, bias, bias, bias};
-#pragma unroll 4
-    for (int ci = 0; ci < 32; ++ci) {
-        const float *r = xs + ci * kPostXS + i0;
-        const float4 a = *reinterpret_cast<const float4 *>(r), c = *reinterpret_cast<const float4 *>(r + 4),
-                     d = *reinterpret_cast<const float4 *>(r + 8);
-        const float xv[12] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
-        const float4 w0 = *reinterpret_cast<const float4 *>(ws + ci * 8), w1 = *reinterpret_cast<const float4 *>(ws + ci * 8 + 4);
-        const float wv[7] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z};
-#pragma unroll
-        for (int k = 0; k < kPostK; ++k)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[j] = fmaf(wv[k], xv[1 + j + k], acc[j]);
-    }
-    float *ap = audio + (size_t)b * L + t0 + i0;
-    if (t0 + i0 + 3 < L && (L & 3) == 0) {
-        *reinterpret_cast<float4 *>(ap) = make_float4(tanhf(acc[0]), tanhf(acc[1]), tanhf(acc[2]), tanhf(acc[3]));
-    } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (t0 + i0 + j < L) ap[j] = tanhf(acc[j]);
-    }
-}
-constexpr int kPostSmem = (32 * kPostXS + 32 * 8) * (int)sizeof(float);
-
 //                     CIN  COUT S  PTOT WC WP WBUF  POST
 using Stage0 = StageCfg<512, 256, 8,  96, 16, 1, 4096, false>;
 using Stage1 = StageCfg<256, 128, 8, 192,  8, 2, 4096, false>;

@@ -19,7 +19,7 @@
 // which is the per-layer zero padding of the reference.
 //
 // Warp roles: NEPI/32 epilogue warps (TMEM -> registers -> bias/LeakyReLU/mask/split -> X), one TMA producer
-// warp, one MMA issuer warp (a single elected thread issues tcgen05.mma for the whole CTA).
+// warp, NIW MMA issuer warps (each runs its loop warp-uniform and one elected lane issues tcgen05.mma for its blocks).
 #include "mg_common.cuh"
 #include "mg_tc.cuh"
 
