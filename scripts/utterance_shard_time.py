@@ -32,7 +32,8 @@ def timed(fn, n=30):
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
-    os.dup2(2, 1) if rank else None  # only rank 0 keeps stdout
+    real_out = os.fdopen(os.dup(1), "w")  # the JSON line goes here; fd 1 (NCCL's banner, warnings) is sent to stderr
+    os.dup2(2, 1)
     dist.init_process_group("nccl")
     g = models.Generator()
     g.load_state_dict({k: torch.from_numpy(v) for k, v in synth.generator_state(1234).items()})
@@ -47,7 +48,8 @@ def main():
            "sharded_with_all_gather_ms": timed(lambda: mgd.generate_sharded(g, mel)),
            "max_abs_diff_vs_whole": float((full - whole).abs().max())}
     if rank == 0:
-        sys.__stdout__.write(json.dumps(out) + "\n")
+        real_out.write(json.dumps(out) + "\n")
+        real_out.flush()
     dist.destroy_process_group()
 
 
