@@ -4,32 +4,34 @@
 //            Discriminator.conv_post1 Conv1d(1024 -> 1024, k5, pad 2) + LeakyReLU       models.py:84,96-97
 //
 // GEMM view: D[v, co] = sum_tap sum_pass X_pass[v + tap - PAD, :] * W_pass[tap][co, :]^T with M = 128 virtual positions
-// (TMEM lane), N = 256 output channels, K = 16 per instruction.  Rows are VIRTUAL positions: the batch items are
+// (TMEM lane), N = 256 or 128 output channels, K = 16 per instruction.  Rows are VIRTUAL positions: the batch items are
 // concatenated with PAD zero rows after each item (v = item*(L+PAD) + s), so every tap -- the same A buffer read
 // `tap - PAD` rows further (row-linear operand layout, mg_tc.cuh) -- sees exactly the zero padding of the reference and
 // short sequences (L = 17..128 in the discriminators, 32 in the generator) still fill the 128-row MMA.
-// One CTA = 128 virtual positions x one group of 256 output channels; K = Cin is streamed: A slots (KCA channels, hi/lo
+// One CTA = 128 virtual positions x one group of N output channels; K = Cin is streamed: A slots (KCA channels, hi/lo
 // split of x, optional LeakyReLU on the way in) are produced by the converter warps straight from the fp32 NCL input,
-// B slots (one tap of 16 input channels: [hi, lo][k-panel][256][8] bf16 = 16 KB) arrive by 1-D bulk TMA.
+// B slots (one tap of 16 input channels: [hi, lo][k-panel][N][8] bf16 = 64 N bytes) arrive by 1-D bulk TMA.
 #include "mg_common.cuh"
 #include "mg_tc.cuh"
 
 namespace mg {
 using namespace tc;
 
-template <int CIN_, int COUT_, int NTAP_, int KCA_, bool LRELU_OUT_, int MINB_ = 1>
+template <int CIN_, int COUT_, int NTAP_, int KCA_, bool LRELU_OUT_, int MINB_ = 1, int N_ = 256>
 struct ConvCfg {
     static constexpr int MINB = MINB_;                      // CTAs per SM the shared-memory footprint is sized for
     static constexpr int CIN = CIN_, COUT = COUT_, NTAP = NTAP_, PAD = NTAP_ / 2, KCA = KCA_;
     static constexpr bool LRELU_OUT = LRELU_OUT_;
-    static constexpr int N = 256;                          // output channels per CTA
+    static constexpr int N = N_;                            // output channels per CTA (= TMEM columns: 128 or 256)
     static constexpr int NCG = COUT / N;
     static constexpr int ROWS = 128;
     static constexpr int AROWS = ROWS + 2 * PAD + 2;        // row index i <-> virtual position r0 - PAD + i
     static constexpr int APITCH = AROWS * 16;
     static constexpr int ASLOT = 2 * (KCA / 8) * APITCH;    // [half][k-panel][AROWS][16 B]
     static constexpr int BSLOT = 2 * 2 * N * 16;            // [half][k-panel: 2][N][16 B]
-    static constexpr int NSA = (CIN == KCA) ? 1 : 2, NSB = 4;
+    // B ring: a CTA streams CIN/16 * NTAP slots and each is consumed in 3 MMAs (192-381 cycles), far less than a bulk copy's
+    // latency, so the ring depth (bytes in flight) sets the pace: 8 x 8 KB for the N = 128 tiles, 4 x 16 KB for N = 256
+    static constexpr int NSA = (CIN == KCA) ? 1 : 2, NSB = (N_ == 128) ? 8 : 4;
     static constexpr int NCONV = 128;
     static constexpr int NT = NCONV + 64;
     static constexpr int SMEM_BYTES = NSA * ASLOT + NSB * BSLOT + (2 * NSA + 2 * NSB + 1) * 8 + 16;
@@ -56,7 +58,7 @@ conv_rows_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const ui
     const int r0 = blockIdx.x * ROWS, cg = blockIdx.y;
     const int Lv = L + PAD;  // virtual rows per item: L positions + PAD zero rows
 
-    if (warp == 0) tmem_alloc(tmem_slot, 256);
+    if (warp == 0) tmem_alloc(tmem_slot, N);
     if (tid == 32) {
         for (int s = 0; s < NSA; ++s) { mbar_init(&fullA[s], NCONV); mbar_init(&emptyA[s], 1); }
         for (int s = 0; s < NSB; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
@@ -121,33 +123,62 @@ conv_rows_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const ui
         if (!ok && lane == 0) atomicExch(status, 23);
     } else {
         // ================= converter warps: A slots = split(x), KCA channels of every row =================
+        // Thread tid owns row tid of every slot and keeps the NEXT chunk's KCA loads in flight while it converts the
+        // current one (the chain of dependent memory round trips, not the MMAs, bounds a CTA: 32 chunks at K = 1024);
+        // the 2 PAD rows beyond the first NCONV are picked up by the first threads without prefetch.
         int sa = 0, pha = 0;
         bool ok = true;
+        constexpr int NCH = CIN / KCA;
+        const int v0 = r0 - PAD + tid;
+        const int item0 = v0 >= 0 ? v0 / Lv : 0, s0 = v0 - item0 * Lv;
+        const bool inr0 = (v0 >= 0 && item0 < B && s0 < L);
+        const float *xrow = x + (size_t)(inr0 ? item0 : 0) * CIN * L + (inr0 ? s0 : 0);
+        auto store_row = [&](uint8_t *slot, int i, const float *f) {
+#pragma unroll
+            for (int kp = 0; kp < KCA / 8; ++kp) {
+                uint32_t h[4], l[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) split2_bf16(f[8 * kp + 2 * e], f[8 * kp + 2 * e + 1], h[e], l[e]);
+                *reinterpret_cast<uint4 *>(slot + kp * APITCH + i * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4 *>(slot + (KCA / 8 + kp) * APITCH + i * 16) = make_uint4(l[0], l[1], l[2], l[3]);
+            }
+        };
+        auto tail_rows = [&](uint8_t *slot, int ca) {
 #pragma unroll 1
-        for (int ca = 0; ca < CIN / KCA; ++ca) {
-            if (ok && !mbar_wait(&emptyA[sa], pha ^ 1)) { ok = false; if (lane == 0) atomicExch(status, 24); }
-            uint8_t *slot = aring + sa * ASLOT;
-#pragma unroll 1
-            for (int i = tid; i < ROWS + 2 * PAD; i += NCONV) {
+            for (int i = NCONV + tid; i < ROWS + 2 * PAD; i += NCONV) {
                 const int v = r0 - PAD + i;
                 const int item = v >= 0 ? v / Lv : 0, s = v - item * Lv;
                 const bool inr = (v >= 0 && item < B && s < L);
                 const float *xp = x + ((size_t)(inr ? item : 0) * CIN + ca * KCA) * L + (inr ? s : 0);
                 float f[KCA];
 #pragma unroll
-                for (int j = 0; j < KCA; ++j) f[j] = inr ? __ldg(xp + (size_t)j * L) : 0.f;  // all in flight together
+                for (int j = 0; j < KCA; ++j) f[j] = inr ? __ldg(xp + (size_t)j * L) : 0.f;
+                store_row(slot, i, f);
+            }
+        };
+        float fa[KCA], fb[KCA];  // chunk ca (even / odd) of this thread's row
 #pragma unroll
-                for (int kp = 0; kp < KCA / 8; ++kp) {
-                    uint32_t h[4], l[4];
+        for (int j = 0; j < KCA; ++j) fa[j] = inr0 ? __ldg(xrow + (size_t)j * L) : 0.f;
+#pragma unroll 1
+        for (int ca = 0; ca < NCH; ca += 2) {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) split2_bf16(f[8 * kp + 2 * e], f[8 * kp + 2 * e + 1], h[e], l[e]);
-                    *reinterpret_cast<uint4 *>(slot + kp * APITCH + i * 16) = make_uint4(h[0], h[1], h[2], h[3]);
-                    *reinterpret_cast<uint4 *>(slot + (KCA / 8 + kp) * APITCH + i * 16) = make_uint4(l[0], l[1], l[2], l[3]);
+            for (int half = 0; half < 2; ++half) {
+                const int cc = ca + half;
+                if (cc < NCH) {
+                    float *cur = half ? fb : fa, *nxt = half ? fa : fb;
+                    if (cc + 1 < NCH) {  // next chunk's loads go out before this chunk is converted
+#pragma unroll
+                        for (int j = 0; j < KCA; ++j) nxt[j] = inr0 ? __ldg(xrow + (size_t)((cc + 1) * KCA + j) * L) : 0.f;
+                    }
+                    if (ok && !mbar_wait(&emptyA[sa], pha ^ 1)) { ok = false; if (lane == 0) atomicExch(status, 24); }
+                    uint8_t *slot = aring + sa * ASLOT;
+                    store_row(slot, tid, cur);
+                    tail_rows(slot, cc);
+                    fence_proxy_async();
+                    mbar_arrive(&fullA[sa]);
+                    if (++sa == NSA) { sa = 0; pha ^= 1; }
                 }
             }
-            fence_proxy_async();
-            mbar_arrive(&fullA[sa]);
-            if (++sa == NSA) { sa = 0; pha ^= 1; }
         }
         // ================= epilogue: D[v, co] + bias (-> LeakyReLU) -> y[item][co][s] =================
         if (ok && !mbar_wait(done, 0)) { ok = false; if (lane == 0) atomicExch(status, 25); }
@@ -176,7 +207,7 @@ conv_rows_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const ui
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 256);
+    if (warp == 0) tmem_dealloc(tmem, N);
 }
 
 template <class Cfg>
@@ -195,9 +226,10 @@ static int launch_conv_rows(const float *x, float *y, const uint8_t *wtc, const 
 }
 
 using PreCfg = ConvCfg<80, 512, 7, 80, false>;          // generator conv_pre
-// discriminator conv_post1 (+ LeakyReLU): 32-channel A slots -> 100 KB, two CTAs per SM (each owns half of TMEM), so the
-// three scales' tiles (132 + 68 + 20 CTAs at 8192 samples) are all resident at once and overlap each other's phases
-using Post1Cfg = ConvCfg<1024, 1024, 5, 32, true, 2>;
+// discriminator conv_post1 (+ LeakyReLU): N = 128 per CTA (an N = 128 MMA is as efficient as an N = 256 one: 64 cycles of
+// math = 64 cycles of operand reads), two CTAs per SM (the prefetching converter wants > 96 registers): the tiles of all three scales
+// (264 + 136 + 40 CTAs at 8192 samples) are resident together and hide each other's conversion and ring stalls
+using Post1Cfg = ConvCfg<1024, 1024, 5, 32, true, 2, kPost1NG>;
 
 // mel [B][80][T] -> y [B][512][T]   (Generator.conv_pre)
 int launch_gen_pre_tc(const float *mel, float *y, const float *packed, int B, int T, int *status, cudaStream_t s) {

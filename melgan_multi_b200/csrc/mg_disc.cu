@@ -5,7 +5,8 @@
 //   conv_pre   1 -> 16, k15  (+ LeakyReLU), with the AvgPool1d chain of the scale fused into the input read
 //              (models.py:114-117,125-127: scale 1 sees AvgPool1d(4,2,pad 2)(y), scale 2 AvgPool1d(4,4,pad 2) of that;
 //              count_include_pad=True, so every window divides by 4)                                   fp32 SIMT
-//   grouped    k41, 4 input channels per group, stride 4/4/4/1 (+ LeakyReLU)                           fp32 SIMT
+//   grouped    k41, 4 input channels per group, stride 4/4/4/1 (+ LeakyReLU)                           tcgen05 (mg_disc_tc.cu;
+//              the fp32 SIMT kernels below are the second implementation, MG_DISC_GROUP=simt)
 //   conv_post1 1024 -> 1024, k5 (+ LeakyReLU): 88% of the FLOPs                                        tcgen05 (mg_conv_tc.cu)
 //   conv_post2 1024 -> 1, k3                                                                           fp32 SIMT
 // Every layer writes its feature map (fp32 NCL) because Discriminator.forward returns all seven (models.py:87-103).
@@ -79,8 +80,8 @@ __global__ void __launch_bounds__(128) disc_pack_kernel(DiscPackArgs a, uint8_t 
             const int ci = j / 5, tap = j - 5 * ci;
             __nv_bfloat16 hi, lo;
             tc::split_bf16(scale * vr[j], hi, lo);
-            tcw[conv_tc_weight_index(1024, 5, row, ci, tap, 0)] = hi;
-            tcw[conv_tc_weight_index(1024, 5, row, ci, tap, 1)] = lo;
+            tcw[conv_tc_weight_index(1024, 5, kPost1NG, row, ci, tap, 0)] = hi;
+            tcw[conv_tc_weight_index(1024, 5, kPost1NG, row, ci, tap, 1)] = lo;
         }
     } else {
         for (int j = threadIdx.x; j < inner; j += blockDim.x) fw[j] = scale * vr[j];  // [ci][tap]

@@ -111,11 +111,13 @@ MG_HD constexpr size_t up_weight_index(int stage, int ci, int co, int k, int h) 
            (size_t)(phi * NG + co % NG) * 8 + (ci % 8);
 }
 // ---- tensor-core blob for stride-1 dense convs run by conv_rows_tc_kernel (mg_conv_tc.cu): conv_pre here, the
-// discriminators' conv_post1 in their own blob.  One ring slot = (256-channel output group, 16-channel K chunk, tap):
-//   [cg = co/256][chunk = ci/16][tap][half: hi, lo][k-panel = (ci%16)/8][co%256][ci%8]   (bf16), 16 KB per slot
-MG_HD constexpr size_t conv_tc_weight_index(int CIN, int NTAP, int co, int ci, int tap, int h) {
-    return (((((size_t)(co / 256) * (CIN / 16) + ci / 16) * NTAP + tap) * 2 + h) * 2 + (ci % 16) / 8) * 256 * 8 +
-           (size_t)(co % 256) * 8 + (ci % 8);
+// discriminators' conv_post1 in their own blob.  One ring slot = (NG-channel output group, 16-channel K chunk, tap):
+//   [cg = co/NG][chunk = ci/16][tap][half: hi, lo][k-panel = (ci%16)/8][co%NG][ci%8]   (bf16), 64 NG bytes per slot
+constexpr int kPreNG = 256;    // conv_pre: 512 output channels = 2 groups
+constexpr int kPost1NG = 128;  // conv_post1: 8 groups of 128 -> twice the CTAs of a 256-wide split at the same MMA efficiency
+MG_HD constexpr size_t conv_tc_weight_index(int CIN, int NTAP, int NG, int co, int ci, int tap, int h) {
+    return (((((size_t)(co / NG) * (CIN / 16) + ci / 16) * NTAP + tap) * 2 + h) * 2 + (ci % 16) / 8) * NG * 8 +
+           (size_t)(co % NG) * 8 + (ci % 8);
 }
 MG_HD constexpr size_t tc_pre_offset() { return tc_up_offset(4); }
 MG_HD constexpr size_t tc_pre_bytes() { return (size_t)kMelBins * kPreCout * kPreK * 4; }

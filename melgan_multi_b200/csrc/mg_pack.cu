@@ -62,8 +62,8 @@ __global__ void __launch_bounds__(128) pack_kernel(PackArgs a, RowTable rt, floa
                 const int ci = j / kPreK, tap = j - kPreK * ci;
                 __nv_bfloat16 hi, lo;
                 tc::split_bf16(scale * vr[j], hi, lo);
-                tcw[conv_tc_weight_index(kMelBins, kPreK, row, ci, tap, 0)] = hi;
-                tcw[conv_tc_weight_index(kMelBins, kPreK, row, ci, tap, 1)] = lo;
+                tcw[conv_tc_weight_index(kMelBins, kPreK, kPreNG, row, ci, tap, 0)] = hi;
+                tcw[conv_tc_weight_index(kMelBins, kPreK, kPreNG, row, ci, tap, 1)] = lo;
             }
         }
         if (l >= 5 && l <= 28) {
