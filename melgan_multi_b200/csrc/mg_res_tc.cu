@@ -615,6 +615,9 @@ int launch_resblock_tc(const float *x, float *y, const float *packed, int stage,
                        long long *trace) {
     switch (stage) {
         //                                       C  NBLK NSTAGE NWG MINB
+        // (C = 256 is paced by its 4-slot weight ring -- 3 slots: 204 us, 4: 184 us -- but a fifth 16 KB slot only fits if the
+        //  bias staging goes: reading the biases from global memory in the epilogue instead cost far more (264 us; at 231 KB of
+        //  shared memory there is no L1 left for them))
         case 0: return launch_resblock<RbCfg<256, 1, 4, 4, 1>>(x, y, packed, stage, B, L, status, trace, s);
         // (C = 128 as two single-block CTAs per SM, RbCfg<128, 1, 2, 2, 2>: measured 244 us vs 213 us at config 2 -- the
         //  25 % halo recompute and the two-slot weight rings cost more than the overlap buys)
