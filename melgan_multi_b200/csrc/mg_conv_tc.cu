@@ -17,8 +17,11 @@
 namespace mg {
 using namespace tc;
 
-template <int CIN_, int COUT_, int NTAP_, int KCA_, bool LRELU_OUT_, int MINB_ = 1, int N_ = 256>
+template <int CIN_, int COUT_, int NTAP_, int KCA_, bool LRELU_OUT_, int MINB_ = 1, int N_ = 256, int CL_ = 1>
 struct ConvCfg {
+    // CL consecutive row tiles form a thread-block cluster: they stream the SAME weight slots (same output-channel group), so
+    // the leader's bulk copies are multicast into every CTA's ring and L2 is read once per cluster instead of once per tile
+    static constexpr int CL = CL_;
     static constexpr int MINB = MINB_;                      // CTAs per SM the shared-memory footprint is sized for
     static constexpr int CIN = CIN_, COUT = COUT_, NTAP = NTAP_, PAD = NTAP_ / 2, KCA = KCA_;
     static constexpr bool LRELU_OUT = LRELU_OUT_;
@@ -61,25 +64,33 @@ conv_rows_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const ui
     if (warp == 0) tmem_alloc(tmem_slot, N);
     if (tid == 32) {
         for (int s = 0; s < NSA; ++s) { mbar_init(&fullA[s], NCONV); mbar_init(&emptyA[s], 1); }
-        for (int s = 0; s < NSB; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
+        for (int s = 0; s < NSB; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], Cfg::CL); }  // every CTA of the cluster frees a slot
         mbar_init(done, 1);
         fence_mbar_init();
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (Cfg::CL > 1) cluster_sync();  // every CTA's barriers exist before a peer's copy or commit can land on them
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    constexpr uint16_t kClusterMask = (uint16_t)((1u << Cfg::CL) - 1);
 
     if (warp == NCONV / 32) {
         // ================= TMA producer: B slot = (16-channel chunk, tap) =================
+        // (cluster: every CTA arms its own full barrier; only the leader copies, into all the CTAs' rings at once)
         if (lane == 0) {
             const uint8_t *src = wtc + (size_t)cg * (CIN / 16) * NTAP * BSLOT;
+            const bool leader = Cfg::CL == 1 || cluster_ctarank() == 0;
             int s = 0, ph = 0;
             bool ok = true;
             for (int i = 0; i < (CIN / 16) * NTAP && ok; ++i) {
                 if (!mbar_wait(&emptyB[s], ph ^ 1)) { ok = false; break; }
                 mbar_arrive_expect_tx(&fullB[s], BSLOT);
-                bulk_g2s(bring + s * BSLOT, src + (size_t)i * BSLOT, BSLOT, &fullB[s]);
+                if constexpr (Cfg::CL > 1) {
+                    if (leader) bulk_g2s_multicast(bring + s * BSLOT, src + (size_t)i * BSLOT, BSLOT, &fullB[s], kClusterMask);
+                } else {
+                    bulk_g2s(bring + s * BSLOT, src + (size_t)i * BSLOT, BSLOT, &fullB[s]);
+                }
                 if (++s == NSB) { s = 0; ph ^= 1; }
             }
             if (!ok) atomicExch(status, 22);
@@ -112,7 +123,10 @@ conv_rows_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const ui
                         const bool acc = !(ca == 0 && j == 0 && tap == 0 && pass == 0);
                         if (elect_one()) mma_bf16(tmem, adesc, bdesc, idesc, acc);
                     }
-                    if (elect_one()) mma_commit(&emptyB[sb]);
+                    if (elect_one()) {
+                        if constexpr (Cfg::CL > 1) mma_commit_multicast(&emptyB[sb], kClusterMask);
+                        else mma_commit(&emptyB[sb]);
+                    }
                     if (++sb == NSB) { sb = 0; phb ^= 1; }
                 }
             }
@@ -208,6 +222,7 @@ conv_rows_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const ui
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, N);
+    if constexpr (Cfg::CL > 1) cluster_sync();  // no CTA leaves while a peer may still multicast into its ring or barriers
 }
 
 template <class Cfg>
@@ -219,9 +234,21 @@ static int launch_conv_rows(const float *x, float *y, const uint8_t *wtc, const 
         configured = true;
     }
     const long long vrows = (long long)B * (L + Cfg::PAD);
-    dim3 grid((unsigned)((vrows + Cfg::ROWS - 1) / Cfg::ROWS), Cfg::NCG);
-    conv_rows_tc_kernel<Cfg><<<grid, Cfg::NT, Cfg::SMEM_BYTES, s>>>(x, y, wtc, bias, L, B, status);
-    MG_CUDA_TRY(cudaGetLastError());
+    unsigned tiles = (unsigned)((vrows + Cfg::ROWS - 1) / Cfg::ROWS);
+    tiles = (tiles + Cfg::CL - 1) / Cfg::CL * Cfg::CL;  // whole clusters (a tile past the last row converts zeros and stores nothing)
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(tiles, Cfg::NCG);
+    cfg.blockDim = dim3(Cfg::NT);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = Cfg::CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = Cfg::CL > 1 ? 1 : 0;
+    MG_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_rows_tc_kernel<Cfg>, x, y, wtc, bias, L, B, status));
     return MG_OK;
 }
 
@@ -229,7 +256,11 @@ using PreCfg = ConvCfg<80, 512, 7, 80, false>;          // generator conv_pre
 // discriminator conv_post1 (+ LeakyReLU): N = 128 per CTA (an N = 128 MMA is as efficient as an N = 256 one: 64 cycles of
 // math = 64 cycles of operand reads), two CTAs per SM (the prefetching converter wants > 96 registers): the tiles of all three scales
 // (264 + 136 + 40 CTAs at 8192 samples) are resident together and hide each other's conversion and ring stalls
-using Post1Cfg = ConvCfg<1024, 1024, 5, 32, true, 2, kPost1NG>;
+// (CL = 2 -- the pair's weight slots multicast from one L2 read, frees by multicast commits -- is correct (the parity tests
+//  pass) and measured neutral: 105 vs 102 us on scale 0.  The kernel is bound by SHARED-memory traffic, not L2: an N = 128 MMA
+//  reads 8 KB of operands per 64 cycles = the whole 128 B/cycle, and the ring's bulk-copy writes (42 B/cycle) and the
+//  converter's stores come on top.  The lever is cta_group::2, where each CTA of a pair holds half of B.)
+using Post1Cfg = ConvCfg<1024, 1024, 5, 32, true, 2, kPost1NG, 1>;
 
 // mel [B][80][T] -> y [B][512][T]   (Generator.conv_pre)
 int launch_gen_pre_tc(const float *mel, float *y, const float *packed, int B, int T, int *status, cudaStream_t s) {
