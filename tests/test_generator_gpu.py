@@ -232,3 +232,18 @@ def test_forward_is_cuda_graph_capturable(gen_module, path, B, T):
         g.replay()
         torch.cuda.synchronize()
         assert torch.equal(static_y, gen_module(x2))
+
+
+def test_large_odd_batch_slices(gen_module, path):
+    """B = 301 x T = 7 (2107 frames -> 4 uneven slices of 76 / 75 items): items at the slice borders equal their
+    single-item forwards bit for bit."""
+    if path != "tc":
+        pytest.skip("batch slicing is a feature of the tensor-core pipeline")
+    B, T = 301, 7
+    assert engine.lib().mg_gen_forward_slices(B, T) == 4
+    x = torch.from_numpy(synth.mel_input(B, T, 77)).cuda()
+    with torch.no_grad():
+        y = gen_module(x)
+        gen_module._dev.check_status(B, T)
+        for i in (0, 75, 76, 150, 151, 225, 226, 300):
+            assert torch.equal(y[i:i + 1], gen_module(x[i:i + 1])), i
