@@ -102,6 +102,13 @@ int mg_gen_resblock(const void *packed, int stage, const float *x, float *y, int
  * mg_gen_resblock: a per-kernel parity entry point. */
 int mg_gen_upres(const void *packed, int stage, const float *x, float *y, int B, int Lin, void *stream);
 
+/* conv_pre alone (models.py:46,62): mel [B,80,T] -> y [B,512,T], device fp32.  Synchronous parity-test entry point of
+ * conv_rows_tc_kernel<80,512,k7>. */
+int mg_gen_conv_pre(const void *packed, const float *mel, float *y, int B, int T, void *stream);
+/* The last ResBlock with its fused epilogue (models.py:66-69 for stage 3: ResBlock -> LeakyReLU -> conv_post -> tanh):
+ * x [B,32,L] (the stage-3 ConvT output) -> audio [B,1,L].  Synchronous parity-test entry point of the conv_post + tanh fusion. */
+int mg_gen_resblock_post(const void *packed, const float *x, float *audio, int B, int L, void *stream);
+
 /* Diagnostic twin of mg_gen_resblock: also returns 128 clock64 stamps (host buffer) of one interior CTA's
  * epilogue and MMA roles (slot meaning documented at the definition in csrc/mg_api.cu). */
 int mg_gen_resblock_trace(const void *packed, int stage, const float *x, float *y, int B, int L, long long *trace_host);
@@ -130,6 +137,14 @@ int mg_msd_pack(const float *const *v, const float *const *g, const float *const
 int mg_msd_lengths(int L, int *lens);
 int mg_msd_forward(const void *packed, const float *y, int Bt, int L, float *const *fmaps, void *status_word, void *stream);
 int mg_msd_check_status(const void *status_word, void *stream);
+
+/* One stand-alone Discriminator (models.py:74-103: Discriminator() called on its own, outside MultiScaleDiscriminator):
+ * v, g, bias: HOST arrays of 7 DEVICE pointers (conv_pre, grouped_convs.0-3, conv_post1, conv_post2); packed: device buffer of
+ * mg_disc_packed_bytes() bytes, 256-byte aligned.  x [Bt,1,L] -> fmaps: HOST array of 7 DEVICE pointers, lengths
+ * lens[0..6] of mg_msd_lengths(L, lens) (the scale-0 row); fmaps[6] is the flattened logits.  status_word as above. */
+size_t mg_disc_packed_bytes(void);
+int mg_disc_pack(const float *const *v, const float *const *g, const float *const *bias, void *packed, void *stream);
+int mg_disc_forward(const void *packed, const float *x, int Bt, int L, float *const *fmaps, void *status_word, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * Host-buffer engine.   The call a non-PyTorch host makes: owns its device buffers, takes and

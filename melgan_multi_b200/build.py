@@ -9,6 +9,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libmelgan_b200.so")
+# test-only second implementation (fp32 SIMT generator, csrc/testlib): built next to the product library, loaded only by
+# tests/test_simt_crosscheck_gpu.py -- never by the package
+TEST_LIB = os.path.join(LIBDIR, "libmelgan_b200_simt_test.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -28,19 +31,21 @@ def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
+def test_sources():
+    d = os.path.join(CSRC, "testlib")
+    return sorted(os.path.join(d, f) for f in os.listdir(d) if f.endswith(".cu")) + [os.path.join(CSRC, "mg_error.cu")]
+
+
 def needs_build():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(TEST_LIB):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "melgan_b200.h")]
+    t = min(os.path.getmtime(LIB), os.path.getmtime(TEST_LIB))
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if not os.path.isdir(os.path.join(CSRC, f))]
+    deps += test_sources() + [os.path.join(HERE, "..", "include", "melgan_b200.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False, extra=()):
-    if not force and not needs_build():
-        return LIB
-    os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + list(extra) + ["-o", LIB] + sources()
+def _run(cmd, verbose):
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
@@ -52,6 +57,15 @@ def build(force=False, verbose=False, extra=()):
         sys.stdout.write(out.stdout)
     if out.returncode:
         raise RuntimeError("nvcc failed (%d)" % out.returncode)
+
+
+def build(force=False, verbose=False, extra=()):
+    if not force and not needs_build():
+        return LIB
+    os.makedirs(LIBDIR, exist_ok=True)
+    _run([_nvcc()] + NVCC_FLAGS + list(extra) + ["-o", TEST_LIB] + test_sources(), False)
+    cmd = [_nvcc()] + NVCC_FLAGS + list(extra) + ["-o", LIB] + sources()
+    _run(cmd, verbose)
     return LIB
 
 

@@ -7,24 +7,8 @@
 
 namespace mg {
 
-static thread_local char g_error[512] = "";
-
-char *error_buffer() { return g_error; }
-
-int set_error(int code, const char *fmt, ...) {
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(g_error, sizeof(g_error), fmt, ap);
-    va_end(ap);
-    return code;
-}
-
-// The product pipeline is the tensor-core one.  MG_GEN_PATH=simt selects the first-generation fp32 SIMT kernels, kept as
-// an independent second implementation for cross-checks (tests/test_tc_gpu.py), never as a fallback.
-static bool use_tc() {
-    const char *e = getenv("MG_GEN_PATH");
-    return !(e && strcmp(e, "simt") == 0);
-}
+// (error plumbing: mg_error.cu.  The first-generation fp32 SIMT generator is NOT part of this library: it builds into the
+//  test-only libmelgan_b200_simt_test.so, csrc/testlib.)
 
 static int *status_ptr(void *workspace, int B, int T) {
     return reinterpret_cast<int *>(reinterpret_cast<float *>(workspace) + ws_offset(6, (size_t)B, (size_t)T));
@@ -33,17 +17,9 @@ static int *status_ptr(void *workspace, int B, int T) {
 // mel_host / audio_host: optional pinned host buffers (the engine entry point); the copies ride on the batch slices' streams
 static int run_generator(const float *packed, const float *mel, float *audio, int B, int T, float *ws, cudaStream_t s,
                          cudaEvent_t *ev, const float *mel_host = nullptr, float *audio_host = nullptr) {
-    if (!use_tc()) {
-        const size_t nin = (size_t)B * T * kMelBins * sizeof(float), nout = (size_t)B * T * 256 * sizeof(float);
-        if (mel_host) MG_CUDA_TRY(cudaMemcpyAsync(const_cast<float *>(mel), mel_host, nin, cudaMemcpyHostToDevice, s));
-        int rc = launch_generator_simt(packed, mel, audio, B, T, ws, s, ev);
-        if (rc == MG_OK && audio_host) MG_CUDA_TRY(cudaMemcpyAsync(audio_host, audio, nout, cudaMemcpyDeviceToHost, s));
-        return rc;
-    }
     int *st = status_ptr(ws, B, T);
     MG_CUDA_TRY(cudaMemsetAsync(st, 0, sizeof(int), s));
-    const char *up = getenv("MG_UP_PATH");
-    return launch_generator_tc(packed, mel, audio, B, T, ws, st, !(up && strcmp(up, "simt") == 0), s, ev, mel_host, audio_host);
+    return launch_generator_tc(packed, mel, audio, B, T, ws, st, s, ev, mel_host, audio_host);
 }
 
 static int check_shape(const char *fn, int B, int T) {
@@ -52,13 +28,31 @@ static int check_shape(const char *fn, int B, int T) {
     return MG_OK;
 }
 
+// Parity-test entry points run ONE kernel synchronously with their own status word: launch, wait, report a timed-out pipeline.
+template <class F>
+static int run_one_kernel(const char *fn, cudaStream_t stream, F launch) {
+    int *st = nullptr;
+    MG_CUDA_TRY(cudaMalloc(&st, sizeof(int)));
+    cudaMemsetAsync(st, 0, sizeof(int), stream);
+    int rc = launch(st);
+    int h = 0;
+    if (rc == MG_OK) {
+        cudaError_t e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) rc = set_error(MG_ERR_CUDA, "%s: %s", fn, cudaGetErrorString(e));
+        else if (cudaMemcpy(&h, st, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess || h)
+            rc = set_error(MG_ERR_CUDA, "%s: pipeline wait timed out (role code %d)", fn, h);
+    }
+    cudaFree(st);
+    return rc;
+}
+
 }  // namespace mg
 
 using namespace mg;
 
 extern "C" {
 
-int mg_abi_version(void) { return 1; }
+int mg_abi_version(void) { return 2; }
 
 const char *mg_last_error_string(void) { return error_buffer(); }
 
@@ -123,16 +117,13 @@ int mg_gen_forward_timed(const void *packed, const float *mel, float *audio, int
 }
 
 const char *mg_gen_kernel_name(int i) {
-    static const char *simt[] = {"conv_pre", "stage0(up+res)", "stage1(up+res)", "stage2(up+res)", "stage3(up+res+post)"};
     static const char *tcn[4][9] = {
         {"conv_pre", "up0", "res0", "up1", "res1", "up2", "res2", "up3", "res3+post"},
         {"conv_pre", "up0", "res0", "up1", "res1", "up2+res2", "up3", "res3+post", ""},
         {"conv_pre", "up0", "res0", "up1", "res1", "up2", "res2", "up3+res3+post", ""},
         {"conv_pre", "up0", "res0", "up1", "res1", "up2+res2", "up3+res3+post", "", ""}};
     if (i < 0 || i >= mg_gen_forward_launches()) return "";
-    const char *up = getenv("MG_UP_PATH");
-    const int fuse = (up && strcmp(up, "simt") == 0) ? 0 : generator_tc_fused_up();
-    return use_tc() ? tcn[fuse & 3][i] : simt[i];
+    return tcn[generator_tc_fused_up() & 3][i];
 }
 
 int mg_gen_stage_output(const void *workspace, int which, float *out, int B, int T, void *stream) {
@@ -202,20 +193,15 @@ int mg_loss_backward(const float *const *a, const float *const *b, const long lo
     return launch_loss_backward(a, b, n, mode, count, grad_out, grad_a, grad_b, (cudaStream_t)stream);
 }
 
-int mg_gen_forward_launches(void) {
-    if (!use_tc()) return generator_simt_num_launches();
-    const char *up = getenv("MG_UP_PATH");
-    return (up && strcmp(up, "simt") == 0) ? 9 : generator_tc_num_launches();
-}
+int mg_gen_forward_launches(void) { return generator_tc_num_launches(); }
 
-int mg_gen_forward_slices(int B, int T) { return (use_tc() && B >= 1 && T >= 1) ? generator_tc_slices(B, T) : 1; }
+int mg_gen_forward_slices(int B, int T) { return (B >= 1 && T >= 1) ? generator_tc_slices(B, T) : 1; }
 
 int mg_gen_check_status(const void *workspace, int B, int T, void *stream) {
     int rc = check_shape("mg_gen_check_status", B, T);
     if (rc) return rc;
     if (!workspace) return set_error(MG_ERR_INVALID_ARGUMENT, "mg_gen_check_status: null workspace");
     MG_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
-    if (!use_tc()) return MG_OK;
     int st = 0;
     MG_CUDA_TRY(cudaMemcpy(&st, status_ptr(const_cast<void *>(workspace), B, T), sizeof(int), cudaMemcpyDeviceToHost));
     if (st) return set_error(MG_ERR_CUDA, "tensor-core pipeline wait timed out (role code %d)", st);
@@ -225,19 +211,23 @@ int mg_gen_check_status(const void *workspace, int B, int T, void *stream) {
 int mg_gen_convt(const void *packed, int stage, const float *x, float *y, int B, int Lin, void *stream) {
     if (!packed || !x || !y || x == y || stage < 0 || stage > 3 || B < 1 || Lin < 1)
         return set_error(MG_ERR_INVALID_ARGUMENT, "mg_gen_convt: bad argument");
-    int *st = nullptr;
-    MG_CUDA_TRY(cudaMalloc(&st, sizeof(int)));
-    cudaMemsetAsync(st, 0, sizeof(int), (cudaStream_t)stream);
-    int rc = launch_convt_tc(x, y, (const float *)packed, stage, B, Lin, st, (cudaStream_t)stream);
-    int h = 0;
-    if (rc == MG_OK) {
-        cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
-        if (e != cudaSuccess) rc = set_error(MG_ERR_CUDA, "mg_gen_convt: %s", cudaGetErrorString(e));
-        else if (cudaMemcpy(&h, st, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess || h)
-            rc = set_error(MG_ERR_CUDA, "mg_gen_convt: pipeline wait timed out (role code %d)", h);
-    }
-    cudaFree(st);
-    return rc;
+    return run_one_kernel("mg_gen_convt", (cudaStream_t)stream, [&](int *st) {
+        return launch_convt_tc(x, y, (const float *)packed, stage, B, Lin, st, (cudaStream_t)stream);
+    });
+}
+
+int mg_gen_conv_pre(const void *packed, const float *mel, float *y, int B, int T, void *stream) {
+    if (!packed || !mel || !y || B < 1 || T < 1) return set_error(MG_ERR_INVALID_ARGUMENT, "mg_gen_conv_pre: bad argument");
+    return run_one_kernel("mg_gen_conv_pre", (cudaStream_t)stream, [&](int *st) {
+        return launch_gen_pre_tc(mel, y, (const float *)packed, B, T, st, (cudaStream_t)stream);
+    });
+}
+
+int mg_gen_resblock_post(const void *packed, const float *x, float *audio, int B, int L, void *stream) {
+    if (!packed || !x || !audio || B < 1 || L < 1) return set_error(MG_ERR_INVALID_ARGUMENT, "mg_gen_resblock_post: bad argument");
+    return run_one_kernel("mg_gen_resblock_post", (cudaStream_t)stream, [&](int *st) {
+        return launch_resblock_tc(x, audio, (const float *)packed, 4, B, L, st, (cudaStream_t)stream);
+    });
 }
 
 /* Diagnostic: runs one tensor-core ResBlock and returns clock64 stamps of one interior CTA in trace[0..127]
@@ -264,37 +254,17 @@ int mg_gen_resblock_trace(const void *packed, int stage, const float *x, float *
 int mg_gen_resblock(const void *packed, int stage, const float *x, float *y, int B, int L, void *stream) {
     if (!packed || !x || !y || x == y || stage < 0 || stage > 3 || B < 1 || L < 1)
         return set_error(MG_ERR_INVALID_ARGUMENT, "mg_gen_resblock: bad argument");
-    int *st = nullptr;
-    MG_CUDA_TRY(cudaMalloc(&st, sizeof(int)));
-    cudaMemsetAsync(st, 0, sizeof(int), (cudaStream_t)stream);
-    int rc = launch_resblock_tc(x, y, (const float *)packed, stage, B, L, st, (cudaStream_t)stream);
-    int h = 0;
-    if (rc == MG_OK) {
-        cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
-        if (e != cudaSuccess) rc = set_error(MG_ERR_CUDA, "mg_gen_resblock: %s", cudaGetErrorString(e));
-        else if (cudaMemcpy(&h, st, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess || h)
-            rc = set_error(MG_ERR_CUDA, "mg_gen_resblock: pipeline wait timed out (role code %d)", h);
-    }
-    cudaFree(st);
-    return rc;
+    return run_one_kernel("mg_gen_resblock", (cudaStream_t)stream, [&](int *st) {
+        return launch_resblock_tc(x, y, (const float *)packed, stage, B, L, st, (cudaStream_t)stream);
+    });
 }
 
 int mg_gen_upres(const void *packed, int stage, const float *x, float *y, int B, int Lin, void *stream) {
     if (!packed || !x || !y || x == y || (stage != 2 && stage != 3) || B < 1 || Lin < 1)
         return set_error(MG_ERR_INVALID_ARGUMENT, "mg_gen_upres: bad argument");
-    int *st = nullptr;
-    MG_CUDA_TRY(cudaMalloc(&st, sizeof(int)));
-    cudaMemsetAsync(st, 0, sizeof(int), (cudaStream_t)stream);
-    int rc = launch_resblock_tc(x, y, (const float *)packed, 10 + stage, B, 2 * Lin, st, (cudaStream_t)stream);
-    int h = 0;
-    if (rc == MG_OK) {
-        cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
-        if (e != cudaSuccess) rc = set_error(MG_ERR_CUDA, "mg_gen_upres: %s", cudaGetErrorString(e));
-        else if (cudaMemcpy(&h, st, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess || h)
-            rc = set_error(MG_ERR_CUDA, "mg_gen_upres: pipeline wait timed out (role code %d)", h);
-    }
-    cudaFree(st);
-    return rc;
+    return run_one_kernel("mg_gen_upres", (cudaStream_t)stream, [&](int *st) {
+        return launch_resblock_tc(x, y, (const float *)packed, 10 + stage, B, 2 * Lin, st, (cudaStream_t)stream);
+    });
 }
 
 /* ------------------------------- multi-scale discriminator ------------------------------- */
@@ -325,6 +295,27 @@ int mg_msd_forward(const void *packed, const float *y, int Bt, int L, float *con
         if (!fmaps[i]) return set_error(MG_ERR_INVALID_ARGUMENT, "mg_msd_forward: null feature-map pointer %d", i);
     MG_CUDA_TRY(cudaMemsetAsync(status_word, 0, sizeof(int), (cudaStream_t)stream));
     return launch_msd_forward(packed, y, Bt, L, fmaps, (int *)status_word, (cudaStream_t)stream);
+}
+
+size_t mg_disc_packed_bytes(void) { return d_blob_bytes(); }
+
+int mg_disc_pack(const float *const *v, const float *const *g, const float *const *bias, void *packed, void *stream) {
+    if (!v || !g || !bias || !packed) return set_error(MG_ERR_INVALID_ARGUMENT, "mg_disc_pack: null argument");
+    if ((uintptr_t)packed % 256) return set_error(MG_ERR_INVALID_ARGUMENT, "mg_disc_pack: packed must be 256-byte aligned");
+    return launch_disc_pack(v, g, bias, packed, (cudaStream_t)stream, 1);
+}
+
+int mg_disc_forward(const void *packed, const float *x, int Bt, int L, float *const *fmaps, void *status_word, void *stream) {
+    if (!packed || !x || !fmaps || !status_word || Bt < 1 || L < 1)
+        return set_error(MG_ERR_INVALID_ARGUMENT, "mg_disc_forward: bad argument");
+    int lens[21];
+    msd_lengths(L, lens);
+    for (int i = 0; i < 7; ++i) {
+        if (lens[i] < 1) return set_error(MG_ERR_INVALID_ARGUMENT, "mg_disc_forward: L = %d is too short", L);
+        if (!fmaps[i]) return set_error(MG_ERR_INVALID_ARGUMENT, "mg_disc_forward: null feature-map pointer %d", i);
+    }
+    MG_CUDA_TRY(cudaMemsetAsync(status_word, 0, sizeof(int), (cudaStream_t)stream));
+    return launch_disc_forward(packed, x, Bt, L, fmaps, (int *)status_word, (cudaStream_t)stream);
 }
 
 int mg_msd_check_status(const void *status_word, void *stream) {
@@ -425,8 +416,7 @@ int mg_gen_engine_forward(mg_gen_engine *e, const float *mel_host, float *audio_
     if (rc) return rc;
     MG_CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
     *e->pin_status = 0;
-    if (use_tc())
-        MG_CUDA_TRY(cudaMemcpyAsync(e->pin_status, status_ptr(e->ws, B, T), sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    MG_CUDA_TRY(cudaMemcpyAsync(e->pin_status, status_ptr(e->ws, B, T), sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     MG_CUDA_TRY(cudaStreamSynchronize(e->stream));
     if (!out_pinned) memcpy(audio_host, e->pin_out, nout);
     if (*e->pin_status)

@@ -37,16 +37,14 @@ __device__ __forceinline__ void cp_async_wait() {
 // ---- launches implemented in the .cu files ------------------------------------------------
 int launch_pack(const float *const *v, const float *const *g, const float *const *bias, float *packed,
                 cudaStream_t s);
-// ev: nullptr, or 6 events recorded before each of the 5 launches and after the last one
+// (test-only library, csrc/testlib) ev: nullptr, or 6 events recorded before each of the 5 launches and after the last one
 int launch_generator_simt(const float *packed, const float *mel, float *audio, int B, int T, float *ws,
                           cudaStream_t s, cudaEvent_t *ev = nullptr);
 int generator_simt_num_launches();
-int launch_up_simt(const float *x, float *y, const float *packed, int stage, int B, int Lin, cudaStream_t s);
-int launch_pre_simt(const float *mel, float *y, const float *packed, int B, int T, cudaStream_t s);
 int generator_tc_num_launches();
 int generator_tc_fused_up();  // bit 0: stage 2, bit 1: stage 3 run their stride-2 ConvT inside the ResBlock kernel
 int generator_tc_slices(int B, int T);  // batch slices (concurrent kernel chains) one forward is cut into
-int launch_generator_tc(const float *packed, const float *mel, float *audio, int B, int T, float *ws, int *status, bool up_tc,
+int launch_generator_tc(const float *packed, const float *mel, float *audio, int B, int T, float *ws, int *status,
                         cudaStream_t s, cudaEvent_t *ev = nullptr, const float *mel_host = nullptr, float *audio_host = nullptr);
 int launch_gen_pre_tc(const float *mel, float *y, const float *packed, int B, int T, int *status, cudaStream_t s);
 int launch_disc_post1_tc(const float *x, float *y, const uint8_t *wtc, const float *bias, int Bt, int L, int *status,
@@ -55,7 +53,8 @@ int launch_disc_group_tc(const float *x, float *out, const uint8_t *wtc, const f
                          int Lin, int Lout, int *status, cudaStream_t s);
 int launch_disc_group4_tc(const float *x, float *out, const uint8_t *wtc, const float *bias, int Bt, int L, int *status,
                           cudaStream_t s);
-int launch_disc_pack(const float *const *v, const float *const *g, const float *const *bias, void *packed, cudaStream_t s);
+int launch_disc_pack(const float *const *v, const float *const *g, const float *const *bias, void *packed, cudaStream_t s, int ndisc = 3);
+int launch_disc_forward(const void *packed, const float *x, int Bt, int L, float *const *fmaps, int *status, cudaStream_t s);
 void msd_lengths(int L, int *lens);
 int launch_lrelu_grad(const float *g1, const float *g2, const float *out, float *dz, long long n, cudaStream_t s);
 size_t grouped_bwd_workspace_bytes(int l, int Bt, int Lout);

@@ -89,13 +89,14 @@ __global__ void __launch_bounds__(128) disc_pack_kernel(DiscPackArgs a, uint8_t 
     if (threadIdx.x == 0) reinterpret_cast<float *>(blob)[d_bias_offset(l) + row] = a.bias[d * kDiscLayers + l][row];
 }
 
-int launch_disc_pack(const float *const *v, const float *const *g, const float *const *bias, void *packed, cudaStream_t s) {
-    DiscPackArgs a;
-    for (int i = 0; i < 3 * kDiscLayers; ++i) {
-        if (!v[i] || !g[i] || !bias[i]) return set_error(MG_ERR_INVALID_ARGUMENT, "mg_msd_pack: null tensor %d", i);
+// ndisc = 3: the multi-scale stack (mg_msd_pack); ndisc = 1: one stand-alone Discriminator (mg_disc_pack), blob = d_blob_bytes()
+int launch_disc_pack(const float *const *v, const float *const *g, const float *const *bias, void *packed, cudaStream_t s, int ndisc) {
+    DiscPackArgs a = {};
+    for (int i = 0; i < ndisc * kDiscLayers; ++i) {
+        if (!v[i] || !g[i] || !bias[i]) return set_error(MG_ERR_INVALID_ARGUMENT, "discriminator pack: null tensor %d", i);
         a.v[i] = v[i]; a.g[i] = g[i]; a.bias[i] = bias[i];
     }
-    disc_pack_kernel<<<3 * kDiscRows, 128, 0, s>>>(a, reinterpret_cast<uint8_t *>(packed));
+    disc_pack_kernel<<<ndisc * kDiscRows, 128, 0, s>>>(a, reinterpret_cast<uint8_t *>(packed));
     MG_CUDA_TRY(cudaGetLastError());
     return MG_OK;
 }
@@ -288,6 +289,8 @@ static int launch_group(const float *x, float *out, const float *w, const float 
 
 // Side streams for the three scales (they are independent until the caller consumes the feature maps): forked from and
 // joined back into the caller's stream with events, so the call stays asynchronous and stream-ordered for the caller.
+// One pool per (host thread, device): streams and events belong to the device that was current at their creation.
+constexpr int kMaxDevices = 64;
 struct ScaleStreams {
     cudaStream_t st[2] = {nullptr, nullptr};
     cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
@@ -304,55 +307,84 @@ struct ScaleStreams {
     }
 };
 
+// One Discriminator (models.py:87-103) on the input of scale `sc` of y [Bt][1][L] (sc = 0: y itself; 1, 2: the AvgPool1d chain
+// of models.py:114-117, evaluated inside conv_pre).  blob: that discriminator's packed weights; f[0..6]: its feature maps;
+// ln[0..6]: their lengths.  Everything is enqueued on q.
+static int disc_chain(const uint8_t *blob, const float *y, int sc, int Bt, int L, int L1, int L2, const int *ln, float *const *f,
+                      int *status, bool group_tc, cudaStream_t q) {
+    const float *fw = reinterpret_cast<const float *>(blob);
+    const int Ls = sc == 0 ? L : sc == 1 ? L1 : L2;
+    int rc;
+    dim3 gpre((Ls + 255) / 256, Bt);
+    if (sc == 0) disc_pre_kernel<0><<<gpre, 256, 0, q>>>(y, f[0], fw, L, L1, L2);
+    else if (sc == 1) disc_pre_kernel<1><<<gpre, 256, 0, q>>>(y, f[0], fw, L, L1, L2);
+    else disc_pre_kernel<2><<<gpre, 256, 0, q>>>(y, f[0], fw, L, L1, L2);
+    MG_CUDA_TRY(cudaGetLastError());
+    for (int l = 1; l <= 3; ++l) {  // stride-4 grouped convs: tcgen05 (MG_DISC_GROUP=simt: the fp32 SIMT second implementation)
+        const DLayer d = d_layer(l);
+        if (group_tc)
+            rc = launch_disc_group_tc(f[l - 1], f[l], blob + d_gtc_start() + d_gtc_offset(l), fw + d_bias_offset(l), Bt, d.cin,
+                                      d.cout, ln[l - 1], ln[l], status, q);
+        else
+            rc = launch_group<16, 4>(f[l - 1], f[l], fw + d_weight_offset(l), fw + d_bias_offset(l), Bt, d.cin, d.cout, ln[l - 1],
+                                     ln[l], q);
+        if (rc) return rc;
+    }
+    if (group_tc)
+        rc = launch_disc_group4_tc(f[3], f[4], blob + d_g4tc_start(), fw + d_bias_offset(4), Bt, ln[4], status, q);
+    else
+        rc = launch_group<4, 1>(f[3], f[4], fw + d_weight_offset(4), fw + d_bias_offset(4), Bt, 1024, 1024, ln[3], ln[4], q);
+    if (rc) return rc;
+    if ((rc = launch_disc_post1_tc(f[4], f[5], blob + d_tc_start(), fw + d_bias_offset(5), Bt, ln[4], status, q))) return rc;
+    dim3 gp2((ln[5] + 7) / 8, Bt);
+    disc_post2_kernel<<<gp2, 256, 0, q>>>(f[5], f[6], fw + d_weight_offset(6), fw + d_bias_offset(6), ln[5]);
+    MG_CUDA_TRY(cudaGetLastError());
+    return MG_OK;
+}
+
+static bool disc_group_tc() {
+    const char *gp = getenv("MG_DISC_GROUP");
+    return !(gp && strcmp(gp, "simt") == 0);
+}
+
+// stand-alone Discriminator.forward (models.py:87-103): x [Bt][1][L] -> fmaps[0..6] (lengths: the scale-0 row of msd_lengths)
+int launch_disc_forward(const void *packed, const float *x, int Bt, int L, float *const *fmaps, int *status, cudaStream_t s) {
+    int lens[3 * kDiscLayers];
+    msd_lengths(L, lens);
+    return disc_chain(reinterpret_cast<const uint8_t *>(packed), x, 0, Bt, L, 0, 0, lens, fmaps, status, disc_group_tc(), s);
+}
+
 // y [Bt][1][L] -> fmaps[sc*7 + l] (device pointers, fp32 NCL, lengths from msd_lengths); status: device int
 int launch_msd_forward(const void *packed, const float *y, int Bt, int L, float *const *fmaps, int *status, cudaStream_t s) {
-    static thread_local ScaleStreams ss;  // per host thread, like the rest of the library's state
+    static thread_local ScaleStreams pools[kMaxDevices];  // per host thread, like the rest of the library's state
+    int dev = 0;
+    MG_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices) return set_error(MG_ERR_INVALID_ARGUMENT, "launch_msd_forward: device ordinal %d", dev);
+    ScaleStreams &ss = pools[dev];
     int rc = ss.init();
     if (rc) return rc;
     int lens[3 * kDiscLayers];
     msd_lengths(L, lens);
     const int L1 = (L + 4 - 4) / 2 + 1, L2 = (L1 + 4 - 4) / 4 + 1;
-    const char *gp = getenv("MG_DISC_GROUP");
-    const bool group_tc = !(gp && strcmp(gp, "simt") == 0);
+    const bool group_tc = disc_group_tc();
     MG_CUDA_TRY(cudaEventRecord(ss.fork, s));
-    for (int sc = 0; sc < 3; ++sc) {
+    int forked = 0;
+    for (int sc = 0; sc < 3 && rc == MG_OK; ++sc) {
         cudaStream_t q = sc == 0 ? s : ss.st[sc - 1];  // scale 0 (the largest) stays on the caller's stream
-        if (sc > 0) MG_CUDA_TRY(cudaStreamWaitEvent(q, ss.fork, 0));
-        const uint8_t *blob = reinterpret_cast<const uint8_t *>(packed) + (size_t)sc * d_blob_bytes();
-        const float *fw = reinterpret_cast<const float *>(blob);
-        float *const *f = fmaps + sc * kDiscLayers;
-        const int *ln = lens + sc * kDiscLayers;
-        const int Ls = sc == 0 ? L : sc == 1 ? L1 : L2;
-        dim3 gpre((Ls + 255) / 256, Bt);
-        if (sc == 0) disc_pre_kernel<0><<<gpre, 256, 0, q>>>(y, f[0], fw, L, L1, L2);
-        else if (sc == 1) disc_pre_kernel<1><<<gpre, 256, 0, q>>>(y, f[0], fw, L, L1, L2);
-        else disc_pre_kernel<2><<<gpre, 256, 0, q>>>(y, f[0], fw, L, L1, L2);
-        MG_CUDA_TRY(cudaGetLastError());
-        for (int l = 1; l <= 3; ++l) {  // stride-4 grouped convs: tcgen05 (MG_DISC_GROUP=simt: the fp32 SIMT second implementation)
-            const DLayer d = d_layer(l);
-            if (group_tc)
-                rc = launch_disc_group_tc(f[l - 1], f[l], blob + d_gtc_start() + d_gtc_offset(l), fw + d_bias_offset(l), Bt, d.cin,
-                                          d.cout, ln[l - 1], ln[l], status, q);
-            else
-                rc = launch_group<16, 4>(f[l - 1], f[l], fw + d_weight_offset(l), fw + d_bias_offset(l), Bt, d.cin, d.cout, ln[l - 1],
-                                         ln[l], q);
-            if (rc) return rc;
-        }
-        if (group_tc)
-            rc = launch_disc_group4_tc(f[3], f[4], blob + d_g4tc_start(), fw + d_bias_offset(4), Bt, ln[4], status, q);
-        else
-            rc = launch_group<4, 1>(f[3], f[4], fw + d_weight_offset(4), fw + d_bias_offset(4), Bt, 1024, 1024, ln[3], ln[4], q);
-        if (rc) return rc;
-        if ((rc = launch_disc_post1_tc(f[4], f[5], blob + d_tc_start(), fw + d_bias_offset(5), Bt, ln[4], status, q))) return rc;
-        dim3 gp2((ln[5] + 7) / 8, Bt);
-        disc_post2_kernel<<<gp2, 256, 0, q>>>(f[5], f[6], fw + d_weight_offset(6), fw + d_bias_offset(6), ln[5]);
-        MG_CUDA_TRY(cudaGetLastError());
         if (sc > 0) {
-            MG_CUDA_TRY(cudaEventRecord(ss.join[sc - 1], q));
-            MG_CUDA_TRY(cudaStreamWaitEvent(s, ss.join[sc - 1], 0));
+            cudaError_t e = cudaStreamWaitEvent(q, ss.fork, 0);
+            if (e != cudaSuccess) { rc = set_error(MG_ERR_CUDA, "launch_msd_forward: fork: %s", cudaGetErrorString(e)); break; }
+            forked = sc;
         }
+        rc = disc_chain(reinterpret_cast<const uint8_t *>(packed) + (size_t)sc * d_blob_bytes(), y, sc, Bt, L, L1, L2,
+                        lens + sc * kDiscLayers, fmaps + sc * kDiscLayers, status, group_tc, q);
     }
-    return MG_OK;
+    for (int sc = 1; sc <= forked; ++sc) {  // join every forked stream, also after an error
+        cudaError_t e = cudaEventRecord(ss.join[sc - 1], ss.st[sc - 1]);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(s, ss.join[sc - 1], 0);
+        if (e != cudaSuccess && rc == MG_OK) rc = set_error(MG_ERR_CUDA, "launch_msd_forward: join: %s", cudaGetErrorString(e));
+    }
+    return rc;
 }
 
 }  // namespace mg

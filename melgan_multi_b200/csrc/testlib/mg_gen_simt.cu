@@ -18,7 +18,7 @@
 // Thread map (all phases): warp (wc, wp) owns output channels [wc*COB, (wc+1)*COB) and positions
 // wp*32*PB + lane + 32*j; lanes run along positions so activation reads are conflict-free and weight
 // reads are warp-uniform broadcasts (float4 of 4 output channels).
-#include "mg_common.cuh"
+#include "../mg_common.cuh"
 
 namespace mg {
 

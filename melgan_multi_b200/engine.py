@@ -55,6 +55,16 @@ def lib():
         L.mg_gen_upres.restype = ctypes.c_int
         L.mg_gen_upres.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                    ctypes.c_int, ctypes.c_void_p]
+        L.mg_gen_conv_pre.restype = ctypes.c_int
+        L.mg_gen_conv_pre.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        L.mg_gen_resblock_post.restype = ctypes.c_int
+        L.mg_gen_resblock_post.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        L.mg_disc_packed_bytes.restype = ctypes.c_size_t
+        L.mg_disc_pack.restype = ctypes.c_int
+        L.mg_disc_pack.argtypes = [ctypes.c_void_p] * 5
+        L.mg_disc_forward.restype = ctypes.c_int
+        L.mg_disc_forward.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                      ctypes.c_void_p, ctypes.c_void_p]
         L.mg_gen_stage_output.restype = ctypes.c_int
         L.mg_gen_stage_output.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                           ctypes.c_int, ctypes.c_void_p]
@@ -118,6 +128,55 @@ def _ptr_array(ptrs):
     return (ctypes.c_void_p * len(ptrs))(*ptrs)
 
 
+class _StatusWatch:
+    """The tcgen05 kernels bound every mbarrier wait and, on a timeout, raise a device status word and carry on (a hung
+    GPU box is worse than a failed call).  A forward must therefore never be trusted silently: after each one the status
+    word is copied to pinned host memory on the same stream (4 bytes, asynchronous), and the copy is inspected at the
+    next forward of the same module, or at the next host synchronisation point the training loop has anyway
+    (``discriminator_loss``' read-back, ``poll_status``).  A non-zero word raises EngineError.  Skipped while the stream
+    is being captured into a CUDA graph (no host-visible copy can be made there; replays are checked by check_status)."""
+    _live = None  # weak set of watches with a copy in flight
+
+    def __init__(self, torch, device, what):
+        import weakref
+        self.torch, self.what = torch, what
+        self.pin = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.event = torch.cuda.Event()
+        self.pending = False
+        if _StatusWatch._live is None:
+            _StatusWatch._live = weakref.WeakSet()
+
+    def arm(self, status_word):
+        """status_word: int32 CUDA tensor view [1] holding the pipeline's status after the work just enqueued."""
+        if self.torch.cuda.is_current_stream_capturing():
+            return
+        self.pin.copy_(status_word, non_blocking=True)
+        self.event.record()
+        self.pending = True
+        _StatusWatch._live.add(self)
+
+    def check(self, wait=False):
+        if not self.pending:
+            return
+        if wait:
+            self.event.synchronize()
+        elif not self.event.query():
+            return
+        self.pending = False
+        _StatusWatch._live.discard(self)
+        code = int(self.pin[0])
+        if code:
+            self.pin[0] = 0
+            raise EngineError("%s: tensor-core pipeline wait timed out (role code %d); the outputs of that call are "
+                              "invalid" % (self.what, code))
+
+
+def poll_status(wait=False):
+    """Checks every status copy in flight (all modules, this process); ``wait=True`` blocks on the copies' events."""
+    for w in list(_StatusWatch._live or ()):
+        w.check(wait)
+
+
 # ------------------------------------------------------------------------------------------
 # Device-pointer path (what models.Generator.forward uses with torch tensors)
 # ------------------------------------------------------------------------------------------
@@ -135,6 +194,7 @@ class GeneratorDevice:
         self.packed = torch.empty((lib().mg_gen_packed_bytes() + 3) // 4, dtype=torch.float32, device=self.device)
         self._ws = None
         self._ws_key = None
+        self._watch = _StatusWatch(torch, self.device, "Generator.forward")
 
     def pack(self, vs, gs, bs):
         """vs/gs/bs: 30 contiguous fp32 CUDA tensors each (weight_v, weight_g, bias; reference order)."""
@@ -173,11 +233,14 @@ class GeneratorDevice:
         B, _, T = mel.shape
         if out is None:
             out = torch.empty((B, 1, 256 * T), dtype=torch.float32, device=self.device)
+        self._watch.check()  # the previous forward's status word, if its copy has landed
         ws = self.workspace(B, T)
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream().cuda_stream
             check(lib().mg_gen_forward(self.packed.data_ptr(), mel.data_ptr(), out.data_ptr(), B, T,
                                        ws.data_ptr(), ws.numel() * 4, stream))
+            off = (lib().mg_gen_workspace_bytes(B, T) - 256) // 4  # the status word sits after the activation buffers
+            self._watch.arm(ws.view(torch.int32)[off:off + 1])
         return out
 
     def forward_timed(self, mel, out):
@@ -239,6 +302,30 @@ class GeneratorDevice:
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream().cuda_stream
             check(lib().mg_gen_upres(self.packed.data_ptr(), stage, x.data_ptr(), y.data_ptr(), B, L, stream))
+        return y
+
+    def conv_pre(self, mel):
+        """conv_pre alone (models.py:46,62): mel [B, 80, T] -> [B, 512, T]; synchronous parity entry point."""
+        torch = self.torch
+        mel = mel.contiguous()
+        B, _, T = mel.shape
+        y = torch.empty((B, 512, T), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            check(lib().mg_gen_conv_pre(self.packed.data_ptr(), mel.data_ptr(), y.data_ptr(), B, T, stream))
+        return y
+
+    def resblock_post(self, x):
+        """Last ResBlock + LeakyReLU -> conv_post -> tanh (models.py:66-69) on x [B, 32, L] -> audio [B, 1, L]; synchronous."""
+        torch = self.torch
+        x = x.contiguous()
+        B, C, L = x.shape
+        if C != 32:
+            raise EngineError("resblock_post expects 32 channels")
+        y = torch.empty((B, 1, L), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            check(lib().mg_gen_resblock_post(self.packed.data_ptr(), x.data_ptr(), y.data_ptr(), B, L, stream))
         return y
 
     def stage_output(self, which, B, T):
@@ -313,25 +400,30 @@ def loss_backward(a, b, modes, grad_out, need_b):
 
 
 class DiscriminatorDevice:
-    """Packed multi-scale-discriminator weights on one CUDA device, driven with torch tensors."""
+    """Packed discriminator weights on one CUDA device, driven with torch tensors: the three-scale stack of
+    MultiScaleDiscriminator (ndisc = 3) or one stand-alone Discriminator (ndisc = 1)."""
 
-    def __init__(self, device):
+    def __init__(self, device, ndisc=3):
         import torch
         self.torch = torch
         self.device = torch.device(device)
+        self.ndisc = ndisc
         if self.device.type != "cuda":
             raise EngineError("the B200 engine runs on CUDA devices only (got %s)" % (device,))
+        if ndisc not in (1, 3):
+            raise EngineError("DiscriminatorDevice: ndisc must be 1 or 3")
         with torch.cuda.device(self.device):
             check(lib().mg_device_check())
-        nbytes = lib().mg_msd_packed_bytes()
+        nbytes = lib().mg_msd_packed_bytes() if ndisc == 3 else lib().mg_disc_packed_bytes()
         self.packed = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=self.device)
         self.status = torch.zeros(64, dtype=torch.int32, device=self.device)
+        self._watch = _StatusWatch(torch, self.device, "Discriminator forward")
 
     def pack(self, vs, gs, bs):
-        """vs/gs/bs: 21 fp32 CUDA tensors each (discriminator-major, layers in registration order)."""
+        """vs/gs/bs: 7 * ndisc fp32 CUDA tensors each (discriminator-major, layers in registration order)."""
         torch = self.torch
-        if not (len(vs) == len(gs) == len(bs) == 21):
-            raise EngineError("expected 21 discriminator layers")
+        if not (len(vs) == len(gs) == len(bs) == 7 * self.ndisc):
+            raise EngineError("expected %d discriminator layers" % (7 * self.ndisc))
         keep = []
 
         def ptrs(ts):
@@ -346,10 +438,11 @@ class DiscriminatorDevice:
             return _ptr_array(out)
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream().cuda_stream
-            check(lib().mg_msd_pack(ptrs(vs), ptrs(gs), ptrs(bs), self.packed.data_ptr(), stream))
+            fn = lib().mg_msd_pack if self.ndisc == 3 else lib().mg_disc_pack
+            check(fn(ptrs(vs), ptrs(gs), ptrs(bs), self.packed.data_ptr(), stream))
 
     def forward(self, y):
-        """y [Bt, 1, L] -> list of 3 lists of 7 feature maps [Bt, C, len] (fresh tensors)."""
+        """y [Bt, 1, L] -> list of ndisc lists of 7 feature maps [Bt, C, len] (fresh tensors)."""
         torch = self.torch
         if y.dim() != 3 or y.shape[1] != 1:
             raise EngineError("audio must be [B, 1, L], got %s" % (tuple(y.shape),))
@@ -358,12 +451,15 @@ class DiscriminatorDevice:
         y = y.contiguous()
         Bt, _, L = y.shape
         lens = msd_lengths(L)
+        self._watch.check()
         fmaps = [[torch.empty((Bt, D_CHANNELS[l], lens[s][l]), dtype=torch.float32, device=self.device)
-                  for l in range(7)] for s in range(3)]
+                  for l in range(7)] for s in range(self.ndisc)]
         ptrs = _ptr_array([f.data_ptr() for sc in fmaps for f in sc])
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream().cuda_stream
-            check(lib().mg_msd_forward(self.packed.data_ptr(), y.data_ptr(), Bt, L, ptrs, self.status.data_ptr(), stream))
+            fn = lib().mg_msd_forward if self.ndisc == 3 else lib().mg_disc_forward
+            check(fn(self.packed.data_ptr(), y.data_ptr(), Bt, L, ptrs, self.status.data_ptr(), stream))
+            self._watch.arm(self.status[:1])
         return fmaps
 
     def grouped_backward(self, scale, layer, dz, x, need_dx=True):
@@ -401,7 +497,7 @@ class DiscriminatorDevice:
         return dz
 
     def wn_backward(self, vs, gs, dws):
-        """(d weight_v, d weight_g) of the 21 layers from the gradients of their folded weights (None: layer skipped)."""
+        """(d weight_v, d weight_g) of the 7 * ndisc layers from the gradients of their folded weights (None: layer skipped)."""
         torch = self.torch
         vs = [t.detach().contiguous() for t in vs]
         gs = [t.detach().contiguous() for t in gs]
@@ -409,11 +505,14 @@ class DiscriminatorDevice:
         dvs = [torch.empty_like(v) if d is not None else None for v, d in zip(vs, dws)]
         dgs = [torch.empty_like(g) if d is not None else None for g, d in zip(gs, dws)]
 
-        def arr(ts):
-            return _ptr_array([t.data_ptr() if t is not None else None for t in ts])
+        pad = 21 - len(vs)  # the launch walks a 21-row table; a stand-alone Discriminator fills the rest with skipped rows
+
+        def arr(ts, fill):
+            return _ptr_array([t.data_ptr() if t is not None else None for t in ts] + [fill] * pad)
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream().cuda_stream
-            check(lib().mg_msd_wn_backward(arr(vs), arr(gs), arr(dws), arr(dvs), arr(dgs), stream))
+            check(lib().mg_msd_wn_backward(arr(vs, vs[0].data_ptr()), arr(gs, gs[0].data_ptr()), arr(dws, None), arr(dvs, None),
+                                           arr(dgs, None), stream))
         return dvs, dgs
 
     def check_status(self):

@@ -162,9 +162,10 @@ class Generator(nn.Module):
 
 
 class Discriminator(nn.Module):
-    """Parameter container with the reference's layout (models.py:74-85).  The three-scale stack runs as one fused
-    pipeline in ``MultiScaleDiscriminator`` (the only caller in the reference, models.py:109-113), so a lone
-    ``Discriminator`` has no forward of its own here and calling it raises: there is no silent stock-op path."""
+    """One discriminator (reference models.py:74-103).  Inside ``MultiScaleDiscriminator`` (its only caller in the
+    reference, models.py:109-113) the three of them run as one fused pipeline on the stacked real + generated batch;
+    called on its own, ``forward(x)`` runs the same sm_100a kernels on this module's weights and returns
+    ``(flattened logits, [7 feature maps])`` like the reference's.  CUDA only, no stock-op fallback."""
 
     def __init__(self):
         super().__init__()
@@ -180,10 +181,39 @@ class Discriminator(nn.Module):
     def layers(self):
         return [self.conv_pre] + list(self.grouped_convs) + [self.conv_post1, self.conv_post2]
 
+    n_scales = 1     # what _MSDFunction walks: this module is "a one-scale stack without pooling"
+    meanpools = ()
+
+    def _param_triplets(self):
+        mods = self.layers()
+        return [m.weight_v for m in mods], [m.weight_g for m in mods], [m.bias for m in mods]
+
+    def _engine_forward(self, x):
+        vs, gs, bs = self._param_triplets()
+        dev = vs[0].device
+        if getattr(self, "_dev", None) is None or self._dev.device != dev:
+            self._dev = _engine.DiscriminatorDevice(dev, ndisc=1)
+            self._packed_key = None
+        key = tuple((t.data_ptr(), t._version) for t in vs + gs + bs)
+        if key != self._packed_key:
+            self._dev.pack(vs, gs, bs)
+            self._packed_key = key
+        return self._dev.forward(x)
+
     def forward(self, x):
-        raise _engine.EngineError(
-            "melgan_multi_b200.Discriminator is a parameter container: run MultiScaleDiscriminator (CUDA), which drives the "
-            "three discriminators through the fused sm_100a kernels; there is deliberately no stock-PyTorch fallback")
+        if not x.is_cuda:
+            raise _engine.EngineError("melgan_multi_b200.Discriminator.forward needs a CUDA tensor (no CPU fallback)")
+        x = x.float()
+        vs, gs, bs = self._param_triplets()
+        needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in vs + gs + bs))
+        if needs_grad:
+            flat = []
+            for v, g, b in zip(vs, gs, bs):
+                flat += [v, g, b]
+            fmap = list(_MSDFunction.apply(self, x, *flat))
+        else:
+            fmap = self._engine_forward(x)[0]
+        return torch.flatten(fmap[6], 1, -1), fmap
 
 
 class _MSDFunction(torch.autograd.Function):
@@ -205,12 +235,13 @@ class _MSDFunction(torch.autograd.Function):
     def backward(ctx, *grads):
         msd, dev = ctx.msd, ctx.msd._dev
         saved = ctx.saved_tensors
-        n = 3 * len(DISCRIMINATOR_LAYERS)
+        nsc = msd.n_scales  # 3 for MultiScaleDiscriminator, 1 for a stand-alone Discriminator
+        n = nsc * len(DISCRIMINATOR_LAYERS)
         y2, params, fm = saved[0], saved[1:1 + 3 * n], saved[1 + 3 * n:]
         need_y = ctx.needs_input_grad[1]
         dws, dbs, g_in = [None] * n, [None] * n, []
         x0, pooled = y2, [y2]
-        for s in range(3):
+        for s in range(nsc):
             if s > 0:
                 x0 = msd.meanpools[s - 1](x0)
                 pooled.append(x0)
@@ -236,7 +267,7 @@ class _MSDFunction(torch.autograd.Function):
             g_in.append(g)
         gy = None
         if need_y:  # AvgPool chain (models.py:114-117,125-127): linear, so its backward is differentiated on zeros
-            for s in (2, 1):
+            for s in range(nsc - 1, 0, -1):
                 if g_in[s] is None:
                     continue
                 with torch.enable_grad():
@@ -255,6 +286,8 @@ class MultiScaleDiscriminator(nn.Module):
     """Reference models.py:106-135: three Discriminators on y, pool(y), pool(pool(y)); returns
     (y_d_rs, y_d_gs, fmap_rs, fmap_gs).  On CUDA the whole stack runs in the hand-written kernels of
     libmelgan_b200.so with y and y_hat stacked into one batch (the reference calls each discriminator twice)."""
+
+    n_scales = 3
 
     def __init__(self):
         super().__init__()
@@ -368,6 +401,9 @@ def discriminator_loss(disc_real_outputs, disc_generated_outputs):
     rows = list(disc_real_outputs) + list(disc_generated_outputs)
     means = _row_means(rows, [None] * (2 * k), [_engine.LOSS_ONE_MINUS_SQ] * k + [_engine.LOSS_SQ] * k)
     vals = means.detach().tolist()
+    # the read-back above synchronised the stream: every forward enqueued before it has finished, so its pipeline status
+    # word (engine._StatusWatch) can be inspected here at no cost -- a stalled tcgen05 pipeline raises instead of training on
+    _engine.poll_status()
     return means.sum(), vals[:k], vals[k:]
 
 

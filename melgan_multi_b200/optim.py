@@ -14,6 +14,20 @@ import torch
 from . import engine as _engine
 
 
+def _bump_versions(params):
+    inc = getattr(torch._C, "_increment_version", None)
+    if inc is not None:
+        try:
+            inc(params)  # torch >= 2.4: takes an iterable of tensors
+            return
+        except TypeError:
+            for p in params:
+                inc(p)
+            return
+    for p in params:  # very old torch: a no-op in-place op (one tiny launch per tensor)
+        p.add_(0)
+
+
 class Adam(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, amsgrad=False):
         if amsgrad:
@@ -28,9 +42,13 @@ class Adam(torch.optim.Optimizer):
         """Device-side tables of one group.  Parameter / moment pointers, sizes and the CTA map are built once (until the
         set of tensors with a gradient changes); only the gradient pointers, which autograd reallocates every step, are
         refreshed: one small pinned-to-device copy."""
-        ids = tuple(id(p) for p in ps)
+        # identity AND storage of every tensor the kernel writes through: after model.to(...), p.data = ..., or a moment
+        # replaced outside load_state_dict, a cached raw pointer would be a silent write into freed memory
+        ids = tuple((id(p), p.data_ptr(), self.state[p]["exp_avg"].data_ptr(), self.state[p]["exp_avg_sq"].data_ptr()) for p in ps)
         tab = self._tables.get(gi)
         if tab is None or tab["ids"] != ids:
+            if tab is not None:
+                self._flush_steps(gi)  # the old table's step count goes back into state before it is replaced
             dev = ps[0].device
             chunk = _engine.lib().mg_adam_chunk()
             first, total = [], 0
@@ -47,6 +65,8 @@ class Adam(torch.optim.Optimizer):
                        g=torch.empty(len(ps), dtype=torch.int64, device=dev),
                        pin=[torch.empty(len(ps), dtype=torch.int64).pin_memory() for _ in range(2)], flip=0, grads=None)
             self._tables[gi] = tab
+        if tab.get("t") is None:
+            tab["t"] = self._group_step(ps)  # (re)read the step count from state for a new table
         ptrs = [p.grad.data_ptr() for p in ps]  # (holding the grad tensors to compare identities would keep them alive)
         if ptrs != tab["grads"]:
             pin = tab["pin"][tab["flip"]]
@@ -88,7 +108,7 @@ class Adam(torch.optim.Optimizer):
             tab = self._table(gi, ps)
             # the per-parameter `step` tensors (torch.optim.Adam's state format) are only touched when somebody looks:
             # between steps the count lives in one Python int per group
-            if tab.get("t") is None or fresh:
+            if fresh:
                 tab["t"] = self._group_step(ps)
             tab["t"] += 1
             tab["dirty"] = True
@@ -100,13 +120,19 @@ class Adam(torch.optim.Optimizer):
                                              ctypes.c_float(group["lr"]), ctypes.c_float(b1), ctypes.c_float(b2),
                                              ctypes.c_float(group["eps"]), ctypes.c_float(group["weight_decay"]),
                                              ctypes.c_longlong(tab["t"]), stream))
+            # The kernel wrote the parameters through raw pointers, which autograd's version counters cannot see.  Everything
+            # that caches derived state keyed on ``_version`` -- the modules' packed weight-norm folds (models.py
+            # ``_ensure_packed``), autograd's saved-tensor checks -- must observe an in-place update, exactly as after
+            # torch.optim.Adam: bump every updated parameter's counter (no kernel, no copy).
+            _bump_versions(ps)
         return loss
 
-    def _flush_steps(self):
+    def _flush_steps(self, only=None):
         for gi, tab in self._tables.items():
-            if tab.get("dirty"):
+            if (only is None or gi == only) and tab.get("dirty"):
+                live = {i[0] for i in tab["ids"]}
                 for p in self.param_groups[gi]["params"]:
-                    if id(p) in tab["ids"]:
+                    if id(p) in live:
                         self.state[p]["step"] = torch.tensor(float(tab["t"]))
                 tab["dirty"] = False
 

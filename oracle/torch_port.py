@@ -35,3 +35,20 @@ def generator_forward(ws, bs, mel):
             h = F.conv1d(F.leaky_relu(x), ws[a], bs[a], padding=d, dilation=d)
             x = F.conv1d(F.leaky_relu(h), ws[b], bs[b], padding=1) + x
     return torch.tanh(F.conv1d(F.leaky_relu(x), ws[29], bs[29], padding=3))
+
+
+def reference_state(state):
+    """state: name -> ndarray.  Returns [(weight_v, weight_g, bias)] * 30 as torch CPU tensors: what the reference's modules
+    hold (old-style weight_norm keeps g and v and recomputes w = g * v / ||v|| in a pre-forward hook on EVERY forward)."""
+    from melgan_multi_b200.synth import GENERATOR_LAYERS
+    return [(torch.from_numpy(state[n + ".weight_v"]), torch.from_numpy(state[n + ".weight_g"]), torch.from_numpy(state[n + ".bias"]))
+            for n, *_ in GENERATOR_LAYERS]
+
+
+@torch.no_grad()
+def generator_forward_reference(params, mel):
+    """Exactly the work of the reference's Generator.forward on a CPU (models.py:61-71 + the 30 weight_norm pre-forward
+    hooks, torch._weight_norm(v, g, 0) as torch.nn.utils.weight_norm computes it): this is what bench.py's reference arm and
+    cpu_baseline time."""
+    ws = [torch._weight_norm(v, g, 0) for v, g, _ in params]
+    return generator_forward(ws, [b for _, _, b in params], mel)

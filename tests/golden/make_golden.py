@@ -62,10 +62,27 @@ def grad_digest(named_params):
     return d
 
 
-def train_step_golden():
+TRAIN_CASE_B16 = dict(B=16, T=32, mel_seed=0, audio_seed=0)  # BASELINE config 3: batch 16, 8192-sample segments
+
+
+def config2_golden():
+    """BASELINE config 2 at full size (B=64, 80x32 mel -> 64x8192 samples) through the unmodified reference on CPU, for
+    N(0,1) and log-mel-like inputs (2 x 2 MB): every item of the bench workload is pinned, not just item 0."""
+    gen = load_state(ref_models.Generator(), synth.generator_state(1234))
+    out = {}
+    with torch.no_grad():
+        for realistic in (False, True):
+            x = synth.mel_input(64, 32, 0, realistic)
+            out["gen_B64_T32_s0_r%d" % int(realistic)] = gen(torch.from_numpy(x)).numpy()
+    path = os.path.join(HERE, "config2_outputs.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, "%.2f MB" % (os.path.getsize(path) / 1e6), len(out), "arrays")
+
+
+def train_step_golden(c=None, fname="train_step_grads.npz"):
     """Losses and parameter-gradient digests of ONE reference training step (train.py:108-129, without the optimizer
     updates): generator step through the discriminators, then the discriminator step on the detached audio."""
-    c = TRAIN_CASE
+    c = c or TRAIN_CASE
     gen = load_state(ref_models.Generator(), synth.generator_state(1234)).train()
     msd = load_state(ref_models.MultiScaleDiscriminator(), synth.discriminator_state(4321)).train()
     x = torch.from_numpy(synth.mel_input(c["B"], c["T"], c["mel_seed"]))
@@ -87,7 +104,8 @@ def train_step_golden():
     out["loss_disc"] = np.array(loss_disc.item())
     for k, v in grad_digest(msd.named_parameters()).items():
         out["dstep/D/" + k] = v
-    path = os.path.join(HERE, "train_step_grads.npz")
+    out["y_ghat_head"] = y_ghat.detach().numpy()[:2, 0, :256].copy()
+    path = os.path.join(HERE, fname)
     np.savez_compressed(path, **out)
     print("wrote", path, "%.2f MB" % (os.path.getsize(path) / 1e6), len(out), "arrays")
 
@@ -96,6 +114,12 @@ def main():
     if "--train-step" in sys.argv:  # only the training-step fixture (leaves reference_outputs.npz untouched)
         torch.set_num_threads(os.cpu_count())
         return train_step_golden()
+    if "--train-step-b16" in sys.argv:  # BASELINE config 3 shape (B=16 x 8192 samples)
+        torch.set_num_threads(os.cpu_count())
+        return train_step_golden(TRAIN_CASE_B16, "train_step_grads_b16.npz")
+    if "--config2" in sys.argv:
+        torch.set_num_threads(os.cpu_count())
+        return config2_golden()
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count())
     out = {}

@@ -177,3 +177,56 @@ def test_grouped_conv_backward_matches_torch(msd_module, layer, Bt, Lin):
         assert msd_module._dev.grouped_backward(scale, layer, dz, x.detach(), need_dx=False)[0] is None
     finally:
         torch.backends.cudnn.conv.fp32_precision = old
+
+
+def test_standalone_discriminator_forward_and_backward(golden, dstate, msd_module):
+    """Discriminator.forward on its own (reference models.py:87-103: returns (flattened logits, 7 feature maps)): scale 0 of
+    the reference golden is exactly discriminators[0] applied to y, so the stand-alone module must reproduce it; its
+    gradients must equal those of the same discriminator run inside the multi-scale stack's autograd function."""
+    from melgan_multi_b200 import models
+    B, L, seed = cases.MSD_CASES[0]
+    d = models.Discriminator()
+    d.load_state_dict({k[len("discriminators.0."):]: torch.from_numpy(v) for k, v in dstate.items()
+                       if k.startswith("discriminators.0.")})
+    d = d.cuda()
+    y = torch.from_numpy(synth.audio_input(B, L, seed)).cuda()
+    with torch.no_grad():
+        logits, fmap = d(y)
+    d._dev.check_status()
+    tag = "msd_B%d_L%d_s%d" % (B, L, seed)
+    ref = golden[tag + "_logit_r0"]
+    assert logits.shape == ref.shape and len(fmap) == 7
+    m, l2 = rel_errors(logits.cpu().numpy(), ref)
+    assert m < TOL and l2 < TOL, (m, l2)
+    for j in range(7):
+        a = fmap[j].cpu().numpy()
+        assert tuple(golden["%s_fmap_r0_%d_shape" % (tag, j)]) == a.shape
+        m, _ = rel_errors(a[:, :4, :48], golden["%s_fmap_r0_%d_head" % (tag, j)])
+        assert m < TOL, (j, m)
+    # backward: loss on the logits and one feature map, against the strict-fp32 stock-op restatement of the same layers
+    old = torch.backends.cudnn.conv.fp32_precision
+    torch.backends.cudnn.conv.fp32_precision = "ieee"
+    try:
+        yg = y.clone().requires_grad_(True)
+        logits, fmap = d(yg)
+        (logits.square().mean() + fmap[2].abs().mean()).backward()
+        got = {n: p.grad.clone() for n, p in d.named_parameters()}
+        gy = yg.grad.clone()
+        d.zero_grad()
+        import torch.nn.functional as F
+        yr = y.clone().requires_grad_(True)
+        x, maps = yr, []
+        for l, (name, _cin, _cout, _k, stride, groups, pad) in enumerate(synth.DISCRIMINATOR_LAYERS):
+            mod = d.layers()[l]
+            w = torch._weight_norm(mod.weight_v, mod.weight_g, 0)
+            x = F.conv1d(x, w, mod.bias, stride=stride, padding=pad, groups=groups)
+            if l < 6:
+                x = F.leaky_relu(x)
+            maps.append(x)
+        (maps[6].flatten(1).square().mean() + maps[2].abs().mean()).backward()
+        for n, p in d.named_parameters():
+            scale = p.grad.norm().item() + 1e-12
+            assert (got[n] - p.grad).norm().item() <= 2e-3 * scale, (n, (got[n] - p.grad).norm().item(), scale)
+        assert (gy - yr.grad).norm().item() <= 2e-3 * yr.grad.norm().item()
+    finally:
+        torch.backends.cudnn.conv.fp32_precision = old

@@ -57,7 +57,7 @@ def test_cabi_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(engine.LIB_PATH)
     for n in set(names):
         assert hasattr(lib, n), "missing export %s" % n
-    assert engine.lib().mg_abi_version() == 1
+    assert engine.lib().mg_abi_version() == 2
     fp32_blob = (4524290 - 4353) * 4
     tc_blob = 6 * 12 * (256 * 256 + 128 * 128 + 64 * 64 + 32 * 32)  # split-bf16 copy of the 24 ResBlock convs
     tc_blob += 4 * (512 * 256 * 16 + 256 * 128 * 16 + 128 * 64 * 4 + 64 * 32 * 4)  # ... and of the 4 ConvTranspose1d
@@ -151,6 +151,18 @@ def test_discriminators_refuse_cpu_tensors():
         d.discriminators[0](torch.zeros(1, 1, 64))
 
 
+def test_simt_test_library_is_separate_from_the_product():
+    """The first-generation fp32 SIMT generator is test infrastructure: it lives in its own library, and the product
+    library neither exports nor contains it."""
+    from melgan_multi_b200 import build
+    prod = ctypes.CDLL(engine.LIB_PATH)
+    assert not hasattr(prod, "mg_simt_gen_forward")
+    assert os.path.exists(build.TEST_LIB) and hasattr(ctypes.CDLL(build.TEST_LIB), "mg_simt_gen_forward")
+    for f in os.listdir(os.path.join(ROOT, "melgan_multi_b200")):
+        if f.endswith(".py") and f != "build.py":
+            assert "simt_test" not in open(os.path.join(ROOT, "melgan_multi_b200", f)).read(), f
+
+
 def test_cabi_argument_errors_are_reported_not_thrown():
     """Error behaviour of the C ABI that needs no GPU: negative return code + message, never an exception or exit."""
     L = engine.lib()
@@ -186,6 +198,9 @@ def test_cabi_argument_errors_are_reported_not_thrown():
     assert b"does not follow" in L.mg_last_error_string()  # Lout must be the conv's output length for Lin
     assert L.mg_msd_grouped_backward(p, 0, 1, p, p, p, p, p, p, 8, 2, 1024, 256, None) == -4  # workspace too small
     assert L.mg_msd_wn_backward(None, None, None, None, None, None) == -1 and L.mg_lrelu_backward(None, None, None, None, 4, None) == -1
+    assert L.mg_gen_conv_pre(None, None, None, 1, 1, None) == -1 and L.mg_gen_resblock_post(p, p, p, 0, 4, None) == -1
+    assert L.mg_disc_packed_bytes() * 3 == L.mg_msd_packed_bytes()
+    assert L.mg_disc_pack(None, None, None, None, None) == -1 and L.mg_disc_forward(p, p, 1, 0, p, p, None) == -1
     assert L.mg_adam_chunk() == 4096 and L.mg_adam_step(None, None, None, None, None, None, 1, 1, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1, None) == -1
 
 

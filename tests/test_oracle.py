@@ -107,3 +107,17 @@ def test_torch_cpu_port_matches_reference(golden):
         y = torch_port.generator_forward(ws, bs, torch.from_numpy(synth.mel_input(*case))).numpy()
         m, l2 = rel_errors(y, golden[cases.gen_key(*case)])
         assert m < TOL and l2 < TOL, (case, m, l2)
+
+
+def test_torch_cpu_port_matches_reference_at_config2():
+    """The timed CPU arm of bench.py (oracle/torch_port.generator_forward_reference: per-forward weight-norm + the conv
+    graph) at BASELINE config 2 full size against the unmodified reference's output (tests/golden/config2_outputs.npz)."""
+    import os
+    import torch
+    from oracle import torch_port
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "config2_outputs.npz"))
+    params = torch_port.reference_state(synth.generator_state(1234))
+    for realistic in (False, True):
+        y = torch_port.generator_forward_reference(params, torch.from_numpy(synth.mel_input(64, 32, 0, realistic))).numpy()
+        m, l2 = rel_errors(y, g["gen_B64_T32_s0_r%d" % int(realistic)])
+        assert m < TOL and l2 < TOL, (realistic, m, l2)

@@ -12,6 +12,7 @@ import numpy as np
 import pytest
 import torch
 
+from conftest import rel_errors
 from melgan_multi_b200 import synth
 from test_host import _train_case, check_grad_digest
 
@@ -26,10 +27,17 @@ def strict_fp32():
     torch.backends.cudnn.conv.fp32_precision = old
 
 
-def test_train_step_losses_and_gradients_match_reference(strict_fp32):
+TRAIN_CASE_B16 = dict(B=16, T=32, mel_seed=0, audio_seed=0)  # tests/golden/make_golden.py TRAIN_CASE_B16 = BASELINE config 3
+
+
+@pytest.mark.parametrize("which", ["small", "config3_b16"])
+def test_train_step_losses_and_gradients_match_reference(strict_fp32, which):
+    """One train.py:108-129 step against the unmodified reference's losses and per-parameter gradient digests: a tiny case
+    (B=2, 1024 samples) and BASELINE config 3 at full size (B=16 x 8192 samples; golden written by make_golden.py
+    --train-step-b16)."""
     from melgan_multi_b200 import models
-    gg = np.load(os.path.join(os.path.dirname(__file__), "golden", "train_step_grads.npz"))
-    c = _train_case()
+    fname, c = (("train_step_grads.npz", _train_case()) if which == "small" else ("train_step_grads_b16.npz", TRAIN_CASE_B16))
+    gg = np.load(os.path.join(os.path.dirname(__file__), "golden", fname))
     gen = models.Generator()
     gen.load_state_dict({k: torch.from_numpy(v) for k, v in synth.generator_state(1234).items()})
     msd = models.MultiScaleDiscriminator()
@@ -39,6 +47,9 @@ def test_train_step_losses_and_gradients_match_reference(strict_fp32):
     y = torch.from_numpy(synth.audio_input(c["B"], 256 * c["T"], c["audio_seed"])).cuda()
 
     y_ghat = gen(x)
+    if "y_ghat_head" in gg.files:
+        head = gg["y_ghat_head"]
+        assert np.abs(y_ghat.detach()[:2, 0, :256].cpu().numpy() - head).max() <= 1e-4 * np.abs(head).max()
     dr, dg, fr, fg = msd(y, y_ghat)
     loss_gen = models.generator_loss(dg) + models.feature_loss(fr, fg)
     loss_gen.backward()
@@ -53,7 +64,55 @@ def test_train_step_losses_and_gradients_match_reference(strict_fp32):
     assert abs(sum(rl) + sum(gl) - loss_disc.item()) < 1e-5
     w3 = check_grad_digest(gg, "dstep/D/", msd.named_parameters(), RTOL)
     msd._dev.check_status()
-    print("worst relative gradient-norm error:", max(w1, w2, w3))
+    print("worst relative gradient-norm error (%s):" % which, max(w1, w2, w3))
+
+
+def test_training_with_multi_tensor_adam_tracks_torch_adam():
+    """melgan_multi_b200.optim.Adam writes parameters through raw pointers; the modules re-fold their
+    packed weights only when a parameter's (data_ptr, _version) changes, so the optimizer must bump the versions or every
+    later forward runs on the initial weights.  Three train.py:108-129 steps with our Adam vs torch.optim.Adam from the same
+    initial state: losses, outputs and parameters must stay together (and must move)."""
+    from melgan_multi_b200 import models
+    from melgan_multi_b200.optim import Adam
+    x = torch.from_numpy(synth.mel_input(2, 4, 5)).cuda()
+    y = torch.from_numpy(synth.audio_input(2, 1024, 6)).cuda()
+
+    def run(opt_cls):
+        gen = models.Generator()
+        gen.load_state_dict({k: torch.from_numpy(v) for k, v in synth.generator_state(1234).items()})
+        msd = models.MultiScaleDiscriminator()
+        msd.load_state_dict({k: torch.from_numpy(v) for k, v in synth.discriminator_state(4321).items()})
+        gen, msd = gen.cuda().train(), msd.cuda().train()
+        g_opt = opt_cls(gen.parameters(), 2e-4, betas=(0.5, 0.9))
+        d_opt = opt_cls(msd.parameters(), 2e-4, betas=(0.5, 0.9))
+        losses = []
+        for _ in range(3):
+            g_opt.zero_grad()
+            y_ghat = gen(x)
+            dr, dg, fr, fg = msd(y, y_ghat)
+            loss_gen = models.generator_loss(dg) + models.feature_loss(fr, fg)
+            loss_gen.backward()
+            g_opt.step()
+            d_opt.zero_grad()
+            dr, dg, _, _ = msd(y, y_ghat.detach())
+            loss_disc, _, _ = models.discriminator_loss(dr, dg)
+            loss_disc.backward()
+            d_opt.step()
+            losses.append((loss_gen.item(), loss_disc.item()))
+        with torch.no_grad():
+            out = gen(x)
+        return losses, out, [p.detach().clone() for p in list(gen.parameters()) + list(msd.parameters())]
+
+    l_ref, o_ref, p_ref = run(torch.optim.Adam)
+    l_our, o_our, p_our = run(Adam)
+    assert abs(l_ref[0][0] - l_ref[2][0]) > 1e-4 * abs(l_ref[0][0])  # training moved the loss
+    for (a, b), (c, d) in zip(l_ref, l_our):
+        assert abs(a - c) <= 2e-3 * abs(a) and abs(b - d) <= 2e-3 * abs(b), (l_ref, l_our)
+    m, l2 = rel_errors(o_our.cpu().numpy(), o_ref.cpu().numpy())
+    assert m < 5e-3 and l2 < 5e-3, (m, l2)
+    # Adam's first steps move every element by ~lr whatever the gradient: parameters agree to a fraction of 3 * lr
+    worst = max(float((a - b).abs().max()) for a, b in zip(p_ref, p_our))
+    assert worst <= 2e-4, worst
 
 
 def test_multi_tensor_adam_matches_torch_adam():
