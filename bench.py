@@ -13,10 +13,11 @@ audio frames.  Weights are seeded random-init (melgan_multi_b200.syn
              in, H2D copy, kernels, D2H copy of the audio out, every step, wall clock, max over ranks.
   roofline   dominant kernel (stage 1: ConvT 256->128 + 128-channel ResBlock, 44% of the FLOPs),
              per-kernel CUDA events from mg_gen_forward_timed in a second pass of K steps.
-  cpu_baseline  oracle/torch_port.py (the reference's arithmetic on PyTorch-CPU/oneDNN, all host
-             threads) on a bounded sample, rank 0 at N=1 only.
-  --impl reference   times that same CPU port as the reference arm (the reference is pure Python and
-             /root/reference does not exist on the GPU box).
+  cpu_baseline  oracle/torch_port.generator_forward_reference (the reference's forward on PyTorch-CPU/oneDNN,
+             per-forward weight-norm included, all host threads) on the FULL config-2 batch, a bounded
+             number of iterations, median; rank 0 at N=1 only.
+  --impl reference   times that same CPU port as the reference arm at the same config (the reference is pure
+             Python and /root/reference does not exist on the GPU box); value from the MEDIAN step.
 """
 import argparse
 import json
@@ -49,6 +50,7 @@ def flops_per_mel_frame():
 
 
 ALG_BYTES_PER_FRAME = 152896  # per-stage-fused design, fp32 activations in/out of each kernel
+ALG_WEIGHT_BYTES = 18080000   # 18.08 MB of folded weights + biases, read once per launch chain
 STAGE_BYTES_PER_FRAME = [320 * 1 + 2048, 2048 + 8192, 8192 + 32768, 32768 + 32768, 32768 + 1024]
 
 
@@ -164,54 +166,48 @@ def usable_cpus():
     return max(1, n)
 
 
-def cpu_port_throughput(sample_B, budget_s, min_iters=2):
-    """Times oracle/torch_port.py on all host threads.  Returns (audio_frames/s, cores, iters, per-iter s)."""
+def cpu_port_steps(n_steps, warmup, budget_s=None):
+    """Times oracle/torch_port.generator_forward_reference (weight-norm fold of the 30 layers + the conv graph: what the
+    reference's Generator.forward does on a CPU) on the whole config-2 batch, all usable host threads.  Returns
+    (per-step seconds list, cores).  budget_s bounds the timed part (at least 2 steps)."""
     import torch
     from melgan_multi_b200 import synth
     from oracle import torch_port
     cores = usable_cpus()
     torch.set_num_threads(cores)
-    ws, bs = torch_port.fold_state(synth.generator_state(1234))
-    x = torch.from_numpy(synth.mel_input(sample_B, T_FRAMES, 0))
-    torch_port.generator_forward(ws, bs, x)  # warm-up
+    params = torch_port.reference_state(synth.generator_state(1234))
+    xs = [torch.from_numpy(synth.mel_input(B_PER_GPU, T_FRAMES, i)) for i in range(2)]
+    for i in range(warmup):  # oneDNN primitive creation + thread-pool spin-up take several calls
+        torch_port.generator_forward_reference(params, xs[i % 2])
     times, t_all = [], time.perf_counter()
-    while len(times) < min_iters or (time.perf_counter() - t_all) < budget_s:
+    for i in range(n_steps):
         t0 = time.perf_counter()
-        torch_port.generator_forward(ws, bs, x)
+        torch_port.generator_forward_reference(params, xs[i % 2])
         times.append(time.perf_counter() - t0)
-        if len(times) >= 50:
+        if budget_s is not None and len(times) >= 2 and time.perf_counter() - t_all > budget_s:
             break
-    med = statistics.median(times)
-    return sample_B * T_FRAMES * 256 / med, cores, len(times), med
+    return times, cores
 
 
 def run_reference(args):
-    """Reference arm: the reference's CPU implementation (PyTorch-CPU port of models.py:61-71)."""
+    """Reference arm: the reference's CPU implementation of the path (PyTorch-CPU restatement of models.py:61-71 with the
+    per-forward weight-norm hooks), same config as the B200 arm: the full B=64 batch per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch
-    from melgan_multi_b200 import synth
-    from oracle import torch_port
-    cores = usable_cpus()
-    torch.set_num_threads(cores)
-    sample_B = 16
-    ws, bs = torch_port.fold_state(synth.generator_state(1234))
-    x = torch.from_numpy(synth.mel_input(sample_B, T_FRAMES, 0))
-    for _ in range(max(5, args.warmup)):  # oneDNN primitive creation + thread-pool spin-up take several calls
-        torch_port.generator_forward(ws, bs, x)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        torch_port.generator_forward(ws, bs, x)
-    dt = time.perf_counter() - t0
-    val = args.steps * sample_B * T_FRAMES * 256 / dt
-    sample = "B=%d of the 64 x 80x32 mel segments per step, PyTorch-CPU (oneDNN) port of the reference forward, %d threads" % (
-        sample_B, cores)
+    times, cores = cpu_port_steps(args.steps, max(3, args.warmup))
+    frames = B_PER_GPU * T_FRAMES * 256
+    med = statistics.median(times)
+    val = frames / med
+    sample = ("the whole config-2 batch (64 x 80x32 mel) per step; PyTorch-CPU (oneDNN) restatement of the reference forward "
+              "incl. its 30 per-forward weight-norm folds, %d threads; value = frames / MEDIAN step (mean %.3f s, min %.3f s, "
+              "max %.3f s over %d steps)" % (cores, sum(times) / len(times), min(times), max(times), len(times)))
     emit(({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "steps": len(times), "warmup": max(3, args.warmup), "ms_per_step": 1e3 * med,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
+        "config": {"workload": WORKLOAD, "batch_per_gpu": B_PER_GPU, "mel_frames": T_FRAMES, "global_batch": B_PER_GPU,
+                   "timing": "median of per-step wall clock", "weights": "seeded random init"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -333,26 +329,26 @@ def main():
     flops_of["up2+res2"] = up_f[2] + res_f[2]  # stride-2 ConvT fused into the stage kernel
     flops_of["up3+res3+post"] = up_f[3] + res_f[3] + post_f * frames
     k_flops = [flops_of[n] for n in names]
-    tc_path = os.environ.get("MG_GEN_PATH", "tc") != "simt"
-    dom = names.index("res1") if tc_path else names.index("stage1(up+res)")
+    dom = names.index("res1")
     dom_tflops = k_flops[dom] / (kms[dom] * 1e-3) / 1e12
     fwd_flops = sum(k_flops)
     packed_bytes = engine.lib().mg_gen_packed_bytes()
-    # algorithmic HBM bytes: SURVEY 8(d) per-stage-fused figure; the tc pipeline currently makes one extra
-    # round trip of the stride-8 ConvT outputs (written by up_i, re-read by res_i): + 2 * (8+32) KB per mel frame
-    # (+ 2 * (32+32) KB when the stride-2 ConvTs run as separate kernels, MG_GEN_FUSE_UP=0)
-    extra = 2 * (8192 + 32768 + (0 if "up2+res2" in names else 32768) + (0 if "up3+res3+post" in names else 32768)) if tc_path else 0
-    fwd_bytes = (ALG_BYTES_PER_FRAME + extra) * frames + packed_bytes
+    # ALGORITHMIC HBM bytes = SURVEY 8(d): 152 896 B per mel frame (per-stage-fused design) + 18.08 MB of folded fp32 weights
+    # = 331.2 MB at config 2.  What this pipeline's kernels actually move by design is more: the ConvT outputs of the
+    # stages whose ConvT is a separate kernel make one extra HBM round trip (written by up_i, re-read by res_i), and the
+    # weights are streamed as split-bf16 (hi + lo: the same 4 bytes per weight) -- reported as moved_bytes / wasted ratio.
+    extra = 2 * (8192 + 32768 + (0 if "up2+res2" in names else 32768) + (0 if "up3+res3+post" in names else 32768))
+    alg_bytes = ALG_BYTES_PER_FRAME * frames + ALG_WEIGHT_BYTES
+    moved_bytes = (ALG_BYTES_PER_FRAME + extra) * frames + packed_bytes
     fwd_ms = total_ms / K
     traffic = None  # dram bytes per launch of the dominant kernel, from the committed ncu --set full capture
     tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
-    if tc_path and os.path.exists(tpath):
+    if os.path.exists(tpath):
         t = json.load(open(tpath)).get("res1")
         if t:
             traffic = t["dram_read_bytes"] + t["dram_write_bytes"]
     roofline = {
-        "kernel": ("resblock_tc_kernel<C=128> (stage-1 ResBlock: 6 k3 convs, 36% of generator FLOPs)" if tc_path else
-                   "gen_stage_kernel<stage 1: lrelu+ConvT(256->128,k16,s8)+ResBlock(128)>"),
+        "kernel": "resblock_tc_kernel<C=128> (stage-1 ResBlock: 6 k3 convs, 36% of generator FLOPs)",
         "bound": "tensor", "achieved": dom_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
         "frac": dom_tflops / peaks["bf16_tflops"], "traffic": traffic,
         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r01_ncu_res1_key_metrics.txt); "
@@ -360,15 +356,15 @@ def main():
         "peak_source": "%s bf16 dense burst (MEASURED_PEAKS.json)" % peaks["source"],
         "algorithmic_flops_per_launch": k_flops[dom], "avg_launch_ms": float(kms[dom]),
         "math": ("split-bf16 tcgen05: 3 MMA passes per product, so tensor-pipe work is 3x the algorithmic FLOPs "
-                 "(pipe-level fraction = 3 * frac); conv_pre/post fp32 SIMT" if tc_path else
-                 "fp32 FFMA (SIMT), 1 pass; tensor pipe not used"),
-        "path": "tc" if tc_path else "simt",
+                 "(pipe-level fraction = 3 * frac)"),
         "kernel_ms": {n: float(v) for n, v in zip(names, kms)},
         "kernel_tflops": {n: k_flops[i] / (kms[i] * 1e-3) / 1e12 for i, n in enumerate(names)},
-        "hbm": {"achieved": fwd_bytes / (fwd_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": fwd_bytes / (fwd_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                "algorithmic_bytes_per_forward": fwd_bytes,
-                "note": "whole forward; the fused generator is 683 FLOP/B, i.e. math-bound (SURVEY 8d)"},
+        "hbm": {"achieved": alg_bytes / (fwd_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": alg_bytes / (fwd_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                "algorithmic_bytes_per_forward": alg_bytes, "moved_bytes_per_forward_by_design": moved_bytes,
+                "wasted_traffic_ratio": moved_bytes / alg_bytes,
+                "note": "whole forward, SURVEY 8(d) bytes (152 896 B/frame + 18.08 MB weights); the fused generator is "
+                        "683 FLOP/B, i.e. math-bound: 60 % of HBM peak would need 2.5 PFLOP/s (SURVEY 8d)"},
         "forward_tflops": fwd_flops / (fwd_ms * 1e-3) / 1e12,
     }
 
@@ -392,17 +388,18 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1:
-        v, cores, iters, med = cpu_port_throughput(16, args.cpu_budget)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "B=16 of the 64 segments (80x32 mel each), %d iterations, median %.3f s; "
-                         "oracle/torch_port.py = the reference forward on PyTorch-CPU/oneDNN, all threads" % (iters, med)}
+        times, cores = cpu_port_steps(50, 3, args.cpu_budget)
+        med = statistics.median(times)
+        cpu = {"value": B * T * 256 / med, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "the whole config-2 batch (64 x 80x32 mel), %d iterations, median %.3f s; oracle/torch_port."
+                         "generator_forward_reference = the reference forward (incl. per-forward weight-norm) on "
+                         "PyTorch-CPU/oneDNN, all threads" % (len(times), med)}
 
     if rank == 0:
         emit(({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": ("f32 in/out; products as 3 split-bf16 tcgen05 passes with fp32 accumulation (fp32-equivalent, ~1e-5)"
-                      if tc_path else "f32"),
+            "dtype": "f32 in/out; products as 3 split-bf16 tcgen05 passes with fp32 accumulation (fp32-equivalent, ~1e-5)",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "mel_frames": T, "global_batch": B * world,
                        "parallelism": "dp%d (independent batches, no collective)" % world,

@@ -156,8 +156,8 @@ class _StatusWatch:
         _StatusWatch._live.add(self)
 
     def check(self, wait=False):
-        if not self.pending:
-            return
+        if not self.pending or self.torch.cuda.is_current_stream_capturing():
+            return  # (event queries are illegal while this thread captures a CUDA graph)
         if wait:
             self.event.synchronize()
         elif not self.event.query():

@@ -215,6 +215,11 @@ def check_grad_digest(golden_grads, prefix, named_params, rtol):
         g = p.grad.detach().double().reshape(-1).cpu()
         l2 = float(golden_grads[prefix + n + "/l2"])
         scale = max(l2, 1e-12)
+        if n.endswith("weight_g") and g.numel() == 1:
+            # d weight_g = <dw, v> / ||v|| of a ONE-row layer (conv_post, conv_post2): a projection that cancels to a value far
+            # below |dw| |v| (1e-5 against 1e-2 at B=16), so its error is set by the size of dw, i.e. of the sibling weight_v's
+            # gradient, not by its own magnitude
+            scale = max(scale, 0.02 * float(golden_grads[prefix + n[:-1] + "v/l2"]))
         assert abs(float(g.norm()) - l2) <= rtol * scale, (prefix, n, float(g.norm()), l2)
         assert abs(float(g.sum()) - float(golden_grads[prefix + n + "/sum"])) <= rtol * scale * max(1.0, g.numel() ** 0.5), (prefix, n)
         head = golden_grads[prefix + n + "/head"]

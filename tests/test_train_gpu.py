@@ -105,14 +105,20 @@ def test_training_with_multi_tensor_adam_tracks_torch_adam():
 
     l_ref, o_ref, p_ref = run(torch.optim.Adam)
     l_our, o_our, p_our = run(Adam)
-    assert abs(l_ref[0][0] - l_ref[2][0]) > 1e-4 * abs(l_ref[0][0])  # training moved the loss
-    for (a, b), (c, d) in zip(l_ref, l_our):
-        assert abs(a - c) <= 2e-3 * abs(a) and abs(b - d) <= 2e-3 * abs(b), (l_ref, l_our)
+    print("losses torch.optim.Adam:", l_ref, "\nlosses optim.Adam:      ", l_our)
+    moved_g, moved_d = abs(l_ref[2][0] - l_ref[0][0]), abs(l_ref[2][1] - l_ref[0][1])
+    assert moved_g > 1e-3 * abs(l_ref[0][0]) and moved_d > 1e-3 * abs(l_ref[0][1])  # three steps moved both losses...
+    for (a, b), (c, d) in zip(l_ref, l_our):  # ...and the two optimizers moved them the same way (a stale forward would not)
+        assert abs(a - c) <= 0.05 * moved_g and abs(b - d) <= 0.05 * moved_d, (l_ref, l_our)
     m, l2 = rel_errors(o_our.cpu().numpy(), o_ref.cpu().numpy())
     assert m < 5e-3 and l2 < 5e-3, (m, l2)
-    # Adam's first steps move every element by ~lr whatever the gradient: parameters agree to a fraction of 3 * lr
-    worst = max(float((a - b).abs().max()) for a, b in zip(p_ref, p_our))
-    assert worst <= 2e-4, worst
+    # Parameters: Adam's first steps move an element by ~lr * sign(g), so an element whose gradient is at the noise level of
+    # the (atomics-based, run-to-run non-deterministic) stock backward can differ by up to 2 * lr per step; nearly all
+    # elements agree far better than that
+    diffs = torch.cat([(a - b).abs().reshape(-1) for a, b in zip(p_ref, p_our)])
+    worst, frac = float(diffs.max()), float((diffs > 2e-5).float().mean())
+    print("parameters after 3 steps: worst |diff| %.2e, fraction above 2e-5: %.2e" % (worst, frac))
+    assert worst <= 3 * 2 * 2e-4 * 1.05 and frac < 0.02, (worst, frac)
 
 
 def test_multi_tensor_adam_matches_torch_adam():
@@ -130,7 +136,10 @@ def test_multi_tensor_adam_matches_torch_adam():
             for a, b in zip(ref_p, our_p):
                 g = torch.randn(a.shape, generator=gen).cuda()
                 a.grad, b.grad = g.clone(), g.clone()
+            v0 = [p._version for p in our_p]
             ref.step(); ours.step()
+            # raw-pointer writes are invisible to autograd: the optimizer must bump the version counters itself
+            assert all(p._version > v for p, v in zip(our_p, v0))
             if it == 2:  # checkpoint written by torch's Adam loads into ours and vice versa
                 sd_ref, sd_ours = ref.state_dict(), ours.state_dict()
                 ours.load_state_dict(sd_ref); ref.load_state_dict(sd_ours)
