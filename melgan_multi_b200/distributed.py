@@ -1,23 +1,36 @@
 """Drop-in for the three functions train.py uses from the reference's distributed.py
 (`init_distributed`, `apply_gradient_allreduce`, `reduce_tensor`; /root/reference/distributed.py:37-142).
 
-Same observable behaviour -- parameters broadcast from rank 0 at wrap time, every parameter's gradient
-replaced by the across-rank mean after each backward, NCCL underneath through torch.distributed -- with the
-data path reorganised for NVLink-class fabrics where launch count, not link bandwidth, is the cost:
+Same observable behaviour -- parameters broadcast from rank 0 at wrap time, every parameter's gradient replaced by the
+across-rank mean before an optimizer consumes it, NCCL underneath through torch.distributed -- with the data path
+reorganised for NVLink-class fabrics, where launch count and exposed latency, not link bandwidth, are the cost:
 
-  * one persistent flat fp32 gradient buffer per module: every ``param.grad`` is a *view* into it, so the
-    all-reduce runs in place on one tensor with no ``torch.cat`` and no copy-back (the reference flattens and
-    un-flattens 18 MB / 68 MB per call, distributed.py:125-129);
-  * one flat buffer for the start-up broadcast instead of 90 / 63 tiny broadcasts (distributed.py:100-103);
-  * the all-reduce is skipped for a module whose gradients were produced by a backward that its owner is
-    about to discard: ``skip_next_reduction(module)`` lets the training loop drop the wasted 67.7 MB
-    discriminator all-reduce of the generator step without changing results.
+  * one persistent flat fp32 gradient buffer per module: every ``param.grad`` is a *view* into it, so the all-reduce runs
+    in place with no ``torch.cat`` and no copy-back (the reference flattens and un-flattens 18 MB / 68 MB per call,
+    distributed.py:125-129).  Gradients that autograd allocated elsewhere (``zero_grad(set_to_none=True)``, the default
+    of torch 2.x) are adopted bucket by bucket with one multi-tensor copy;
+  * **overlap with backward**: the buffer is cut into buckets (reverse registration order, <= 24 MiB: one per
+    Discriminator, one for the Generator); a bucket's all-reduce is launched asynchronously from the gradient hooks the
+    moment its last gradient exists, while autograd is still computing the other buckets (the reference reduces
+    everything after backward has finished, distributed.py:131-135); the end-of-backward callback only waits;
+  * **no wasted collective, without touching train.py**: in the generator step ``loss_gen.backward()`` also produces
+    discriminator gradients that ``d_optim.zero_grad()`` throws away (train.py:117,120), yet the reference all-reduces
+    them (67.7 MB of the 153.5 MB per step).  The wrapper watches what happens to each backward's gradients -- consumed
+    by an ``optimizer.step`` (global optimizer pre-hook) or dropped by the module's next forward -- keyed by the set of
+    wrapped modules that ran forward before that backward ({G, D} in the generator step, {D} in the discriminator step).
+    Once a key has been seen to end in a discard, that key's gradients are kept local and *lazily* reduced only if an
+    optimizer does ask for them after all, so results never differ from the reference's (MG_DDP_DEDUP=0 turns it off);
+  * one flat buffer for the start-up broadcast instead of 90 / 63 tiny broadcasts (distributed.py:100-103).
 
 Batches shard naturally across ranks (DistributedSampler, train.py:71); there is no other collective.
 """
+import os
+
 import torch
 import torch.distributed as dist
 from torch.autograd import Variable
+
+BUCKET_BYTES = 24 << 20
 
 
 def reduce_tensor(tensor, num_gpus):
@@ -36,47 +49,169 @@ def init_distributed(rank, num_gpus, group_name, dist_backend, dist_url):
                             group_name=group_name)
 
 
-class _FlatGrads:
-    """Owns the flat gradient buffer of one module and re-points ``param.grad`` at views of it."""
+# ---- process-wide bookkeeping of the wrapped modules -------------------------------------------------------------------
+_REDUCERS = []          # every _GradReducer of this process
+_FORWARD_SET = set()    # ids of the reducers whose module ran forward since the last backward pass ended
+_PASS = {"key": None}   # key of the backward pass in flight (frozenset of reducer ids), None between passes
+_OPT_HOOK = {"handle": None}
+
+
+def _end_pass():
+    _PASS["key"] = None
+    _FORWARD_SET.clear()
+
+
+def _optimizer_pre_step(optimizer, args, kwargs):
+    """Global optimizer hook: the gradients of every wrapped module this optimizer owns are about to be consumed."""
+    owned = getattr(optimizer, "_mg_reducers", None)
+    if owned is None or owned[0] != len(_REDUCERS):
+        ids = {id(p) for g in optimizer.param_groups for p in g["params"]}
+        owned = (len(_REDUCERS), [r for r in _REDUCERS if any(id(p) in ids for p in r.params)])
+        optimizer._mg_reducers = owned
+    for r in owned[1]:
+        r.consume()
+
+
+class _GradReducer:
+    """Flat gradient buffer, buckets and reduction state of one wrapped module."""
 
     def __init__(self, module):
+        self.module = module
+        self.world = dist.get_world_size()
         self.params = [p for p in module.parameters() if p.requires_grad]
+        self.dedup = os.environ.get("MG_DDP_DEDUP", "1") != "0"
+        self.stats = {"allreduce_calls": 0, "allreduce_bytes": 0, "skipped_bytes": 0, "lazy_flushes": 0, "passes": 0}
+        self.history = {}            # pass key -> "consumed" | "discarded"
+        self.unconsumed_key = None   # key of the last backward whose gradients nobody has consumed or dropped yet
+        self.pending = False         # ... and those gradients are still local (lazy mode): reduce them if consumed
+        self.in_pass = False
+        self.skip_once = False
         if not self.params:
             self.flat = None
             return
         ref = self.params[0]
+        if any(p.dtype != ref.dtype or p.device != ref.device for p in self.params):
+            raise ValueError("apply_gradient_allreduce: parameters of one module must share dtype and device")
         n = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(n, dtype=ref.dtype, device=ref.device)
-        self.views = []
-        off = 0
-        for p in self.params:
-            self.views.append(self.flat.narrow(0, off, p.numel()).view_as(p))
+        # the flat buffer is laid out in REVERSE registration order: gradients appear roughly in that order during backward,
+        # so bucket 0 (the last layers) fills -- and starts its all-reduce -- first
+        self.views, self.bucket_of, self.buckets = [None] * len(self.params), [0] * len(self.params), []
+        off, b_start, b_members = 0, 0, []
+        for i in reversed(range(len(self.params))):
+            p = self.params[i]
+            nbytes = p.numel() * p.element_size()
+            if b_members and (off - b_start) * ref.element_size() + nbytes > BUCKET_BYTES:
+                self.buckets.append((b_start, off, b_members))
+                b_start, b_members = off, []
+            self.views[i] = self.flat.narrow(0, off, p.numel()).view_as(p)
+            self.bucket_of[i] = len(self.buckets)
+            b_members.append(i)
             off += p.numel()
+        self.buckets.append((b_start, off, b_members))
+        self._reset_pass()
 
-    def adopt(self):
-        """Make every existing .grad a view of the flat buffer (copying a foreign grad in once).  Returns
-        False if some parameter has no gradient yet (then nothing is reduced for it, like the reference)."""
-        complete = True
-        for p, v in zip(self.params, self.views):
-            if p.grad is None:
-                complete = False
-                v.zero_()
-            elif p.grad.data_ptr() != v.data_ptr():
-                v.copy_(p.grad)
-                p.grad = v
-        return complete
+    def _reset_pass(self):
+        nb = len(self.buckets)
+        self.ready, self.launched = [0] * nb, [False] * nb
+        self.foreign = [([], []) for _ in range(nb)]
+        self.works = []
+
+    # -- forward / backward events ------------------------------------------------------------------------------------
+    def on_forward(self):
+        self.module.needs_reduction = True
+        _FORWARD_SET.add(id(self))
+        if self.unconsumed_key is not None:  # the previous backward's gradients were never asked for: remember that
+            self.history[self.unconsumed_key] = "discarded"
+            if self.pending:
+                self.stats["skipped_bytes"] += self.flat.numel() * self.flat.element_size()
+            self.unconsumed_key, self.pending = None, False
+
+    def _begin_pass(self):
+        if _PASS["key"] is None:
+            _PASS["key"] = frozenset(_FORWARD_SET)
+            Variable._execution_engine.queue_callback(_end_pass)
+        self.key = _PASS["key"]
+        self.in_pass = True
+        self.stats["passes"] += 1
+        self._reset_pass()
+        self.lazy = self.skip_once or (self.dedup and self.history.get(self.key) == "discarded")
+        Variable._execution_engine.queue_callback(self._finish_pass)
+
+    def on_grad(self, i):
+        """post-accumulate-grad hook of parameter i: adopt the gradient into the flat buffer; launch a full bucket."""
+        if not self.module.needs_reduction:
+            return  # (reference: nothing is reduced unless the module ran forward since the last reduction)
+        if not self.in_pass:
+            self._begin_pass()
+        p, v, b = self.params[i], self.views[i], self.bucket_of[i]
+        g = p.grad
+        if g is not None and g.data_ptr() != v.data_ptr():
+            self.foreign[b][0].append(v)
+            self.foreign[b][1].append(g.detach())
+            p.grad = v
+        self.ready[b] += 1
+        if self.ready[b] == len(self.buckets[b][2]):
+            self._launch(b)
+
+    def _launch(self, b):
+        if self.launched[b]:
+            return
+        self.launched[b] = True
+        dsts, srcs = self.foreign[b]
+        if dsts:
+            torch._foreach_copy_(dsts, srcs)  # one multi-tensor copy per bucket
+        if not self.lazy:
+            start, end, _ = self.buckets[b]
+            chunk = self.flat.narrow(0, start, end - start)
+            self.works.append(dist.all_reduce(chunk, async_op=True))
+            self.stats["allreduce_calls"] += 1
+            self.stats["allreduce_bytes"] += chunk.numel() * chunk.element_size()
+
+    def _finish_pass(self):
+        """End-of-backward callback (the reference does ALL its work here, distributed.py:105-129): buckets whose
+        parameters did not all receive a gradient are launched now, then the in-flight all-reduces are awaited."""
+        if not self.in_pass:
+            return
+        self.in_pass = False
+        self.module.needs_reduction = False
+        for b in range(len(self.buckets)):
+            self._launch(b)
+        if self.lazy:
+            if self.skip_once:  # skip_next_reduction(): the caller promised to throw these gradients away
+                self.skip_once = False
+                self.unconsumed_key, self.pending = None, False
+                return
+            self.unconsumed_key, self.pending = self.key, True
+            return
+        for w in self.works:
+            w.wait()
+        self.works = []
+        self.flat.div_(self.world)
+        self.unconsumed_key, self.pending = self.key, False
+
+    def consume(self):
+        """An optimizer is about to read this module's gradients."""
+        if self.unconsumed_key is None:
+            return
+        if self.pending:  # predicted "discarded", but they are wanted after all: reduce now (blocking, exact)
+            dist.all_reduce(self.flat)
+            self.flat.div_(self.world)
+            self.stats["lazy_flushes"] += 1
+            self.stats["allreduce_calls"] += 1
+            self.stats["allreduce_bytes"] += self.flat.numel() * self.flat.element_size()
+        self.history[self.unconsumed_key] = "consumed"
+        self.unconsumed_key, self.pending = None, False
 
 
 def skip_next_reduction(module):
-    """The next backward's gradients of `module` will be thrown away by the caller (train.py:117 followed by
-    d_optim.zero_grad() at :120): do not all-reduce them."""
-    module._skip_reduction_once = True
+    """Explicit form of what the wrapper learns by itself: the next backward's gradients of `module` will be thrown
+    away by the caller (train.py:117 followed by d_optim.zero_grad() at :120), do not all-reduce them."""
+    module._grad_reducer.skip_once = True
 
 
 def apply_gradient_allreduce(module):
     """Same contract as the reference's apply_gradient_allreduce (distributed.py:90-142)."""
-    world = dist.get_world_size()
-
     # start-up sync: one flat broadcast per dtype instead of one per tensor
     tensors = [t for t in module.state_dict().values() if torch.is_tensor(t)]
     by_dtype = {}
@@ -90,34 +225,19 @@ def apply_gradient_allreduce(module):
             t.detach().copy_(flat.narrow(0, off, t.numel()).view_as(t))
             off += t.numel()
 
-    state = _FlatGrads(module)
-    module._flat_grads = state
+    red = _GradReducer(module)
+    _REDUCERS.append(red)
+    module._grad_reducer = red
+    module._flat_grads = red  # (name kept from round 1)
     module.needs_reduction = False
-    module._skip_reduction_once = False
+    if _OPT_HOOK["handle"] is None:
+        from torch.optim.optimizer import register_optimizer_step_pre_hook
+        _OPT_HOOK["handle"] = register_optimizer_step_pre_hook(_optimizer_pre_step)
 
-    def allreduce_params():
-        if not module.needs_reduction:
-            return
-        module.needs_reduction = False
-        if module._skip_reduction_once:
-            module._skip_reduction_once = False
-            return
-        if state.flat is None:
-            return
-        state.adopt()
-        dist.all_reduce(state.flat)
-        state.flat /= world
+    for i, p in enumerate(red.params):
+        p.register_post_accumulate_grad_hook(lambda _p, i=i: red.on_grad(i))
 
-    def allreduce_hook(*unused):
-        Variable._execution_engine.queue_callback(allreduce_params)
-
-    for p in state.params:
-        p.register_hook(allreduce_hook)
-
-    def set_needs_reduction(self, inputs, output):
-        self.needs_reduction = True
-
-    module.register_forward_hook(set_needs_reduction)
+    module.register_forward_hook(lambda mod, inputs, output: red.on_forward())
     return module
 
 

@@ -181,8 +181,7 @@ class Discriminator(nn.Module):
     def layers(self):
         return [self.conv_pre] + list(self.grouped_convs) + [self.conv_post1, self.conv_post2]
 
-    n_scales = 1     # what _MSDFunction walks: this module is "a one-scale stack without pooling"
-    meanpools = ()
+    meanpools = ()   # what _MSDFunction walks for scale 0: no pooling
 
     def _param_triplets(self):
         mods = self.layers()
@@ -210,84 +209,82 @@ class Discriminator(nn.Module):
             flat = []
             for v, g, b in zip(vs, gs, bs):
                 flat += [v, g, b]
-            fmap = list(_MSDFunction.apply(self, x, *flat))
+            fmap = list(_MSDFunction.apply(self, 0, {}, x, *flat))
         else:
             fmap = self._engine_forward(x)[0]
         return torch.flatten(fmap[6], 1, -1), fmap
 
 
 class _MSDFunction(torch.autograd.Function):
-    """Forward on the fused sm_100a kernels (real and generated stacked as one batch).  Backward layer by layer on the
-    saved feature maps, without recomputing the forward: the grouped k41 convs (layers 1..4) and weight-norm on the
+    """ONE discriminator of the stack as an autograd node: forward on the fused sm_100a kernels, backward layer by layer on
+    the saved feature maps without recomputing the forward -- the grouped k41 convs (layers 1..4) and weight-norm on the
     hand-written kernels of csrc/mg_disc_bwd.cu (cuDNN launches one kernel per group for them), the dense layers
     (conv_pre, conv_post1, conv_post2) through aten::convolution_backward (open row: native tcgen05 dgrad/wgrad).
-    Inputs: stacked audio [2B,1,L], then 21 x (weight_v, weight_g, bias); outputs: the 21 feature maps, scale-major."""
+
+    The three scales of a MultiScaleDiscriminator are three nodes that share one forward: the first node to run launches the
+    whole fused stack (real and generated stacked as one batch, the scales on forked streams) and parks the feature maps
+    in ``cache``; the other two pick theirs up.  Separate nodes mean each discriminator's parameter gradients exist as soon
+    as ITS backward is done, so the data-parallel wrapper (distributed.py) all-reduces them while the other scales'
+    backward is still running.
+    Inputs: scale index, cache dict, stacked audio [2B,1,L], then 7 x (weight_v, weight_g, bias) of that discriminator;
+    outputs: its 7 feature maps."""
 
     @staticmethod
-    def forward(ctx, msd, y2, *params):
-        ctx.msd = msd
-        fmaps = msd._engine_forward(y2)
-        flat = tuple(f for sc in fmaps for f in sc)
-        ctx.save_for_backward(y2, *params, *flat)
-        return flat
+    def forward(ctx, host, s, cache, y2, *params):
+        ctx.host, ctx.s = host, s
+        if "fmaps" not in cache:
+            cache["fmaps"] = host._engine_forward(y2)
+        fm = tuple(cache["fmaps"][s])
+        ctx.save_for_backward(y2, *params, *fm)
+        return fm
 
     @staticmethod
     def backward(ctx, *grads):
-        msd, dev = ctx.msd, ctx.msd._dev
+        host, s, dev = ctx.host, ctx.s, ctx.host._dev
         saved = ctx.saved_tensors
-        nsc = msd.n_scales  # 3 for MultiScaleDiscriminator, 1 for a stand-alone Discriminator
-        n = nsc * len(DISCRIMINATOR_LAYERS)
-        y2, params, fm = saved[0], saved[1:1 + 3 * n], saved[1 + 3 * n:]
-        need_y = ctx.needs_input_grad[1]
-        dws, dbs, g_in = [None] * n, [None] * n, []
-        x0, pooled = y2, [y2]
-        for s in range(nsc):
-            if s > 0:
-                x0 = msd.meanpools[s - 1](x0)
-                pooled.append(x0)
-            inputs = [x0] + list(fm[7 * s:7 * s + 6])
-            g = None
-            for l in range(6, -1, -1):
-                i = 7 * s + l
-                go = grads[i]
-                if g is None and go is None:
-                    continue
-                if l < 6:  # (g + go) * LeakyReLU'(layer output), one launch
-                    dz = dev.lrelu_backward(g, go, fm[i])
-                else:
-                    dz = (go if g is None else g if go is None else g + go).contiguous()
-                need_dx = l > 0 or need_y
-                _n, _cin, cout, _k, stride, groups, pad = DISCRIMINATOR_LAYERS[l]
-                if groups > 1:
-                    g, dws[i], dbs[i] = dev.grouped_backward(s, l, dz, inputs[l], need_dx)
-                else:
-                    w = torch._weight_norm(params[3 * i], params[3 * i + 1], 0)
-                    g, dws[i], dbs[i] = torch.ops.aten.convolution_backward(
-                        dz, inputs[l], w, [cout], [stride], [pad], [1], False, [0], 1, [need_dx, True, True])
-            g_in.append(g)
+        y2, params, fm = saved[0], saved[1:22], saved[22:]
+        need_y = ctx.needs_input_grad[3]
+        x0 = y2
+        for k in range(s):  # the scale's input: the AvgPool chain of models.py:114-117,125-127
+            x0 = host.meanpools[k](x0)
+        inputs = [x0] + list(fm[:6])
+        dws, dbs = [None] * 7, [None] * 7
+        g = None
+        for l in range(6, -1, -1):
+            go = grads[l]
+            if g is None and go is None:
+                continue
+            if l < 6:  # (g + go) * LeakyReLU'(layer output), one launch
+                dz = dev.lrelu_backward(g, go, fm[l])
+            else:
+                dz = (go if g is None else g if go is None else g + go).contiguous()
+            need_dx = l > 0 or need_y
+            _n, _cin, cout, _k, stride, groups, pad = DISCRIMINATOR_LAYERS[l]
+            if groups > 1:
+                g, dws[l], dbs[l] = dev.grouped_backward(s, l, dz, inputs[l], need_dx)
+            else:
+                w = torch._weight_norm(params[3 * l], params[3 * l + 1], 0)
+                g, dws[l], dbs[l] = torch.ops.aten.convolution_backward(
+                    dz, inputs[l], w, [cout], [stride], [pad], [1], False, [0], 1, [need_dx, True, True])
         gy = None
-        if need_y:  # AvgPool chain (models.py:114-117,125-127): linear, so its backward is differentiated on zeros
-            for s in range(nsc - 1, 0, -1):
-                if g_in[s] is None:
-                    continue
+        if need_y and g is not None:  # back through the (linear) AvgPool chain: differentiate it on zeros
+            gy = g
+            lens = [y2.shape[2], y2.shape[2] // 2 + 1]  # input lengths of pools 0, 1: AvgPool1d(4, 2, pad 2) gives L // 2 + 1
+            for k in range(s - 1, -1, -1):
                 with torch.enable_grad():
-                    a = torch.zeros_like(pooled[s - 1]).requires_grad_(True)
-                    (ga,) = torch.autograd.grad(msd.meanpools[s - 1](a), a, g_in[s])
-                g_in[s - 1] = ga if g_in[s - 1] is None else g_in[s - 1] + ga
-            gy = g_in[0]
-        dvs, dgs = dev.wn_backward([params[3 * i] for i in range(n)], [params[3 * i + 1] for i in range(n)], dws)
+                    a = torch.zeros((y2.shape[0], 1, lens[k]), dtype=y2.dtype, device=y2.device).requires_grad_(True)
+                    (gy,) = torch.autograd.grad(host.meanpools[k](a), a, gy)
+        dvs, dgs = dev.wn_backward([params[3 * l] for l in range(7)], [params[3 * l + 1] for l in range(7)], dws)
         out = []
-        for i in range(n):
-            out += [dvs[i], dgs[i], dbs[i]]
-        return (None, gy, *out)
+        for l in range(7):
+            out += [dvs[l], dgs[l], dbs[l]]
+        return (None, None, None, gy, *out)
 
 
 class MultiScaleDiscriminator(nn.Module):
     """Reference models.py:106-135: three Discriminators on y, pool(y), pool(pool(y)); returns
     (y_d_rs, y_d_gs, fmap_rs, fmap_gs).  On CUDA the whole stack runs in the hand-written kernels of
     libmelgan_b200.so with y and y_hat stacked into one batch (the reference calls each discriminator twice)."""
-
-    n_scales = 3
 
     def __init__(self):
         super().__init__()
@@ -338,11 +335,12 @@ class MultiScaleDiscriminator(nn.Module):
         vs, gs, bs = self._param_triplets()
         needs_grad = torch.is_grad_enabled() and (y2.requires_grad or any(p.requires_grad for p in vs + gs + bs))
         if needs_grad:
-            flat = []
-            for v, g, b in zip(vs, gs, bs):
-                flat += [v, g, b]
-            flat_maps = _MSDFunction.apply(self, y2, *flat)
-            fmaps = [list(flat_maps[7 * s:7 * s + 7]) for s in range(3)]
+            cache, fmaps = {}, []
+            for s in range(3):  # three autograd nodes, one fused forward launch (see _MSDFunction)
+                flat = []
+                for i in range(7 * s, 7 * s + 7):
+                    flat += [vs[i], gs[i], bs[i]]
+                fmaps.append(list(_MSDFunction.apply(self, s, cache, y2, *flat)))
         else:
             fmaps = self._engine_forward(y2)
         y_d_rs, y_d_gs, fmap_rs, fmap_gs = [], [], [], []
