@@ -213,6 +213,123 @@ def run_reference(args):
     }))
 
 
+def multi_gpu_blocks(dev, rank, world, barrier, max_over_ranks, steps=10, warmup=3):
+    """Extra keys of the JSON line when WORLD_SIZE > 1 (the headline metric is unchanged): the two paths of SURVEY 8(e)
+    that DO talk to other ranks, measured with CUDA events under barriers, max over ranks.
+      ddp_train_step   BASELINE config 4: one train.py:108-129 step (G-step + D-step, losses, backward, multi-tensor Adam) at
+                       batch 16 x 8192 samples per GPU through melgan_multi_b200.distributed over NCCL, against the same step
+                       without any communication and against the bare all-reduces of the two gradient buffers.
+      utterance_shard  BASELINE config 5 cut along TIME over the ranks (8-frame halo, no data-path collective, one
+                       all_gather of the audio) against the whole utterance on one GPU."""
+    import torch
+    import torch.distributed as dist
+    from melgan_multi_b200 import distributed as mgd
+    from melgan_multi_b200 import models, synth
+    from melgan_multi_b200.optim import Adam
+
+    def build():
+        gen = models.Generator()
+        gen.load_state_dict({k: torch.from_numpy(v) for k, v in synth.generator_state(1234).items()})
+        msd = models.MultiScaleDiscriminator()
+        msd.load_state_dict({k: torch.from_numpy(v) for k, v in synth.discriminator_state(4321).items()})
+        return gen.to(dev).train(), msd.to(dev).train()
+
+    x = torch.from_numpy(synth.mel_input(16, 32, 100 + rank)).to(dev)
+    y = torch.from_numpy(synth.audio_input(16, 8192, 200 + rank)).to(dev)
+
+    def train_step(gen, msd, g_opt, d_opt, comm):
+        g_opt.zero_grad()
+        y_ghat = gen(x)
+        dr, dg, fr, fg = msd(y, y_ghat)
+        loss_gen = models.generator_loss(dg) + models.feature_loss(fr, fg)
+        if comm:
+            mgd.reduce_tensor(loss_gen.data, world)  # train.py:113-114 (logging all-reduce; the .item() sync is left out)
+        loss_gen.backward()
+        g_opt.step()
+        d_opt.zero_grad()
+        dr, dg, _, _ = msd(y, y_ghat.detach())
+        loss_disc, _, _ = models.discriminator_loss(dr, dg)
+        if comm:
+            mgd.reduce_tensor(loss_disc.data, world)
+        loss_disc.backward()
+        d_opt.step()
+        return loss_gen, loss_disc
+
+    def timed(fn, n, w):
+        for _ in range(w):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1) / n)
+
+    out = {}
+    # -- same step, no communication (unwrapped replicas): the compute floor
+    gen0, msd0 = build()
+    g0, d0 = Adam(gen0.parameters(), 2e-4, betas=(0.5, 0.9)), Adam(msd0.parameters(), 2e-4, betas=(0.5, 0.9))
+    nocomm_ms = timed(lambda: train_step(gen0, msd0, g0, d0, False), steps, warmup)
+    del gen0, msd0, g0, d0
+    # -- data-parallel step
+    gen1, msd1 = build()
+    mgd.apply_gradient_allreduce(gen1)
+    mgd.apply_gradient_allreduce(msd1)
+    g1, d1 = Adam(gen1.parameters(), 2e-4, betas=(0.5, 0.9)), Adam(msd1.parameters(), 2e-4, betas=(0.5, 0.9))
+    ddp_ms = timed(lambda: train_step(gen1, msd1, g1, d1, True), steps, warmup)
+    sg, sd = gen1._grad_reducer.stats, msd1._grad_reducer.stats
+    passes = max(1, sg["passes"])
+    bytes_step = (sg["allreduce_bytes"] + sd["allreduce_bytes"]) / passes
+    skipped_step = sd["skipped_bytes"] / passes
+    # -- the bare collectives of one step: G's 18.1 MB buffer once, D's three per-Discriminator buckets once
+    fg_, fd_ = gen1._grad_reducer, msd1._grad_reducer
+
+    def bare():
+        ws = [dist.all_reduce(fg_.flat, async_op=True)]
+        for s_, e_, _m in fd_.buckets:
+            ws.append(dist.all_reduce(fd_.flat.narrow(0, s_, e_ - s_), async_op=True))
+        for w_ in ws:
+            w_.wait()
+    bare_ms = timed(bare, 20, 5)
+    gbytes, dbytes = fg_.flat.numel() * 4, fd_.flat.numel() * 4
+    exposed = max(0.0, ddp_ms - nocomm_ms)
+    out["ddp_train_step"] = {
+        "config": "configs[3]: DDP train step batch=16/gpu, 8192-sample segments, %d x B200, NCCL all-reduce" % world,
+        "ms": ddp_ms, "ms_same_step_without_communication": nocomm_ms, "exposed_communication_ms": exposed,
+        "allreduce_ms": bare_ms, "overlap_frac": (max(0.0, min(1.0, 1.0 - exposed / bare_ms)) if bare_ms > 0 else None),
+        "bytes": bytes_step, "bytes_reference_would_send": gbytes + 2 * dbytes, "bytes_skipped_per_step": skipped_step,
+        "segments_per_s": 16 * world / (ddp_ms * 1e-3),
+        "allreduce_busbw_gbs": 2 * (world - 1) / world * (gbytes + dbytes) / (bare_ms * 1e-3) / 1e9,
+        "buckets_bytes": {"G": [(e_ - s_) * 4 for s_, e_, _m in fg_.buckets], "D": [(e_ - s_) * 4 for s_, e_, _m in fd_.buckets]},
+        "limiting_collective": "all-reduce of the discriminators' gradients: 3 buckets of 22.6 MB (one per Discriminator, "
+                               "21 MB of each is conv_post1's 1024x1024x5 weight_v), launched as each scale's backward ends; "
+                               "the generator's 18.1 MB bucket is launched when its (single-node) backward returns",
+        "dedup": "discriminator gradients of the generator step (67.7 MB) are not reduced: learned at run time from the "
+                 "optimizer/forward order, no train.py edit",
+        "steps": steps, "warmup": warmup, "dtype": "f32 (forwards: 3-pass split-bf16 tcgen05; backward: see DESIGN.md)",
+    }
+    del gen1, msd1, g1, d1
+    # -- config 5 sharded along time
+    gen, _ = build()
+    gen.eval()
+    mel = torch.from_numpy(synth.mel_input(1, 1000, 0)).to(dev)
+    with torch.no_grad():
+        whole_ms = timed(lambda: gen(mel), 20, 5)
+        shard_ms = timed(lambda: mgd.generate_sharded(gen, mel, gather=False), 20, 5)
+        gather_ms = timed(lambda: mgd.generate_sharded(gen, mel, gather=True), 20, 5)
+    out["utterance_shard"] = {
+        "config": "configs[4]: long-utterance inference, batch=1, 80x1000 mel, cut along time over %d GPUs (8-frame halo)" % world,
+        "ms_one_gpu_whole_utterance": whole_ms, "ms_sharded": shard_ms, "ms_sharded_with_all_gather": gather_ms,
+        "speedup": whole_ms / shard_ms, "efficiency": whole_ms / shard_ms / world,
+        "collective": "none on the data path; optional all_gather of 256 000 fp32 samples",
+        "note": "one utterance is bound by the latency of a tile's six dependent convs, not by throughput: sharding time "
+                "shortens each rank's grid, not the per-tile chain",
+    }
+    return out
+
+
 _JSON_OUT = None
 
 
@@ -239,6 +356,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU-baseline timing")
+    ap.add_argument("--no-multi", action="store_true", help="skip the DDP train-step / utterance-shard blocks at N > 1")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -395,6 +513,8 @@ def main():
                          "generator_forward_reference = the reference forward (incl. per-forward weight-norm) on "
                          "PyTorch-CPU/oneDNN, all threads" % (len(times), med)}
 
+    multi = multi_gpu_blocks(dev, rank, world, barrier, max_over_ranks) if world > 1 and not args.no_multi else None
+
     if rank == 0:
         emit(({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -410,6 +530,7 @@ def main():
                     "api": "mg_gen_engine_forward (host buffers, pinned)", "output_abs_sum": checksum},
             "gpu_launches": K * world * engine.lib().mg_gen_forward_launches() * engine.lib().mg_gen_forward_slices(B, T),
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            **({"multi_gpu": multi} if multi else {}),
         }))
     if world > 1:
         dist.destroy_process_group()

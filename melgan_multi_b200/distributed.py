@@ -84,7 +84,7 @@ class _GradReducer:
         self.history = {}            # pass key -> "consumed" | "discarded"
         self.unconsumed_key = None   # key of the last backward whose gradients nobody has consumed or dropped yet
         self.pending = False         # ... and those gradients are still local (lazy mode): reduce them if consumed
-        self.in_pass = False
+        self.state = 0               # 0: no backward pass in flight, 1: eager pass, 2: lazy pass
         self.skip_once = False
         if not self.params:
             self.flat = None
@@ -109,12 +109,12 @@ class _GradReducer:
             b_members.append(i)
             off += p.numel()
         self.buckets.append((b_start, off, b_members))
+        self.bucket_len = [len(m) for _, _, m in self.buckets]
         self._reset_pass()
 
     def _reset_pass(self):
         nb = len(self.buckets)
         self.ready, self.launched = [0] * nb, [False] * nb
-        self.foreign = [([], []) for _ in range(nb)]
         self.works = []
 
     # -- forward / backward events ------------------------------------------------------------------------------------
@@ -132,58 +132,71 @@ class _GradReducer:
             _PASS["key"] = frozenset(_FORWARD_SET)
             Variable._execution_engine.queue_callback(_end_pass)
         self.key = _PASS["key"]
-        self.in_pass = True
         self.stats["passes"] += 1
         self._reset_pass()
-        self.lazy = self.skip_once or (self.dedup and self.history.get(self.key) == "discarded")
+        lazy = self.skip_once or (self.dedup and self.history.get(self.key) == "discarded")
+        self.state = 2 if lazy else 1
         Variable._execution_engine.queue_callback(self._finish_pass)
 
     def on_grad(self, i):
-        """post-accumulate-grad hook of parameter i: adopt the gradient into the flat buffer; launch a full bucket."""
-        if not self.module.needs_reduction:
-            return  # (reference: nothing is reduced unless the module ran forward since the last reduction)
-        if not self.in_pass:
+        """post-accumulate-grad hook of parameter i (runs ~150 times per backward on a host-bound training step: keep it
+        to a few bytecodes).  state 0: no pass in flight, 1: eager pass (count, launch full buckets), 2: lazy pass."""
+        st = self.state
+        if st == 2:
+            return
+        if st == 0:
+            if not self.module.needs_reduction:
+                return  # (reference: nothing is reduced unless the module ran forward since the last reduction)
             self._begin_pass()
-        p, v, b = self.params[i], self.views[i], self.bucket_of[i]
-        g = p.grad
-        if g is not None and g.data_ptr() != v.data_ptr():
-            self.foreign[b][0].append(v)
-            self.foreign[b][1].append(g.detach())
-            p.grad = v
-        self.ready[b] += 1
-        if self.ready[b] == len(self.buckets[b][2]):
+            if self.state == 2:
+                return
+        b = self.bucket_of[i]
+        n = self.ready[b] + 1
+        self.ready[b] = n
+        if n == self.bucket_len[b]:
             self._launch(b)
+
+    def _adopt(self, members):
+        """Make the gradients of parameters `members` views of the flat buffer (one multi-tensor copy for those autograd
+        allocated elsewhere: zero_grad(set_to_none=True) makes that all of them, every step)."""
+        dsts, srcs = [], []
+        for i in members:
+            p, v = self.params[i], self.views[i]
+            g = p.grad
+            if g is not None and g.data_ptr() != v.data_ptr():
+                dsts.append(v)
+                srcs.append(g.detach())
+                p.grad = v
+        if dsts:
+            torch._foreach_copy_(dsts, srcs)
 
     def _launch(self, b):
         if self.launched[b]:
             return
         self.launched[b] = True
-        dsts, srcs = self.foreign[b]
-        if dsts:
-            torch._foreach_copy_(dsts, srcs)  # one multi-tensor copy per bucket
-        if not self.lazy:
-            start, end, _ = self.buckets[b]
-            chunk = self.flat.narrow(0, start, end - start)
-            self.works.append(dist.all_reduce(chunk, async_op=True))
-            self.stats["allreduce_calls"] += 1
-            self.stats["allreduce_bytes"] += chunk.numel() * chunk.element_size()
+        start, end, members = self.buckets[b]
+        self._adopt(members)
+        chunk = self.flat.narrow(0, start, end - start)
+        self.works.append(dist.all_reduce(chunk, async_op=True))
+        self.stats["allreduce_calls"] += 1
+        self.stats["allreduce_bytes"] += chunk.numel() * chunk.element_size()
 
     def _finish_pass(self):
         """End-of-backward callback (the reference does ALL its work here, distributed.py:105-129): buckets whose
         parameters did not all receive a gradient are launched now, then the in-flight all-reduces are awaited."""
-        if not self.in_pass:
+        st, self.state = self.state, 0
+        if st == 0:
             return
-        self.in_pass = False
         self.module.needs_reduction = False
-        for b in range(len(self.buckets)):
-            self._launch(b)
-        if self.lazy:
+        if st == 2:  # gradients stay where autograd put them, un-reduced
             if self.skip_once:  # skip_next_reduction(): the caller promised to throw these gradients away
                 self.skip_once = False
                 self.unconsumed_key, self.pending = None, False
-                return
-            self.unconsumed_key, self.pending = self.key, True
+            else:
+                self.unconsumed_key, self.pending = self.key, True
             return
+        for b in range(len(self.buckets)):
+            self._launch(b)
         for w in self.works:
             w.wait()
         self.works = []
@@ -195,6 +208,7 @@ class _GradReducer:
         if self.unconsumed_key is None:
             return
         if self.pending:  # predicted "discarded", but they are wanted after all: reduce now (blocking, exact)
+            self._adopt(range(len(self.params)))
             dist.all_reduce(self.flat)
             self.flat.div_(self.world)
             self.stats["lazy_flushes"] += 1
@@ -234,8 +248,9 @@ def apply_gradient_allreduce(module):
         from torch.optim.optimizer import register_optimizer_step_pre_hook
         _OPT_HOOK["handle"] = register_optimizer_step_pre_hook(_optimizer_pre_step)
 
+    on_grad = red.on_grad
     for i, p in enumerate(red.params):
-        p.register_post_accumulate_grad_hook(lambda _p, i=i: red.on_grad(i))
+        p.register_post_accumulate_grad_hook(lambda _p, i=i, f=on_grad: f(i))
 
     module.register_forward_hook(lambda mod, inputs, output: red.on_forward())
     return module
