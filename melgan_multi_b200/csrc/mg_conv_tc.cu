@@ -140,6 +140,7 @@ conv_rows_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const ui
         // Thread tid owns row tid of every slot and keeps the NEXT chunk's KCA loads in flight while it converts the
         // current one (the chain of dependent memory round trips, not the MMAs, bounds a CTA: 32 chunks at K = 1024);
         // the 2 PAD rows beyond the first NCONV are picked up by the first threads without prefetch.
+        pdl_wait();  // x: the previous kernel's output
         int sa = 0, pha = 0;
         bool ok = true;
         constexpr int NCH = CIN / KCA;
@@ -197,6 +198,7 @@ conv_rows_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const ui
         // ================= epilogue: D[v, co] + bias (-> LeakyReLU) -> y[item][co][s] =================
         if (ok && !mbar_wait(done, 0)) { ok = false; if (lane == 0) atomicExch(status, 25); }
         tc_fence_after();
+        pdl_trigger();  // MMAs done, only the output store is left: the next kernel of the chain may be scheduled
         const int q = warp & 3;
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
         const int v = r0 + q * 32 + lane;
@@ -236,19 +238,8 @@ static int launch_conv_rows(const float *x, float *y, const uint8_t *wtc, const 
     const long long vrows = (long long)B * (L + Cfg::PAD);
     unsigned tiles = (unsigned)((vrows + Cfg::ROWS - 1) / Cfg::ROWS);
     tiles = (tiles + Cfg::CL - 1) / Cfg::CL * Cfg::CL;  // whole clusters (a tile past the last row converts zeros and stores nothing)
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(tiles, Cfg::NCG);
-    cfg.blockDim = dim3(Cfg::NT);
-    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = Cfg::CL;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = Cfg::CL > 1 ? 1 : 0;
-    MG_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_rows_tc_kernel<Cfg>, x, y, wtc, bias, L, B, status));
+    MG_CUDA_TRY(launch_ex(conv_rows_tc_kernel<Cfg>, dim3(tiles, Cfg::NCG), dim3(Cfg::NT), Cfg::SMEM_BYTES, s, Cfg::CL, true, x, y, wtc,
+                          bias, L, B, status));
     return MG_OK;
 }
 

@@ -20,6 +20,8 @@
 //
 // Warp roles: NEPI/32 epilogue warps (TMEM -> registers -> bias/LeakyReLU/mask/split -> X), one TMA producer
 // warp, NIW MMA issuer warps (each runs its loop warp-uniform and one elected lane issues tcgen05.mma for its blocks).
+#include <stdlib.h>
+
 #include "mg_common.cuh"
 #include "mg_tc.cuh"
 
@@ -37,8 +39,16 @@ using namespace tc;
 // row offsets 1, 0, 2, 1 -- the even outputs accumulate in the D1 columns of output block 2cb, the odd ones in those of
 // block 2cb + 1.  The pairs are then de-interleaved through shared memory (fp32, in the X region that is not in use
 // yet) so that lane = output position can fill R, and from there on the kernel is the plain ResBlock.
-template <int C_, int NBLK_, int NSTAGE_, int NWG_, int MINB_, bool POST_ = false, bool UPF_ = false>
+// CL = 2 (C = 256): two CTAs of a thread-block cluster own the two halves of ONE 2P-position super-tile.  After every conv
+// each CTA pushes its 16 boundary rows of X into the slack rows of its peer's X buffer through distributed shared memory,
+// so the 16-row halo is only recomputed at the super-tile's outer edges (a stage-0 tile is one 128-row block: alone it would
+// spend 32 of its 128 rows on halo, and at T = 32 an item of 256 positions would need three tiles = 1.5x over-compute; as a
+// pair it is ONE super-tile without any halo, 128 CTAs = one wave).  The pair runs in lock step -- `done` counts the MMA
+// commits of BOTH CTAs, so nobody overwrites rows a peer's MMAs may still read -- and streams the same weights: the leader's
+// bulk copies are multicast into both rings, the ring slots freed by multicast commits.
+template <int C_, int NBLK_, int NSTAGE_, int NWG_, int MINB_, bool POST_ = false, bool UPF_ = false, int CL_ = 1>
 struct RbCfg {
+    static constexpr int CL = CL_;
     static constexpr bool UPF = UPF_;
     static constexpr int C = C_;
     static constexpr int NBLK = NBLK_, MINB = MINB_;
@@ -73,6 +83,9 @@ struct RbCfg {
     // (measured: -5 % per conv at C = 128; at C = 256 the early MMAs and the epilogue's stores fight for shared-memory
     //  bandwidth and it is a wash, so that stage keeps the single hand-off)
     static constexpr int NH = (C == 128) ? 2 : 1;
+    static constexpr int BND = SLACK;  // boundary rows pushed to the peer CTA (CL = 2); the widest tap reaches 9
+    static constexpr int XARRIVE = NEPI + (CL > 1 ? BND * PARTS : 0);  // xready arrivals: local epilogue threads + the peer's boundary threads
+    static_assert(CL == 1 || (CL == 2 && !UPF_ && !POST_), "CTA pairs: plain ResBlock only");
     static constexpr int SMEM_BYTES = 2 * XBYTES + NSTAGE * CHUNK + 2 * C * 4 + (2 * NSTAGE + 1 + NH) * 8 + 16;
     static_assert(KSL % NH == 0 && (CW / NH) % 32 == 0 && (NH == 1 || ITEMS == NWG), "hand-off split");
     // fused ConvT: input rows s = o/2 - 1 .. o/2 + P/2 of 2C channels (2 KP k-panels), NCB blocks of 128 output pairs
@@ -102,6 +115,28 @@ __device__ __forceinline__ void store_x16(uint8_t *Xh, uint8_t *Xl, int xpitch, 
     *reinterpret_cast<uint4 *>(pl) = make_uint4(l[0], l[1], l[2], l[3]);
     *reinterpret_cast<uint4 *>(pl + xpitch) = make_uint4(l[4], l[5], l[6], l[7]);
 }
+// the same, plus (push: this row is one of the CTA's boundary rows) a copy into the peer CTA's X buffer at row offset
+// peer_row_bytes; rxh / rxl: cluster addresses of the peer's Xh / Xl
+__device__ __forceinline__ void store_x16_push(uint8_t *Xh, uint8_t *Xl, int xpitch, int c0, int xrow_bytes, const float *f,
+                                               bool push, uint32_t rxh, uint32_t rxl, int peer_row_bytes) {
+    uint32_t h[8], l[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) split2_bf16(f[2 * e], f[2 * e + 1], h[e], l[e]);
+    const int poff = (c0 >> 3) * xpitch;
+    uint8_t *ph = Xh + poff + xrow_bytes;
+    uint8_t *pl = Xl + poff + xrow_bytes;
+    *reinterpret_cast<uint4 *>(ph) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4 *>(ph + xpitch) = make_uint4(h[4], h[5], h[6], h[7]);
+    *reinterpret_cast<uint4 *>(pl) = make_uint4(l[0], l[1], l[2], l[3]);
+    *reinterpret_cast<uint4 *>(pl + xpitch) = make_uint4(l[4], l[5], l[6], l[7]);
+    if (push) {
+        const uint32_t o = (uint32_t)(poff + peer_row_bytes);
+        st_cluster_v4(rxh + o, make_uint4(h[0], h[1], h[2], h[3]));
+        st_cluster_v4(rxh + o + xpitch, make_uint4(h[4], h[5], h[6], h[7]));
+        st_cluster_v4(rxl + o, make_uint4(l[0], l[1], l[2], l[3]));
+        st_cluster_v4(rxl + o + xpitch, make_uint4(l[4], l[5], l[6], l[7]));
+    }
+}
 
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB)
@@ -125,10 +160,20 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
     // Edge-aware tiling: a halo is only needed where the tile borders MORE sequence.  Tile 0 starts at position 0 (its
     // left edge is the real zero padding) and keeps P - HALO outputs; later tiles keep P - 2*HALO, and a tile that reaches
     // the end of the sequence keeps its right HALO rows too.  (L = 2048, P = 256: 9 tiles instead of 10.)
-    const int o = blockIdx.x == 0 ? 0 : (P - HALO) + ((int)blockIdx.x - 1) * Cfg::PVALID - HALO;  // position of tile-local p = 0
-    const int p_lo = blockIdx.x == 0 ? 0 : HALO;
-    const int p_hi = (o + P >= L) ? P : P - HALO;  // first tile-local row that is NOT a valid output
+    // CL > 1: all of this at super-tile granularity (PS = CL * P rows), CTA `rank` of the cluster owning rows [rank * P, + P).
+    constexpr int CL = Cfg::CL, PS = CL * P, PVS = PS - 2 * HALO;
+    const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
+    const int stile = (int)blockIdx.x / CL;
+    const int os = stile == 0 ? 0 : (PS - HALO) + (stile - 1) * PVS - HALO;  // position of super-tile row 0
+    const int o = os + rank * P;                                              // position of tile-local p = 0
+    const int s_lo = stile == 0 ? 0 : HALO;
+    const int s_hi = (os + PS >= L) ? PS : PS - HALO;  // first super-tile row that is NOT a valid output
+    const int p_lo = min(max(s_lo - rank * P, 0), P), p_hi = min(max(s_hi - rank * P, 0), P);
     const bool interior = (o >= 0 && o + P <= L);  // every row of the tile is a real position
+    // CTA pair: my boundary rows (rank 0: the last BND rows, rank 1: the first BND) mirror into the peer's slack rows
+    const uint32_t peer = (uint32_t)(rank ^ 1);
+    const uint32_t rxh = CL > 1 ? mapa_shared(smem_u32(smem), peer) : 0u, rxl = rxh + XBYTES;
+    uint32_t rxready[Cfg::NH];
     // consumption order of the six convs of ResBlock `stage`: c1[0], c2[0], c1[1], c2[1], c1[2], c2[2]
     const int l0 = 5 + 6 * stage;
     const uint8_t *tc_base = reinterpret_cast<const uint8_t *>(packed) + tc_region_start();
@@ -137,22 +182,26 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
     if (tid == 32) {
         for (int s = 0; s < NSTAGE; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], NIW);  // every issuer warp commits its own arrival
+            mbar_init(&empty[s], NIW * CL);  // every issuer warp (of every CTA of the pair) commits its own arrival
         }
-        mbar_init(done, NIW);
-        for (int h = 0; h < Cfg::NH; ++h) mbar_init(&xready[h], NEPI);
+        mbar_init(done, NIW * CL);
+        for (int h = 0; h < Cfg::NH; ++h) mbar_init(&xready[h], Cfg::XARRIVE);
         fence_mbar_init();
     }
+    for (int h = 0; h < Cfg::NH; ++h) rxready[h] = CL > 1 ? mapa_shared(smem_u32(&xready[h]), peer) : 0u;
     // (fused ConvT: the X region first holds the ConvT operand and the staging buffer; its slack rows are zeroed later)
     for (int i = Cfg::UPF ? 1 << 30 : tid; i < 2 * Cfg::KP * 2 * SLACK; i += Cfg::NT) {  // zero the slack rows of Xh and Xl
         const int r = i % (2 * SLACK), kp = (i / (2 * SLACK)) % Cfg::KP, hl = i / (2 * SLACK * Cfg::KP);
         const int row = r < SLACK ? r : P + r;  // r in [SLACK, 2*SLACK) -> rows P+SLACK .. P+2*SLACK-1
-        *reinterpret_cast<uint4 *>((hl ? Xl : Xh) + kp * XPITCH + row * 16) = make_uint4(0, 0, 0, 0);
+        // (pair: the slack rows facing the peer are ITS boundary rows, written by it before every conv -- not zeroed here)
+        if (CL == 1 || (r < SLACK ? rank == 0 : rank == CL - 1))
+            *reinterpret_cast<uint4 *>((hl ? Xl : Xh) + kp * XPITCH + row * 16) = make_uint4(0, 0, 0, 0);
     }
     for (int i = tid; i < C; i += Cfg::NT) pend[i] = 0.f;
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
+    if constexpr (CL > 1) cluster_sync();  // the peer's barriers exist before a copy, commit or arrival of mine can land on them
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     // optional timeline of one interior CTA (clock64 stamps; see mg_gen_resblock_trace)
@@ -182,9 +231,14 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
                     constexpr int KH = Cfg::KSL / Cfg::NH;
                     const int h = i / (3 * KH), tap = (i / KH) % 3, ks = h * KH + i % KH;
                     const int ch = tap * Cfg::KSL + ks;
-                    if (!mbar_wait(&empty[s], ph ^ 1)) { ok = false; break; }
+                    if (!mbar_wait(&empty[s], ph ^ 1)) { ok = false; break; }  // (pair: free in BOTH CTAs, see the commits)
                     mbar_arrive_expect_tx(&full[s], CHUNK);
-                    bulk_g2s(ring + s * CHUNK, src + (size_t)ch * CHUNK, CHUNK, &full[s]);
+                    if constexpr (CL > 1) {  // every CTA arms its own barrier; the leader's copy lands in both rings
+                        if (rank == 0)
+                            bulk_g2s_multicast(ring + s * CHUNK, src + (size_t)ch * CHUNK, CHUNK, &full[s], (uint16_t)((1u << CL) - 1));
+                    } else {
+                        bulk_g2s(ring + s * CHUNK, src + (size_t)ch * CHUNK, CHUNK, &full[s]);
+                    }
                     if (++s == NSTAGE) { s = 0; ph ^= 1; }
                 }
             }
@@ -249,7 +303,7 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
                 constexpr int KH = Cfg::KSL / Cfg::NH;
                 const int h = ch / (3 * KH), tap = (ch / KH) % 3, ks = h * KH + ch % KH;
                 if (ch % (3 * KH) == 0) {  // first chunk of channel half h: wait until the epilogue has written those channels of X
-                    ok &= mbar_wait(&xready[h], (conv + PH0) & 1);
+                    ok &= CL > 1 ? mbar_wait_cluster(&xready[h], (conv + PH0) & 1) : mbar_wait(&xready[h], (conv + PH0) & 1);
                     tc_fence_after();
                     if (ch == 0 && iw == 0) MG_TR(64 + 3 * conv);
                 }
@@ -274,10 +328,16 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
                         }
                     }
                 }
-                if (elect_one()) mma_commit(&empty[s]);  // ring slot free once these MMAs have read it
+                if (elect_one()) {  // ring slot free once these MMAs have read it
+                    if constexpr (CL > 1) mma_commit_multicast(&empty[s], (uint16_t)((1u << CL) - 1));
+                    else mma_commit(&empty[s]);
+                }
                 if (++s == NSTAGE) { s = 0; ph ^= 1; }
             }
-            if (elect_one()) mma_commit(done);
+            if (elect_one()) {
+                if constexpr (CL > 1) mma_commit_multicast(done, (uint16_t)((1u << CL) - 1));  // the peer's epilogue may write my slack rows
+                else mma_commit(done);
+            }
             if (iw == 0) MG_TR(66 + 3 * conv);
             if (!ok && lane == 0) atomicExch(status, 3);
             __syncwarp();
@@ -288,6 +348,7 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
         const int row = q * 32 + lane;
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
 
+        pdl_wait();  // x is the previous kernel's output (and y may still be read by it): every global access of this kernel is below
         if (warp == 0) MG_TR(0);
         constexpr int NH = Cfg::NH, CH = CW / NH;
         if constexpr (Cfg::UPF) {
@@ -436,11 +497,15 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
         } else {
         // ---- load the input tile: R <- x (fp32, exact), X <- split(lrelu(x))
         // an item (blk, part) owns, in every channel half h, the CH = CW/NH columns  h*C/NH + part*CH .. + CH
+        int nb0 = 0;  // boundary items this thread pushed to the peer (CL = 2)
 #pragma unroll 1
         for (int it = wg; it < ITEMS; it += NWG) {
             const int blk = it / PARTS, part = it % PARTS;
             const int p = blk * 128 + row, t = o + p;
             const bool inr = (t >= 0 && t < L);
+            const bool push = CL > 1 && (rank == 0 ? p >= P - Cfg::BND : p < Cfg::BND);
+            const int prow = (rank == 0 ? p - (P - Cfg::BND) : SLACK + P + p) * 16;  // row offset in the peer's X buffer
+            nb0 += push;
             const float *xp = x + (size_t)b * C * L + (inr ? t : 0);
             // all CW loads of the item are issued before the first use: one memory round trip, not CW/16
             uint32_t v[CW];
@@ -460,13 +525,17 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
                     f[j] = lrelu(__uint_as_float(v[c0 + j]));
                 }
                 tmem_st16(lane_addr + blk * 2 * C + col0, w);
-                store_x16(Xh, Xl, XPITCH, col0, (p + SLACK) * 16, f);
+                if constexpr (CL > 1) store_x16_push(Xh, Xl, XPITCH, col0, (p + SLACK) * 16, f, push, rxh, rxl, prow);
+                else store_x16(Xh, Xl, XPITCH, col0, (p + SLACK) * 16, f);
             }
         }
         tmem_st_wait();
-        fence_proxy_async();
+        if constexpr (CL > 1) fence_proxy_async_all(); else fence_proxy_async();
         tc_fence_before();
-        for (int h = 0; h < NH; ++h) mbar_arrive(&xready[h]);  // conv 0 may start (phase 0 of both halves)
+        for (int h = 0; h < NH; ++h) {  // conv 0 may start (phase 0 of both halves)
+            mbar_arrive(&xready[h]);
+            for (int k = 0; k < nb0; ++k) mbar_arrive_cluster(rxready[h]);
+        }
         }
         if (warp == 0) MG_TR(1);
 
@@ -487,16 +556,26 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
             if (ok && !mbar_wait(done, (conv + (Cfg::UPF ? 1 : 0)) & 1)) { ok = false; if (lane == 0) atomicExch(status, 4); }
             tc_fence_after();
             if (warp == 0) MG_TR(3 + 3 * conv);
-            if (conv == 5) break;
+            if (conv == 5) {
+                // all MMAs of this tile are done: the next kernel of the chain may be scheduled (its CTAs set up and prefetch
+                // weights on SMs this grid has already vacated, then sit in pdl_wait() until this grid has completed).
+                // Late on purpose: an early trigger parks waiting CTAs on SMs that other streams' kernels could be using.
+                pdl_trigger();
+                break;
+            }
             const uint32_t scol = (conv & 1) ? 0 : C;  // next input comes from R (after c2) or D1 (after c1)
             const float *bsrc = (conv & 1) ? pend : b1s;
 #pragma unroll 1
             for (int h = 0; h < NH; ++h) {
+                int nb = 0;
 #pragma unroll 1
                 for (int it = wg; it < ITEMS; it += NWG) {
                     const int blk = it / PARTS, cbeg = h * (C / NH) + (it % PARTS) * CH;
                     const int p = blk * 128 + row, t = o + p;
                     const bool inr = (t >= 0 && t < L);
+                    const bool push = CL > 1 && (rank == 0 ? p >= P - Cfg::BND : p < Cfg::BND);
+                    const int prow = (rank == 0 ? p - (P - Cfg::BND) : SLACK + P + p) * 16;
+                    nb += push;
 #pragma unroll 1
                     for (int c0 = cbeg; c0 < cbeg + CH; c0 += 32) {
                         uint32_t v[32];
@@ -510,14 +589,20 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
 #pragma unroll
                             for (int j = 0; j < 32; ++j) f[j] = inr ? lrelu(__uint_as_float(v[j]) + bsrc[c0 + j]) : 0.f;
                         }
-                        store_x16(Xh, Xl, XPITCH, c0, (p + SLACK) * 16, f);
-                        store_x16(Xh, Xl, XPITCH, c0 + 16, (p + SLACK) * 16, f + 16);
+                        if constexpr (CL > 1) {
+                            store_x16_push(Xh, Xl, XPITCH, c0, (p + SLACK) * 16, f, push, rxh, rxl, prow);
+                            store_x16_push(Xh, Xl, XPITCH, c0 + 16, (p + SLACK) * 16, f + 16, push, rxh, rxl, prow);
+                        } else {
+                            store_x16(Xh, Xl, XPITCH, c0, (p + SLACK) * 16, f);
+                            store_x16(Xh, Xl, XPITCH, c0 + 16, (p + SLACK) * 16, f + 16);
+                        }
                     }
                 }
                 // channels [h*C/NH, (h+1)*C/NH) of the next conv's input are in place: let its MMAs start on them
-                fence_proxy_async();
+                if constexpr (CL > 1) fence_proxy_async_all(); else fence_proxy_async();
                 tc_fence_before();
                 mbar_arrive(&xready[h]);
+                for (int k = 0; k < nb; ++k) mbar_arrive_cluster(rxready[h]);  // my boundary rows are in the peer's slack rows
             }
             if (warp == 0) MG_TR(4 + 3 * conv);
         }
@@ -593,6 +678,7 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, Cfg::TCOLS);
+    if constexpr (CL > 1) cluster_sync();  // nobody leaves while the peer may still multicast into its ring or arrive on its barriers
 }
 
 template <class Cfg>
@@ -603,10 +689,10 @@ static int launch_resblock(const float *x, float *y, const float *packed, int st
         MG_CUDA_TRY(cudaFuncSetAttribute(resblock_tc_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         configured = true;
     }
-    const int ntiles = 1 + (L > Cfg::P ? (L - Cfg::P + Cfg::PVALID - 1) / Cfg::PVALID : 0);  // edge-aware tiling, see the kernel
-    dim3 grid(ntiles, B);
-    resblock_tc_kernel<Cfg><<<grid, Cfg::NT, Cfg::SMEM_BYTES, s>>>(x, y, packed, stage, L, status, trace);
-    MG_CUDA_TRY(cudaGetLastError());
+    constexpr int PS = Cfg::CL * Cfg::P, PVS = PS - 2 * Cfg::HALO;  // edge-aware tiling in super-tiles of CL tiles, see the kernel
+    const int ntiles = 1 + (L > PS ? (L - PS + PVS - 1) / PVS : 0);
+    MG_CUDA_TRY(launch_ex(resblock_tc_kernel<Cfg>, dim3(ntiles * Cfg::CL, B), dim3(Cfg::NT), Cfg::SMEM_BYTES, s, Cfg::CL, true, x, y,
+                          packed, stage, L, status, trace));
     return MG_OK;
 }
 
@@ -618,7 +704,12 @@ int launch_resblock_tc(const float *x, float *y, const float *packed, int stage,
         // (C = 256 is paced by its 4-slot weight ring -- 3 slots: 204 us, 4: 184 us -- but a fifth 16 KB slot only fits if the
         //  bias staging goes: reading the biases from global memory in the epilogue instead cost far more (264 us; at 231 KB of
         //  shared memory there is no L1 left for them))
-        case 0: return launch_resblock<RbCfg<256, 1, 4, 4, 1>>(x, y, packed, stage, B, L, status, trace, s);
+        // L > 128: CTA pairs sharing a 256-position super-tile (no halo between the two; multicast weights).  MG_RES0_PAIR=0: A/B.
+        case 0: {
+            static const bool pair = [] { const char *e = getenv("MG_RES0_PAIR"); return !(e && e[0] == '0'); }();
+            if (pair && L > 128) return launch_resblock<RbCfg<256, 1, 4, 4, 1, false, false, 2>>(x, y, packed, stage, B, L, status, trace, s);
+            return launch_resblock<RbCfg<256, 1, 4, 4, 1>>(x, y, packed, stage, B, L, status, trace, s);
+        }
         // (C = 128 as two single-block CTAs per SM, RbCfg<128, 1, 2, 2, 2>: measured 244 us vs 213 us at config 2 -- the
         //  25 % halo recompute and the two-slot weight rings cost more than the overlap buys)
         case 1: return launch_resblock<RbCfg<128, 2, 4, 4, 1>>(x, y, packed, stage, B, L, status, trace, s);

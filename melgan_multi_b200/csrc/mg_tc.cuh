@@ -71,8 +71,50 @@ __device__ __forceinline__ void bulk_g2s_multicast(void *smem_dst, const void *g
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
                  : "memory");
 }
+// ---- distributed shared memory (CTA pairs that exchange tile-boundary rows, mg_res_tc.cu) ------------------------------------
+// address of the same shared-memory offset in CTA `cta_rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t local_addr, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, uint4 v) {
+    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// arrive on an mbarrier of another CTA of the cluster; release at cluster scope: this thread's earlier writes (to that CTA's
+// shared memory) are visible to whoever observes the arrival with an acquire.cluster wait
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ bool mbar_wait_cluster(uint64_t *bar, uint32_t parity, uint32_t max_spins = 1u << 24) {
+    for (uint32_t i = 0; i < max_spins; ++i)
+        if (mbar_try_wait_cluster(bar, parity)) return true;
+    return false;
+}
+// generic-proxy writes -> async proxy, every state space (used after stores into a PEER CTA's shared memory)
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 // generic-proxy writes (st.shared) -> visible to the async proxy (UMMA operand reads, bulk copies)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- programmatic dependent launch (PDL): the generator chain's kernels are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so kernel N+1's CTAs may start -- barrier init, TMEM allocation, the
+// weight stream of its first ring slots: everything that does not touch kernel N's output -- while kernel N's last wave is
+// still running.  pdl_trigger(): "my dependents may be scheduled" (they still wait for this whole grid's completion and
+// memory flush in pdl_wait()); pdl_wait(): executed by every thread that reads or writes activations, before it does.
+// Both are no-ops in a launch without the attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---- TMEM ------------------------------------------------------------------------------------
 // One full warp executes these.  ncols: power of two in [32, 512].

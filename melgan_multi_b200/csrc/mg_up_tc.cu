@@ -145,6 +145,7 @@ convt_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const float 
         if (!ok && lane == 0) atomicExch(status, 13);
     } else {
         // ================= converter warps: A slots = split(lrelu(x)), KCA channels of every row =================
+        pdl_wait();  // x: the previous kernel's output
         int sa = 0, pha = 0;
         bool ok = true;
 #pragma unroll 1
@@ -176,6 +177,7 @@ convt_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const float 
         // ================= epilogue: D[s, phi*NG + co] + bias -> out[co][S*s + phi - pad] =================
         if (ok && !mbar_wait(done, 0)) { ok = false; if (lane == 0) atomicExch(status, 15); }
         tc_fence_after();
+        pdl_trigger();  // MMAs done, only the output store is left: the next kernel of the chain may be scheduled
         const int wg = warp >> 2, q = warp & 3;
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
         const float *bias = packed + bias_offset(1 + Cfg::STAGE) + cg * NG;
@@ -238,8 +240,7 @@ static int launch_convt(const float *x, float *y, const float *packed, int B, in
     }
     const long long vrows = (long long)B * (Lin + 1);  // Lin + 1 rows per item: position s = Lin feeds the last `pad` outputs
     dim3 grid((unsigned)((vrows + Cfg::ROWS - 1) / Cfg::ROWS), Cfg::NCG);
-    convt_tc_kernel<Cfg><<<grid, Cfg::NT, Cfg::SMEM_BYTES, s>>>(x, y, packed, Lin, B, status);
-    MG_CUDA_TRY(cudaGetLastError());
+    MG_CUDA_TRY(launch_ex(convt_tc_kernel<Cfg>, grid, dim3(Cfg::NT), Cfg::SMEM_BYTES, s, 1, true, x, y, packed, Lin, B, status));
     return MG_OK;
 }
 
@@ -335,6 +336,7 @@ convt_resident_tc_kernel(const float *__restrict__ x, float *__restrict__ y, con
         if (!ok && lane == 0) atomicExch(status, 33);
     } else if (warp < NCONV / 32) {
         // ================= converter: the whole A tile, once =================
+        pdl_wait();  // x: the previous kernel's output
 #pragma unroll 1
         for (int ca = 0; ca < CIN / 64; ++ca) {
 #pragma unroll 1
@@ -372,6 +374,7 @@ convt_resident_tc_kernel(const float *__restrict__ x, float *__restrict__ y, con
             const int buf = cg & 1, use = cg >> 1;
             if (ok && !mbar_wait(&done[buf], use & 1)) { ok = false; if (lane == 0) atomicExch(status, 35); }
             tc_fence_after();
+            if (cg == NCG - 1) pdl_trigger();  // last channel group's MMAs done: the next kernel may be scheduled
             const float *bias = packed + bias_offset(1 + Cfg::STAGE) + cg * NG;
             float *yb = y + ((size_t)(row_ok ? item : 0) * COUT + cg * NG) * Lout;
 #pragma unroll 1
@@ -410,8 +413,8 @@ static int launch_convt_resident(const float *x, float *y, const float *packed, 
         configured = true;
     }
     const long long vrows = (long long)B * (Lin + 1);
-    convt_resident_tc_kernel<Cfg><<<(unsigned)((vrows + 127) / 128), 192, smem, s>>>(x, y, packed, Lin, B, status);
-    MG_CUDA_TRY(cudaGetLastError());
+    MG_CUDA_TRY(launch_ex(convt_resident_tc_kernel<Cfg>, dim3((unsigned)((vrows + 127) / 128)), dim3(192), smem, s, 1, true, x, y,
+                          packed, Lin, B, status));
     return MG_OK;
 }
 

@@ -43,7 +43,12 @@ def oracle_resblock(state, stage, x):
 
 
 @pytest.mark.parametrize("stage,B,L", [(3, 2, 2100), (2, 2, 1000), (1, 2, 500), (0, 2, 200), (3, 1, 5), (0, 1, 8),
-                                       (1, 1, 224), (1, 1, 225)])
+                                       (1, 1, 224), (1, 1, 225),
+                                       # stage 0 above 128 positions runs as CTA pairs (256-position super-tiles, boundary rows
+                                       # exchanged through distributed shared memory): one super-tile with a partly / fully
+                                       # empty second CTA, exactly one, the tile borders of several, odd tails
+                                       (0, 1, 129), (0, 2, 144), (0, 3, 256), (0, 1, 257), (0, 2, 480), (0, 1, 481), (0, 2, 1000),
+                                       (0, 1, 128), (0, 64, 256)])
 def test_resblock_tc_matches_oracle(state, dev, stage, B, L):
     C = 256 >> stage
     rs = np.random.RandomState(stage * 100 + L)
