@@ -444,10 +444,13 @@ def main():
         flops_of["stage%d(up+res)" % i] = up_f[i] + res_f[i]
     flops_of["stage3(up+res+post)"] = up_f[3] + res_f[3] + post_f * frames
     flops_of["res3+post"] = res_f[3] + post_f * frames
-    flops_of["up2+res2"] = up_f[2] + res_f[2]  # stride-2 ConvT fused into the stage kernel
+    flops_of["up2+res2"] = up_f[2] + res_f[2]  # stride-2 ConvT fused at the front of the stage kernel
     flops_of["up3+res3+post"] = up_f[3] + res_f[3] + post_f * frames
+    for i in range(3):  # the next stage's ConvT fused at the tail of ResBlock i's kernel (the default chain)
+        flops_of["res%d+up%d" % (i, i + 1)] = res_f[i] + up_f[i + 1]
     k_flops = [flops_of[n] for n in names]
-    dom = names.index("res1")
+    dom = [i for i, n in enumerate(names) if n.startswith("res1")][0]
+    dom_name = names[dom]
     dom_tflops = k_flops[dom] / (kms[dom] * 1e-3) / 1e12
     fwd_flops = sum(k_flops)
     packed_bytes = engine.lib().mg_gen_packed_bytes()
@@ -455,7 +458,11 @@ def main():
     # = 331.2 MB at config 2.  What this pipeline's kernels actually move by design is more: the ConvT outputs of the
     # stages whose ConvT is a separate kernel make one extra HBM round trip (written by up_i, re-read by res_i), and the
     # weights are streamed as split-bf16 (hi + lo: the same 4 bytes per weight) -- reported as moved_bytes / wasted ratio.
-    extra = 2 * (8192 + 32768 + (0 if "up2+res2" in names else 32768) + (0 if "up3+res3+post" in names else 32768))
+    # per mel frame, fp32: every kernel boundary of the chain is one write + one read of the tensor that crosses it
+    boundary = {"conv_pre": 2048, "up0": 8192, "res0": 8192, "up1": 32768, "res0+up1": 32768, "res1": 32768, "up2": 32768,
+                "res1+up2": 32768, "res2": 32768, "up2+res2": 32768, "up3": 32768, "res2+up3": 32768}
+    moved_frame = 320 + 1024 + 2 * sum(boundary[n] for n in names if n in boundary)
+    extra = moved_frame - ALG_BYTES_PER_FRAME
     alg_bytes = ALG_BYTES_PER_FRAME * frames + ALG_WEIGHT_BYTES
     moved_bytes = (ALG_BYTES_PER_FRAME + extra) * frames + packed_bytes
     fwd_ms = total_ms / K
@@ -466,7 +473,8 @@ def main():
         if t:
             traffic = t["dram_read_bytes"] + t["dram_write_bytes"]
     roofline = {
-        "kernel": "resblock_tc_kernel<C=128> (stage-1 ResBlock: 6 k3 convs, 36% of generator FLOPs)",
+        "kernel": ("resblock_tc_kernel<C=128> (%s: stage-1 ResBlock, 6 k3 convs%s; %.0f%% of generator FLOPs)" % (
+            dom_name, " + stage-2 ConvTranspose at its tail" if "+" in dom_name else "", 100.0 * k_flops[dom] / sum(k_flops))),
         "bound": "tensor", "achieved": dom_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
         "frac": dom_tflops / peaks["bf16_tflops"], "traffic": traffic,
         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r01_ncu_res1_key_metrics.txt); "

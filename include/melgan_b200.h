@@ -102,6 +102,11 @@ int mg_gen_resblock(const void *packed, int stage, const float *x, float *y, int
  * mg_gen_resblock: a per-kernel parity entry point. */
 int mg_gen_upres(const void *packed, int stage, const float *x, float *y, int B, int Lin, void *stream);
 
+/* ResBlock `stage` (0..2) with the NEXT stage's LeakyReLU -> ConvTranspose1d fused at its tail, as the default pipeline runs it
+ * (models.py:66 followed by :64-65 of the next loop iteration): x [B][C][L] is stage `stage`'s ConvT output, y
+ * [B][C/2][S L] is stage+1's (S = 8 for stage 0, else 2).  Synchronous parity entry point. */
+int mg_gen_resup(const void *packed, int stage, const float *x, float *y, int B, int L, void *stream);
+
 /* conv_pre alone (models.py:46,62): mel [B,80,T] -> y [B,512,T], device fp32.  Synchronous parity-test entry point of
  * conv_rows_tc_kernel<80,512,k7>. */
 int mg_gen_conv_pre(const void *packed, const float *mel, float *y, int B, int T, void *stream);
@@ -145,6 +150,22 @@ int mg_msd_check_status(const void *status_word, void *stream);
 size_t mg_disc_packed_bytes(void);
 int mg_disc_pack(const float *const *v, const float *const *g, const float *const *bias, void *packed, void *stream);
 int mg_disc_forward(const void *packed, const float *x, int Bt, int L, float *const *fmaps, void *status_word, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Mel-spectrogram front end.   Replaces: mel_spectrogram (meldataset.py:44-55: zero-pad by (n_fft - hop)/2, librosa
+ * melspectrogram with power 1 and Slaney-normalised triangles, log(clip(., 1e-5))) for the reference's analysis parameters
+ * n_fft = 1024, hop = 256, win = 1024 (config.json:15-17), on the GPU: the loader's and the validation loop's librosa call
+ * (train.py:164) without the host round trip.
+ *   mg_mel_tables_build fills a HOST buffer of mg_mel_tables_bytes() bytes (window, twiddles, sparse filter bank);
+ *     norm: 0 none, 1 Slaney area normalisation (= librosa 0.6/0.7 `norm=1`, today's `norm="slaney"`), 2 L1.  The caller
+ *     copies it to device memory (16-byte aligned) once.
+ *   mg_mel_spectrogram: audio [B][L] device fp32 in [-1, 1] -> mel [B][n_mels][T] device fp32, T = mg_mel_frames(L)
+ *     (= L / 256 when L is a multiple of 256).  Asynchronous on `stream`.
+ */
+size_t mg_mel_tables_bytes(void);
+int mg_mel_tables_build(int sampling_rate, int n_mels, float fmin, float fmax, int norm, void *tables_host);
+int mg_mel_frames(int L);
+int mg_mel_spectrogram(const void *tables, const float *audio, float *mel, int B, int L, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * Host-buffer engine.   The call a non-PyTorch host makes: owns its device buffers, takes and
@@ -213,6 +234,10 @@ int mg_loss_backward(const float *const *a, const float *const *b, const long lo
  * (joined back into `stream` before it returns), so one forward enqueues slices x launches kernels. */
 int mg_gen_forward_launches(void);
 int mg_gen_forward_slices(int B, int T);
+/* Selects the generator chain for the calling thread: bit i (1..3) of tail_mask = stage i's ConvT fused at the tail of
+ * ResBlock i-1's kernel; 0 = one kernel per ConvT / ResBlock (all stage outputs materialised: mg_gen_stage_output works for
+ * which = 1..3); -1 = the default (environment MG_GEN_TAIL, else all three).  For tests and A/B measurements. */
+int mg_gen_set_pipeline(int tail_mask);
 const char *mg_gen_kernel_name(int i);
 
 #ifdef __cplusplus

@@ -102,7 +102,7 @@ int mg_gen_forward_timed(const void *packed, const float *mel, float *audio, int
     if (workspace_bytes < mg_gen_workspace_bytes(B, T))
         return set_error(MG_ERR_WORKSPACE_TOO_SMALL, "mg_gen_forward_timed: workspace too small");
     const int n = mg_gen_forward_launches();  // events: one before each launch + one after the last
-    cudaEvent_t ev[17];
+    cudaEvent_t ev[17];  // at most 12 kernels
     for (int i = 0; i <= n; ++i) MG_CUDA_TRY(cudaEventCreate(&ev[i]));
     rc = run_generator((const float *)packed, mel, audio, B, T, (float *)workspace, (cudaStream_t)stream, ev);
     if (rc == MG_OK) {
@@ -116,14 +116,12 @@ int mg_gen_forward_timed(const void *packed, const float *mel, float *audio, int
     return rc;
 }
 
-const char *mg_gen_kernel_name(int i) {
-    static const char *tcn[4][9] = {
-        {"conv_pre", "up0", "res0", "up1", "res1", "up2", "res2", "up3", "res3+post"},
-        {"conv_pre", "up0", "res0", "up1", "res1", "up2+res2", "up3", "res3+post", ""},
-        {"conv_pre", "up0", "res0", "up1", "res1", "up2", "res2", "up3+res3+post", ""},
-        {"conv_pre", "up0", "res0", "up1", "res1", "up2+res2", "up3+res3+post", "", ""}};
-    if (i < 0 || i >= mg_gen_forward_launches()) return "";
-    return tcn[generator_tc_fused_up() & 3][i];
+const char *mg_gen_kernel_name(int i) { return generator_tc_kernel_name(i); }
+
+int mg_gen_set_pipeline(int tail_mask) {
+    if (tail_mask < -1 || tail_mask > 15) return set_error(MG_ERR_INVALID_ARGUMENT, "mg_gen_set_pipeline: mask %d", tail_mask);
+    generator_tc_set_tail(tail_mask);
+    return MG_OK;
 }
 
 int mg_gen_stage_output(const void *workspace, int which, float *out, int B, int T, void *stream) {
@@ -131,6 +129,9 @@ int mg_gen_stage_output(const void *workspace, int which, float *out, int B, int
     if (rc) return rc;
     if (which < 0 || which > 3 || !workspace || !out)
         return set_error(MG_ERR_INVALID_ARGUMENT, "mg_gen_stage_output: which must be 0..3 (the last stage is fused with conv_post)");
+    if (which > 0 && generator_tc_tail() != 0)
+        return set_error(MG_ERR_INVALID_ARGUMENT, "mg_gen_stage_output: ResBlock outputs are not materialised while the next stage's "
+                         "ConvT is fused at their kernel's tail; select the unfused chain with mg_gen_set_pipeline(0) first");
     const size_t off = ws_offset(which, B, T), n = ws_offset(which + 1, B, T) - off;
     MG_CUDA_TRY(cudaMemcpyAsync(out, (const float *)workspace + off, n * sizeof(float), cudaMemcpyDeviceToDevice,
                                 (cudaStream_t)stream));
@@ -259,6 +260,14 @@ int mg_gen_resblock(const void *packed, int stage, const float *x, float *y, int
     });
 }
 
+int mg_gen_resup(const void *packed, int stage, const float *x, float *y, int B, int L, void *stream) {
+    if (!packed || !x || !y || x == y || stage < 0 || stage > 2 || B < 1 || L < 1)
+        return set_error(MG_ERR_INVALID_ARGUMENT, "mg_gen_resup: bad argument");
+    return run_one_kernel("mg_gen_resup", (cudaStream_t)stream, [&](int *st) {
+        return launch_resblock_tc(x, y, (const float *)packed, 20 + stage, B, L, st, (cudaStream_t)stream);
+    });
+}
+
 int mg_gen_upres(const void *packed, int stage, const float *x, float *y, int B, int Lin, void *stream) {
     if (!packed || !x || !y || x == y || (stage != 2 && stage != 3) || B < 1 || Lin < 1)
         return set_error(MG_ERR_INVALID_ARGUMENT, "mg_gen_upres: bad argument");
@@ -325,6 +334,23 @@ int mg_msd_check_status(const void *status_word, void *stream) {
     MG_CUDA_TRY(cudaMemcpy(&st, status_word, sizeof(int), cudaMemcpyDeviceToHost));
     if (st) return set_error(MG_ERR_CUDA, "tensor-core pipeline wait timed out (role code %d)", st);
     return MG_OK;
+}
+
+/* ------------------------------- mel-spectrogram front end -------------------------------- */
+
+size_t mg_mel_tables_bytes(void) { return mel_tables_bytes(); }
+
+int mg_mel_tables_build(int sampling_rate, int n_mels, float fmin, float fmax, int norm, void *tables_host) {
+    if (!tables_host) return set_error(MG_ERR_INVALID_ARGUMENT, "mg_mel_tables_build: null buffer");
+    return mel_tables_build(sampling_rate, n_mels, fmin, fmax, norm, reinterpret_cast<MelTables *>(tables_host));
+}
+
+int mg_mel_frames(int L) { return L < 1 ? 0 : mel_frames(L); }
+
+int mg_mel_spectrogram(const void *tables, const float *audio, float *mel, int B, int L, void *stream) {
+    if (!tables || !audio || !mel || B < 1 || L < 1) return set_error(MG_ERR_INVALID_ARGUMENT, "mg_mel_spectrogram: bad argument");
+    if ((uintptr_t)tables % 16) return set_error(MG_ERR_INVALID_ARGUMENT, "mg_mel_spectrogram: tables must be 16-byte aligned");
+    return launch_mel(tables, audio, mel, B, L, (cudaStream_t)stream);
 }
 
 /* ------------------------------- host-buffer engine ------------------------------------- */

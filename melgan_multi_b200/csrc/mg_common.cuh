@@ -72,7 +72,10 @@ int launch_generator_simt(const float *packed, const float *mel, float *audio, i
                           cudaStream_t s, cudaEvent_t *ev = nullptr);
 int generator_simt_num_launches();
 int generator_tc_num_launches();
-int generator_tc_fused_up();  // bit 0: stage 2, bit 1: stage 3 run their stride-2 ConvT inside the ResBlock kernel
+int generator_tc_fused_up();  // bit 0: stage 2, bit 1: stage 3 run their stride-2 ConvT at the FRONT of the ResBlock kernel
+int generator_tc_tail();      // bit i: stage i's ConvT runs at the TAIL of ResBlock i-1's kernel
+void generator_tc_set_tail(int mask);
+const char *generator_tc_kernel_name(int i);
 int generator_tc_slices(int B, int T);  // batch slices (concurrent kernel chains) one forward is cut into
 int launch_generator_tc(const float *packed, const float *mel, float *audio, int B, int T, float *ws, int *status,
                         cudaStream_t s, cudaEvent_t *ev = nullptr, const float *mel_host = nullptr, float *audio_host = nullptr);
@@ -99,6 +102,11 @@ int launch_loss_forward(const float *const *a, const float *const *b, const long
                         float *partial, cudaStream_t s);
 int launch_loss_backward(const float *const *a, const float *const *b, const long long *n, const int *mode, int count,
                          const float *gout, float *const *ga, float *const *gb, cudaStream_t s);
+struct MelTables;
+size_t mel_tables_bytes();
+int mel_tables_build(int sr, int n_mels, float fmin, float fmax, int norm, MelTables *t);
+int mel_frames(int L);
+int launch_mel(const void *tables, const float *audio, float *mel, int B, int L, cudaStream_t s);
 int launch_msd_forward(const void *packed, const float *y, int Bt, int L, float *const *fmaps, int *status, cudaStream_t s);
 int launch_convt_tc(const float *x, float *y, const float *packed, int stage, int B, int Lin, int *status, cudaStream_t s);
 int launch_resblock_tc(const float *x, float *y, const float *packed, int stage, int B, int L, int *status, cudaStream_t s,

@@ -7,9 +7,24 @@
 
 namespace mg {
 
-// Which stride-2 stages run their ConvT inside the ResBlock kernel: bit 0 = stage 2, bit 1 = stage 3.  Default: stage 3
-// only (measured at config 2: up3 + res3 194 -> 176 us fused, up2 + res2 221 -> 241 us: at C = 64 the extra serial phases
-// of the fused tile cost more than the separate ConvT kernel).  MG_GEN_FUSE_UP = 0 / 2 / 3 / 23 overrides (A/B runs).
+// Pipeline shape.  TAIL mask: bit i (i = 1..3) set = ConvTranspose of stage i runs at the TAIL of ResBlock i-1's kernel
+// (mg_res_tc.cu, UPT): the chain is then  conv_pre, up0, res0+up1, res1+up2, res2+up3, res3+post  -- six kernels, no ResBlock
+// output ever written to HBM.  Default: stages 1 and 3 (measured at config 2: res0+up1 and res2+up3 beat their two-kernel
+// forms; res1+up2 does not -- the extra halo row a tail ConvT needs turns the 9 tiles of a 2048-position item into 10, i.e.
+// 640 CTAs = 5 waves instead of 576 = 4).  MG_GEN_TAIL=<digits> ("123", "0" for none) / mg_gen_set_pipeline() override it.  Where stage 3's ConvT is not at res2's tail it runs at the FRONT of the last
+// kernel (UPF, "up3+res3+post") unless MG_GEN_FUSE_UP says otherwise (bit 0: stage 2 front-fused, bit 1: stage 3).
+static thread_local int g_tail_override = -1;
+void generator_tc_set_tail(int mask) { g_tail_override = mask; }
+int generator_tc_tail() {
+    static const int env_mask = [] {
+        const char *e = getenv("MG_GEN_TAIL");
+        if (!e) return 0b1010;
+        int m = 0;
+        for (; *e; ++e) m |= (*e >= '1' && *e <= '3') ? 1 << (*e - '0') : 0;
+        return m;
+    }();
+    return g_tail_override >= 0 ? (g_tail_override & 0b1110) : env_mask;
+}
 int generator_tc_fused_up() {
     static const int mask = [] {
         const char *e = getenv("MG_GEN_FUSE_UP");
@@ -20,48 +35,77 @@ int generator_tc_fused_up() {
     }();
     return mask;
 }
-int generator_tc_num_launches() { return 9 - (generator_tc_fused_up() & 1) - ((generator_tc_fused_up() >> 1) & 1); }
 
-// Tensor-core pipeline of one contiguous slice of the batch: conv_pre -> 4 x [ConvT (tcgen05) -> ResBlock (tcgen05)], the
-// last ResBlock with LeakyReLU -> conv_post -> tanh fused into its epilogue.
-// a0, a[0..2], u: this slice's part of the workspace buffers.
+// The chain as a list of steps (shared by the launcher, the launch counter and the kernel-name table).
+struct ChainStep {
+    const char *name;
+    int kind;  // 0 conv_pre, 1 ConvT (arg = stage), 2 ResBlock kernel (arg = launch_resblock_tc code)
+    int arg;
+};
+static int build_chain(ChainStep *st) {
+    const int tail = generator_tc_tail(), front = generator_tc_fused_up();
+    int n = 0;
+    st[n++] = {"conv_pre", 0, 0};
+    st[n++] = {"up0", 1, 0};
+    if (tail & 2) st[n++] = {"res0+up1", 2, 20};
+    else { st[n++] = {"res0", 2, 0}; st[n++] = {"up1", 1, 1}; }
+    if (tail & 4) st[n++] = {"res1+up2", 2, 21};
+    else if (front & 1) st[n++] = {"res1", 2, 1};
+    else { st[n++] = {"res1", 2, 1}; st[n++] = {"up2", 1, 2}; }
+    const bool front2 = !(tail & 4) && (front & 1);
+    if (tail & 8) { st[n++] = {front2 ? "up2+res2+up3" : "res2+up3", 2, front2 ? -1 : 22}; st[n++] = {"res3+post", 2, 4}; }
+    else if (front & 2) { st[n++] = {front2 ? "up2+res2" : "res2", 2, front2 ? 12 : 2}; st[n++] = {"up3+res3+post", 2, 14}; }
+    else { st[n++] = {front2 ? "up2+res2" : "res2", 2, front2 ? 12 : 2}; st[n++] = {"up3", 1, 3}; st[n++] = {"res3+post", 2, 4}; }
+    return n;
+}
+int generator_tc_num_launches() {
+    ChainStep st[12];
+    return build_chain(st);
+}
+const char *generator_tc_kernel_name(int i) {
+    ChainStep st[12];
+    const int n = build_chain(st);
+    return (i >= 0 && i < n) ? st[i].name : "";
+}
+
+// Tensor-core pipeline of one contiguous slice of the batch.  a0: conv_pre output; a[0]: ResBlock-0 output (unfused chains);
+// a[1], a[2], u: three buffers of 8192 T floats per item that the stages rotate through (a kernel never writes its input).
 static int generator_tc_chain(const float *packed, const float *mel, float *audio, int B, int T, float *a0, float *const *a,
                               float *u, int *status, cudaStream_t s, cudaEvent_t *ev) {
-#define MG_MARK(i) do { if (ev) MG_CUDA_TRY(cudaEventRecord(ev[i], s)); } while (0)
+    ChainStep st[12];
+    const int n = build_chain(st);
     int rc;
-    MG_MARK(0);
-    if ((rc = launch_gen_pre_tc(mel, a0, packed, B, T, status, s))) return rc;
-    MG_MARK(1);
-    if ((rc = launch_convt_tc(a0, u, packed, 0, B, T, status, s))) return rc;
-    MG_MARK(2);
-    if ((rc = launch_resblock_tc(u, a[0], packed, 0, B, 8 * T, status, s))) return rc;
-    MG_MARK(3);
-    if ((rc = launch_convt_tc(a[0], u, packed, 1, B, 8 * T, status, s))) return rc;
-    MG_MARK(4);
-    if ((rc = launch_resblock_tc(u, a[1], packed, 1, B, 64 * T, status, s))) return rc;
-    MG_MARK(5);
-    // stages 2 and 3 can run LeakyReLU -> ConvT(k4, s2) -> ResBlock (-> conv_post -> tanh) as ONE kernel reading the previous
-    // stage's output, so that the ConvT output never goes to HBM (generator_tc_fused_up(): bit 0 = stage 2, bit 1 = stage 3)
-    const int fuse = generator_tc_fused_up();
-    int m = 6;
-    if (fuse & 1) {
-        if ((rc = launch_resblock_tc(a[1], a[2], packed, 12, B, 128 * T, status, s))) return rc;
-    } else {
-        if ((rc = launch_convt_tc(a[1], u, packed, 2, B, 64 * T, status, s))) return rc;
-        MG_MARK(m); ++m;
-        if ((rc = launch_resblock_tc(u, a[2], packed, 2, B, 128 * T, status, s))) return rc;
+    float *big[3] = {a[1], a[2], u};
+    auto other = [&](const float *x, const float *y) -> float * {  // a rotation buffer that is neither x nor y
+        for (float *b : big)
+            if (b != x && b != y) return b;
+        return nullptr;
+    };
+    const float *cur = mel;
+    int len = T;  // length of `cur`
+    for (int i = 0; i < n; ++i) {
+        if (ev) MG_CUDA_TRY(cudaEventRecord(ev[i], s));
+        const ChainStep &k = st[i];
+        if (k.kind == 0) {
+            if ((rc = launch_gen_pre_tc(cur, a0, packed, B, T, status, s))) return rc;
+            cur = a0;
+        } else if (k.kind == 1) {
+            float *out = cur != u ? u : other(cur, nullptr);  // (unfused chain: ConvT outputs live in u, ResBlock i's in a[i])
+            if ((rc = launch_convt_tc(cur, out, packed, k.arg, B, len, status, s))) return rc;
+            cur = out;
+            len *= stage_stride(k.arg);
+        } else {
+            if (k.arg < 0) return set_error(MG_ERR_INVALID_ARGUMENT, "generator pipeline: MG_GEN_FUSE_UP=2 cannot be combined with a tail-fused up3");
+            const bool last = k.arg == 4 || k.arg == 14;
+            const bool front = k.arg >= 12 && k.arg <= 14, tailf = k.arg >= 20;
+            float *out = last ? audio : (k.arg <= 2 && cur != a[k.arg]) ? a[k.arg] : other(cur, nullptr);
+            const int Lk = front ? 2 * len : len;  // the ResBlock's own length
+            if ((rc = launch_resblock_tc(cur, out, packed, k.arg, B, Lk, status, s))) return rc;
+            cur = out;
+            len = tailf ? Lk * stage_stride(k.arg - 20 + 1) : Lk;
+        }
     }
-    MG_MARK(m); ++m;
-    if (fuse & 2) {
-        if ((rc = launch_resblock_tc(a[2], audio, packed, 14, B, 256 * T, status, s))) return rc;
-    } else {
-        if ((rc = launch_convt_tc(a[2], u, packed, 3, B, 128 * T, status, s))) return rc;
-        MG_MARK(m); ++m;
-        // stage 4 = ResBlock 3 with LeakyReLU -> conv_post -> tanh fused into its final epilogue: writes the audio
-        if ((rc = launch_resblock_tc(u, audio, packed, 4, B, 256 * T, status, s))) return rc;
-    }
-    MG_MARK(m);
-#undef MG_MARK
+    if (ev) MG_CUDA_TRY(cudaEventRecord(ev[n], s));
     return MG_OK;
 }
 

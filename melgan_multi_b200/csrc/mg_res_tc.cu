@@ -46,9 +46,21 @@ using namespace tc;
 // pair it is ONE super-tile without any halo, 128 CTAs = one wave).  The pair runs in lock step -- `done` counts the MMA
 // commits of BOTH CTAs, so nobody overwrites rows a peer's MMAs may still read -- and streams the same weights: the leader's
 // bulk copies are multicast into both rings, the ring slots freed by multicast commits.
-template <int C_, int NBLK_, int NSTAGE_, int NWG_, int MINB_, bool POST_ = false, bool UPF_ = false, int CL_ = 1>
+// UPT = S (2 or 8): the NEXT stage's LeakyReLU -> ConvTranspose1d(C -> C/2, k = 2S, stride S) runs at the TAIL of this kernel
+// (models.py:64-65 of the following loop iteration): after the sixth conv the epilogue writes X = split(lrelu(x)) exactly as
+// it does between convs, and the ConvT is two more "taps" on that operand -- out[S s + phi - pad] = x[s] W[phi] + x[s-1] W[phi+S],
+// all S phases stacked along N like mg_up_tc.cu (N = S * NG = C in every stage), accumulators in the TMEM columns the
+// ResBlock no longer needs.  The kernel then stores the ConvT output [B][C/2][S L] instead of the ResBlock output: the
+// ResBlock output never goes to HBM, and the separate ConvT kernel (its activation re-read, operand conversion and launch)
+// disappears.  An input position s owns the outputs [S s - pad, S s - pad + S) and needs x[s - 1]: tiles overlap by one
+// more row on the left (HL = HALO + 1).  Position L (x[L] = 0) would own the last `pad` outputs; giving it a row would cost a
+// whole extra tile exactly where sequences are a multiple of the tile (stage 0 at T = 32: 256 positions = one CTA pair), so
+// those pad * C/2 outputs -- dot products of x[L-1] with the tap-1 weights -- are computed in fp32 by the CTA that owns
+// position L - 1 (fix-up at the end of the epilogue).
+template <int C_, int NBLK_, int NSTAGE_, int NWG_, int MINB_, bool POST_ = false, bool UPF_ = false, int CL_ = 1, int UPT_ = 0>
 struct RbCfg {
     static constexpr int CL = CL_;
+    static constexpr int UPT = UPT_;
     static constexpr bool UPF = UPF_;
     static constexpr int C = C_;
     static constexpr int NBLK = NBLK_, MINB = MINB_;
@@ -58,7 +70,8 @@ struct RbCfg {
     // zero rows either side of X (dilation-9 taps reach 9 rows out); 12 lets two C = 128 single-block CTAs share an SM
     static constexpr int SLACK = (C_ == 128 && NBLK_ == 1) ? 12 : 16;
     static constexpr int HALO = 16 + (POST ? 3 : 0);  // 1+1+3+1+9+1 (+3 for the fused k7 conv_post)
-    static constexpr int PVALID = P - 2 * HALO;
+    static constexpr int HL = HALO + (UPT_ ? 1 : 0);  // left halo: a fused tail ConvT also reads x[s - 1]
+    static constexpr int PVALID = P - HALO - HL;
     static constexpr int ROWS = P + 2 * SLACK;
     static constexpr int XPITCH = ROWS * 16;  // bytes between k-panels
     static constexpr int KP = C / 8;
@@ -86,7 +99,13 @@ struct RbCfg {
     static constexpr int BND = SLACK;  // boundary rows pushed to the peer CTA (CL = 2); the widest tap reaches 9
     static constexpr int XARRIVE = NEPI + (CL > 1 ? BND * PARTS : 0);  // xready arrivals: local epilogue threads + the peer's boundary threads
     static_assert(CL == 1 || (CL == 2 && !UPF_ && !POST_), "CTA pairs: plain ResBlock only");
-    static constexpr int SMEM_BYTES = 2 * XBYTES + NSTAGE * CHUNK + 2 * C * 4 + (2 * NSTAGE + 1 + NH) * 8 + 16;
+    // tail ConvT: TNG output channels per group (mg_layout.h up_ng of the next stage), TN = MMA N, TNCG groups, ring slots of
+    // TSLOT bytes (stride 8: one tap of a 16-channel chunk; stride 2: both taps), TNSLOT of them
+    static constexpr int TNG = UPT == 8 ? 32 : C / 2, TN = (UPT ? UPT : 1) * TNG, TNCG = (C / 2) / TNG;
+    static constexpr int TSLOT = UPT == 8 ? 16384 : 128 * UPT * TNG, TNSLOT = UPT ? TNCG * (C / 16) * (UPT == 8 ? 2 : 1) : 0;
+    static_assert(UPT == 0 || ((UPT == 2 || UPT == 8) && TN == C && TSLOT <= CHUNK && !POST_ && !UPF_), "tail ConvT shape");
+    static_assert(UPT != 8 || (NBLK == 1 && TCOLS == 512), "stride-8 tail ConvT double-buffers its accumulators in the 512 columns");
+    static constexpr int SMEM_BYTES = 2 * XBYTES + NSTAGE * CHUNK + 2 * C * 4 + (2 * NSTAGE + 1 + NH + 4) * 8 + 16;
     static_assert(KSL % NH == 0 && (CW / NH) % 32 == 0 && (NH == 1 || ITEMS == NWG), "hand-off split");
     // fused ConvT: input rows s = o/2 - 1 .. o/2 + P/2 of 2C channels (2 KP k-panels), NCB blocks of 128 output pairs
     static constexpr int UROWS = P / 2 + 2, UPITCH = UROWS * 16, NCB = NBLK / 2, UKSL = 2 * C / KC, NUPCH = UPF ? 4 * UKSL : 0;
@@ -153,7 +172,9 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
     uint64_t *empty = full + NSTAGE;
     uint64_t *done = empty + NSTAGE;
     uint64_t *xready = done + 1;  // [NH]: X channels [h*C/NH, (h+1)*C/NH) of the next conv are written (all epilogue threads arrive)
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(xready + Cfg::NH);
+    uint64_t *dup = xready + Cfg::NH;  // [2] tail ConvT (stride 8): accumulator buffer complete;  tfree[2]: drained by the epilogue
+    uint64_t *tfree = dup + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tfree + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.y;
@@ -161,13 +182,14 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
     // left edge is the real zero padding) and keeps P - HALO outputs; later tiles keep P - 2*HALO, and a tile that reaches
     // the end of the sequence keeps its right HALO rows too.  (L = 2048, P = 256: 9 tiles instead of 10.)
     // CL > 1: all of this at super-tile granularity (PS = CL * P rows), CTA `rank` of the cluster owning rows [rank * P, + P).
-    constexpr int CL = Cfg::CL, PS = CL * P, PVS = PS - 2 * HALO;
+    constexpr int CL = Cfg::CL, PS = CL * P, HL = Cfg::HL, PVS = PS - HALO - HL;
     const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
     const int stile = (int)blockIdx.x / CL;
-    const int os = stile == 0 ? 0 : (PS - HALO) + (stile - 1) * PVS - HALO;  // position of super-tile row 0
-    const int o = os + rank * P;                                              // position of tile-local p = 0
-    const int s_lo = stile == 0 ? 0 : HALO;
-    const int s_hi = (os + PS >= L) ? PS : PS - HALO;  // first super-tile row that is NOT a valid output
+    const int os = stile == 0 ? 0 : (PS - HALO) + (stile - 1) * PVS - HL;  // position of super-tile row 0
+    const int o = os + rank * P;                                            // position of tile-local p = 0
+    const int Lc = L;  // (tail ConvT: position L would own the last `pad` outputs; they are x[L-1]-only and fixed up below)
+    const int s_lo = stile == 0 ? 0 : HL;
+    const int s_hi = (os + PS >= Lc) ? PS : PS - HALO;  // first super-tile row that is NOT a valid output
     const int p_lo = min(max(s_lo - rank * P, 0), P), p_hi = min(max(s_hi - rank * P, 0), P);
     const bool interior = (o >= 0 && o + P <= L);  // every row of the tile is a real position
     // CTA pair: my boundary rows (rank 0: the last BND rows, rank 1: the first BND) mirror into the peer's slack rows
@@ -186,6 +208,7 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
         }
         mbar_init(done, NIW * CL);
         for (int h = 0; h < Cfg::NH; ++h) mbar_init(&xready[h], Cfg::XARRIVE);
+        for (int k = 0; k < 2; ++k) { mbar_init(&dup[k], NIW * CL); mbar_init(&tfree[k], NEPI); }
         fence_mbar_init();
     }
     for (int h = 0; h < Cfg::NH; ++h) rxready[h] = CL > 1 ? mapa_shared(smem_u32(&xready[h]), peer) : 0u;
@@ -238,6 +261,20 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
                             bulk_g2s_multicast(ring + s * CHUNK, src + (size_t)ch * CHUNK, CHUNK, &full[s], (uint16_t)((1u << CL) - 1));
                     } else {
                         bulk_g2s(ring + s * CHUNK, src + (size_t)ch * CHUNK, CHUNK, &full[s]);
+                    }
+                    if (++s == NSTAGE) { s = 0; ph ^= 1; }
+                }
+            }
+            if constexpr (Cfg::UPT != 0) {  // the tail ConvT's B slots, in blob order [group][16-channel chunk][tap]
+                const uint8_t *src = tc_base + tc_up_offset(stage + 1);
+                for (int i = 0; i < Cfg::TNSLOT && ok; ++i) {
+                    if (!mbar_wait(&empty[s], ph ^ 1)) { ok = false; break; }
+                    mbar_arrive_expect_tx(&full[s], Cfg::TSLOT);
+                    if constexpr (CL > 1) {
+                        if (rank == 0)
+                            bulk_g2s_multicast(ring + s * CHUNK, src + (size_t)i * Cfg::TSLOT, Cfg::TSLOT, &full[s], (uint16_t)((1u << CL) - 1));
+                    } else {
+                        bulk_g2s(ring + s * CHUNK, src + (size_t)i * Cfg::TSLOT, Cfg::TSLOT, &full[s]);
                     }
                     if (++s == NSTAGE) { s = 0; ph ^= 1; }
                 }
@@ -340,6 +377,60 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
             }
             if (iw == 0) MG_TR(66 + 3 * conv);
             if (!ok && lane == 0) atomicExch(status, 3);
+            __syncwarp();
+        }
+        if constexpr (Cfg::UPT != 0) {
+            // ---- tail ConvT: D[s, phi*TNG + co] (+)= X[s - tap, :] * Wstack_tap^T over the C channels of X = split(lrelu(x_out))
+            constexpr int S = Cfg::UPT, TN = Cfg::TN;
+            const uint64_t tbdesc_t = desc_template(TN * 16, 128);
+            for (int h = 0; h < Cfg::NH; ++h)
+                ok &= CL > 1 ? mbar_wait_cluster(&xready[h], (6 + PH0) & 1) : mbar_wait(&xready[h], (6 + PH0) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int cg = 0; cg < Cfg::TNCG; ++cg) {
+                const int buf = cg & 1;
+                if (S == 8 && cg >= 2) {  // the epilogue must have drained this accumulator buffer (group cg - 2)
+                    ok &= mbar_wait(&tfree[buf], ((cg >> 1) - 1) & 1);
+                    tc_fence_after();
+                }
+#pragma unroll 1
+                for (int ch = 0; ch < C / 16; ++ch) {
+#pragma unroll 1
+                    for (int ts = 0; ts < (S == 8 ? 2 : 1); ++ts) {  // stride 8: one ring slot per tap
+                        ok &= mbar_wait(&full[s], ph);
+                        tc_fence_after();
+                        const uint64_t bbase = desc_at(tbdesc_t, ring_addr + s * CHUNK);
+#pragma unroll
+                        for (int tp = 0; tp < (S == 8 ? 1 : 2); ++tp) {
+                            const int tap = S == 8 ? ts : tp;  // tap 0 reads x[s], tap 1 x[s - 1]: the same buffer one row earlier
+#pragma unroll
+                            for (int pass = 0; pass < 3; ++pass) {
+                                const uint32_t boff = (uint32_t)((((S == 8 ? 0 : tp * 2) + (pass == 2 ? 1 : 0)) * 2) * TN * 16);
+                                const uint64_t bdesc = bbase + (uint64_t)(boff >> 4);
+#pragma unroll
+                                for (int bi = 0; bi < NBLK / NIW; ++bi) {
+                                    const int blk = iw + bi * NIW;
+                                    const uint32_t arow = (uint32_t)((SLACK + blk * 128 - tap) * 16 + 2 * ch * XPITCH);
+                                    const uint64_t adesc = desc_at(adesc_t, (pass == 1 ? xl_addr : xh_addr) + arow);
+                                    const uint32_t dc = S == 8 ? (uint32_t)(buf * 256) : (uint32_t)(blk * 2 * C + C);
+                                    if (elect_one()) mma_bf16(tmem + dc, adesc, bdesc, idesc, !(ch == 0 && tap == 0 && pass == 0));
+                                }
+                            }
+                        }
+                        if (elect_one()) {
+                            if constexpr (CL > 1) mma_commit_multicast(&empty[s], (uint16_t)((1u << CL) - 1));
+                            else mma_commit(&empty[s]);
+                        }
+                        if (++s == NSTAGE) { s = 0; ph ^= 1; }
+                    }
+                }
+                if (elect_one()) {
+                    uint64_t *bar = S == 8 ? &dup[buf] : done;
+                    if constexpr (CL > 1) mma_commit_multicast(bar, (uint16_t)((1u << CL) - 1));
+                    else mma_commit(bar);
+                }
+            }
+            if (!ok && lane == 0) atomicExch(status, 7);
             __syncwarp();
         }
     } else {
@@ -556,13 +647,14 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
             if (ok && !mbar_wait(done, (conv + (Cfg::UPF ? 1 : 0)) & 1)) { ok = false; if (lane == 0) atomicExch(status, 4); }
             tc_fence_after();
             if (warp == 0) MG_TR(3 + 3 * conv);
-            if (conv == 5) {
+            if (conv == 5 && Cfg::UPT == 0) {
                 // all MMAs of this tile are done: the next kernel of the chain may be scheduled (its CTAs set up and prefetch
                 // weights on SMs this grid has already vacated, then sit in pdl_wait() until this grid has completed).
                 // Late on purpose: an early trigger parks waiting CTAs on SMs that other streams' kernels could be using.
                 pdl_trigger();
                 break;
             }
+            // (tail ConvT: the sixth conv is followed by one more hand-off -- X = split(lrelu(R + pend)) is the ConvT's operand)
             const uint32_t scol = (conv & 1) ? 0 : C;  // next input comes from R (after c2) or D1 (after c1)
             const float *bsrc = (conv & 1) ? pend : b1s;
 #pragma unroll 1
@@ -588,6 +680,10 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
                         } else {
 #pragma unroll
                             for (int j = 0; j < 32; ++j) f[j] = inr ? lrelu(__uint_as_float(v[j]) + bsrc[c0 + j]) : 0.f;
+                        }
+                        if (Cfg::UPT != 0 && conv == 5 && t == L - 1) {  // lrelu(x[L-1]) in fp32 for the fix-up (b1s is free now)
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) b1s[c0 + j] = f[j];
                         }
                         if constexpr (CL > 1) {
                             store_x16_push(Xh, Xl, XPITCH, c0, (p + SLACK) * 16, f, push, rxh, rxl, prow);
@@ -652,6 +748,100 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
                     y[(size_t)b * L + t] = tanhf(acc);
                 }
             }
+        } else if constexpr (Cfg::UPT != 0) {
+            // ---- tail ConvT epilogue: the thread of input position s stores the S outputs [S s - pad, S s - pad + S) of its channels
+            constexpr int S = Cfg::UPT, TNG = Cfg::TNG, PADT = S / 2, COT = C / 2;
+            const int Lout = S * L;
+            const float *tbias = packed + bias_offset(1 + stage + 1);
+            // ---- fix-up (first: it only needs b1s[], so it runs while the tensor core works on the ConvT): out[co][S L - pad + j] = bias + sum_ci lrelu(x[ci][L-1]) * W[ci][co][j + S], j < pad (the outputs position
+            // L would own: x[L] = 0 leaves only the x[L-1] tap), by the CTA whose owned rows include position L - 1.  fp32 FFMA
+            // on the fp32 copy of the ConvT weights ([Cin][Cout][S][2], mg_layout.h): pad * C/2 dot products of length C.
+            {
+                const int pl = L - 1 - o;  // tile-local row of position L - 1
+                if (pl >= p_lo && pl < p_hi) {  // CTA-uniform
+                    named_bar_sync(2, NEPI);     // every thread's b1s[] contribution (written during the last hand-off) is visible
+                    const float *wf = packed + weight_offset(1 + stage + 1);
+                    for (int i = tid; i < PADT * COT; i += NEPI) {
+                        const int co = i / PADT, j = i - co * PADT;
+                        const float *wp = wf + ((size_t)co * S + j) * 2 + 1;  // + ci * COT * S * 2
+                        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+#pragma unroll 1
+                        for (int c0 = 0; c0 < C; c0 += 32) {  // 32 weights in flight per round trip
+                            float wv[32];
+#pragma unroll
+                            for (int k = 0; k < 32; ++k) wv[k] = __ldg(wp + (size_t)(c0 + k) * COT * S * 2);
+#pragma unroll
+                            for (int k = 0; k < 32; k += 4) {
+                                acc0 = fmaf(b1s[c0 + k], wv[k], acc0);
+                                acc1 = fmaf(b1s[c0 + k + 1], wv[k + 1], acc1);
+                                acc2 = fmaf(b1s[c0 + k + 2], wv[k + 2], acc2);
+                                acc3 = fmaf(b1s[c0 + k + 3], wv[k + 3], acc3);
+                            }
+                        }
+                        y[((size_t)b * COT + co) * Lout + (size_t)S * L - PADT + j] = (acc0 + acc1) + (acc2 + acc3) + __ldg(tbias + co);
+                    }
+                }
+            }
+            if constexpr (S == 2) {
+                if (ok && !mbar_wait(done, (6 + (Cfg::UPF ? 1 : 0)) & 1)) { ok = false; if (lane == 0) atomicExch(status, 8); }
+                tc_fence_after();
+                pdl_trigger();
+                constexpr int COI = TNG / PARTS;  // output channels per item
+                static_assert(COI % 16 == 0, "tail ConvT epilogue split");
+#pragma unroll 1
+                for (int it = wg; it < ITEMS; it += NWG) {
+                    const int blk = it / PARTS, jbeg = (it % PARTS) * COI;
+                    const int p = blk * 128 + row, sg = o + p;  // sg: global input position
+                    const bool own = (p >= p_lo && p < p_hi && sg < L);
+                    const bool lo_ok = own && sg >= 1, hi_ok = own;
+                    float *yb = y + (size_t)b * COT * Lout + (own ? 2 * sg - PADT : 0);
+#pragma unroll 1
+                    for (int j0 = jbeg; j0 < jbeg + COI; j0 += 16) {
+                        uint32_t v0[16], v1[16];
+                        tmem_ld16(lane_addr + blk * 2 * C + C + j0, v0);
+                        tmem_ld16(lane_addr + blk * 2 * C + C + TNG + j0, v1);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float bj = __ldg(tbias + j0 + j);
+                            float *yp = yb + (size_t)(j0 + j) * Lout;
+                            if (lo_ok) yp[0] = __uint_as_float(v0[j]) + bj;
+                            if (hi_ok) yp[1] = __uint_as_float(v1[j]) + bj;
+                        }
+                    }
+                }
+            } else {
+                static_assert(S == 2 || (NBLK == 1 && PARTS * 8 == TNG), "stride-8 tail: each warpgroup stores 8 channels of a group");
+                const int p = row, sg = o + p;
+                const bool own = (p >= p_lo && p < p_hi && sg < L);
+                const bool lo_ok = own && sg >= 1, hi_ok = own;
+#pragma unroll 1
+                for (int cg = 0; cg < Cfg::TNCG; ++cg) {
+                    const int buf = cg & 1;
+                    if (ok && !mbar_wait(&dup[buf], (cg >> 1) & 1)) { ok = false; if (lane == 0) atomicExch(status, 8); }
+                    tc_fence_after();
+                    if (cg == Cfg::TNCG - 1) pdl_trigger();
+                    const int j0 = wg * 8;  // this warpgroup's 8 channels of the group
+                    uint32_t w[8][8];
+#pragma unroll
+                    for (int phi = 0; phi < 8; ++phi) tmem_ld8(lane_addr + buf * 256 + phi * TNG + j0, w[phi]);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    mbar_arrive(&tfree[buf]);  // values are in registers: the buffer may be overwritten by group cg + 2
+                    float *yb = y + ((size_t)b * COT + cg * TNG + j0) * Lout + (own ? 8 * sg - PADT : 0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float bj = __ldg(tbias + cg * TNG + j0 + j);
+                        float *yp = yb + (size_t)j * Lout;
+                        if (lo_ok)
+                            *reinterpret_cast<float4 *>(yp) = make_float4(__uint_as_float(w[0][j]) + bj, __uint_as_float(w[1][j]) + bj,
+                                                                          __uint_as_float(w[2][j]) + bj, __uint_as_float(w[3][j]) + bj);
+                        if (hi_ok)
+                            *reinterpret_cast<float4 *>(yp + 4) = make_float4(__uint_as_float(w[4][j]) + bj, __uint_as_float(w[5][j]) + bj,
+                                                                              __uint_as_float(w[6][j]) + bj, __uint_as_float(w[7][j]) + bj);
+                    }
+                }
+            }
         } else {
         // ---- store the valid part of R + pend
 #pragma unroll 1
@@ -689,8 +879,9 @@ static int launch_resblock(const float *x, float *y, const float *packed, int st
         MG_CUDA_TRY(cudaFuncSetAttribute(resblock_tc_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         configured = true;
     }
-    constexpr int PS = Cfg::CL * Cfg::P, PVS = PS - 2 * Cfg::HALO;  // edge-aware tiling in super-tiles of CL tiles, see the kernel
-    const int ntiles = 1 + (L > PS ? (L - PS + PVS - 1) / PVS : 0);
+    constexpr int PS = Cfg::CL * Cfg::P, PVS = PS - Cfg::HALO - Cfg::HL;  // edge-aware tiling in super-tiles of CL tiles, see the kernel
+    const int Lc = L;
+    const int ntiles = 1 + (Lc > PS ? (Lc - PS + PVS - 1) / PVS : 0);
     MG_CUDA_TRY(launch_ex(resblock_tc_kernel<Cfg>, dim3(ntiles * Cfg::CL, B), dim3(Cfg::NT), Cfg::SMEM_BYTES, s, Cfg::CL, true, x, y,
                           packed, stage, L, status, trace));
     return MG_OK;
@@ -723,6 +914,12 @@ int launch_resblock_tc(const float *x, float *y, const float *packed, int stage,
         case 4: return launch_resblock<RbCfg<32, 4, 4, 2, 2, true>>(x, y, packed, 3, B, L, status, trace, s);
         // 12 / 13 / 14 = stages 2 / 3 / 3+post with the stage's stride-2 ConvT fused in: x is the PREVIOUS stage's output
         // [B][2C][L/2] (L stays the output length)
+        // 20 / 21 / 22 = ResBlock 0 / 1 / 2 with the NEXT stage's LeakyReLU -> ConvT at its tail: y is [B][C/2][S L]
+        case 20:
+            if (L > 128) return launch_resblock<RbCfg<256, 1, 4, 4, 1, false, false, 2, 8>>(x, y, packed, 0, B, L, status, trace, s);
+            return launch_resblock<RbCfg<256, 1, 4, 4, 1, false, false, 1, 8>>(x, y, packed, 0, B, L, status, trace, s);
+        case 21: return launch_resblock<RbCfg<128, 2, 4, 4, 1, false, false, 1, 2>>(x, y, packed, 1, B, L, status, trace, s);
+        case 22: return launch_resblock<RbCfg<64, 2, 2, 2, 2, false, false, 1, 2>>(x, y, packed, 2, B, L, status, trace, s);
         case 12: return launch_resblock<RbCfg<64, 2, 2, 2, 2, false, true>>(x, y, packed, 2, B, L, status, trace, s);
         case 13: return launch_resblock<RbCfg<32, 4, 4, 2, 2, false, true>>(x, y, packed, 3, B, L, status, trace, s);
         case 14: return launch_resblock<RbCfg<32, 4, 4, 2, 2, true, true>>(x, y, packed, 3, B, L, status, trace, s);

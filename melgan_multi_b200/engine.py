@@ -65,6 +65,11 @@ def lib():
         L.mg_disc_forward.restype = ctypes.c_int
         L.mg_disc_forward.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                       ctypes.c_void_p, ctypes.c_void_p]
+        L.mg_gen_resup.restype = ctypes.c_int
+        L.mg_gen_resup.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                   ctypes.c_void_p]
+        L.mg_gen_set_pipeline.restype = ctypes.c_int
+        L.mg_gen_set_pipeline.argtypes = [ctypes.c_int]
         L.mg_gen_stage_output.restype = ctypes.c_int
         L.mg_gen_stage_output.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                           ctypes.c_int, ctypes.c_void_p]
@@ -302,6 +307,20 @@ class GeneratorDevice:
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream().cuda_stream
             check(lib().mg_gen_upres(self.packed.data_ptr(), stage, x.data_ptr(), y.data_ptr(), B, L, stream))
+        return y
+
+    def resup(self, stage, x):
+        """ResBlock `stage` (0..2) + the next stage's LeakyReLU -> ConvTranspose1d at its tail, one kernel:
+        x [B, 256>>stage, L] -> [B, 128>>stage, S L] (S = 8 for stage 0, else 2); synchronous parity entry point."""
+        torch = self.torch
+        x = x.contiguous()
+        B, C, L = x.shape
+        if stage not in (0, 1, 2) or C != (256 >> stage):
+            raise EngineError("resup: stage 0..2 with 256>>stage channels")
+        y = torch.empty((B, C // 2, L * (8 if stage == 0 else 2)), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            check(lib().mg_gen_resup(self.packed.data_ptr(), stage, x.data_ptr(), y.data_ptr(), B, L, stream))
         return y
 
     def conv_pre(self, mel):

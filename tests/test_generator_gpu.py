@@ -64,10 +64,22 @@ def test_module_forward_matches_golden_and_stage_taps(golden, gen_module):
     torch.cuda.synchronize()
     m, l2 = rel_errors(y.cpu().numpy(), golden["gen_taps_T3_s5_audio"])
     assert m < TOL and l2 < TOL, (m, l2)
-    for which in range(4):
-        tap = gen_module._dev.stage_output(which, 1, 3).cpu().numpy()
-        m, l2 = rel_errors(tap, golden["gen_taps_T3_s5_%d" % which])
-        assert m < TOL and l2 < TOL, (which, m, l2)
+    with pytest.raises(engine.EngineError):  # the default chain never writes the ResBlock outputs to memory
+        gen_module._dev.stage_output(1, 1, 3)
+    # the per-stage taps exist in the unfused chain (one kernel per ConvT / ResBlock)
+    engine.check(engine.lib().mg_gen_set_pipeline(0))
+    try:
+        with torch.no_grad():
+            y0 = gen_module(x)
+        torch.cuda.synchronize()
+        m, l2 = rel_errors(y0.cpu().numpy(), golden["gen_taps_T3_s5_audio"])
+        assert m < TOL and l2 < TOL, (m, l2)
+        for which in range(4):
+            tap = gen_module._dev.stage_output(which, 1, 3).cpu().numpy()
+            m, l2 = rel_errors(tap, golden["gen_taps_T3_s5_%d" % which])
+            assert m < TOL and l2 < TOL, (which, m, l2)
+    finally:
+        engine.check(engine.lib().mg_gen_set_pipeline(-1))
 
 
 @pytest.mark.parametrize("B,T", [(1, 1), (1, 2), (3, 5), (1, 13), (2, 40), (1, 97)])

@@ -181,7 +181,11 @@ def test_cabi_argument_errors_are_reported_not_thrown():
     assert L.mg_gen_forward(ctypes.c_void_p(256), ctypes.c_void_p(256), ctypes.c_void_p(256), 1, 4,
                             ctypes.c_void_p(256), 16, None) == -4  # MG_ERR_WORKSPACE_TOO_SMALL
     assert L.mg_gen_kernel_name(0) == b"conv_pre" and L.mg_gen_kernel_name(99) == b""
-    assert L.mg_gen_forward_launches() == 8 and L.mg_gen_kernel_name(7) == b"up3+res3+post"
+    assert L.mg_gen_forward_launches() == 7 and L.mg_gen_kernel_name(6) == b"res3+post" and L.mg_gen_kernel_name(2) == b"res0+up1"
+    assert L.mg_gen_set_pipeline(0) == 0 and L.mg_gen_forward_launches() == 8 and L.mg_gen_kernel_name(7) == b"up3+res3+post"
+    assert L.mg_gen_set_pipeline(14) == 0 and L.mg_gen_forward_launches() == 6 and L.mg_gen_kernel_name(3) == b"res1+up2"
+    assert L.mg_gen_set_pipeline(99) == -1 and L.mg_gen_set_pipeline(-1) == 0 and L.mg_gen_forward_launches() == 7
+    assert L.mg_gen_resup(p0 := ctypes.c_void_p(256), 3, p0, ctypes.c_void_p(512), 1, 4, None) == -1  # stages 0..2 only
     # batch slices: config 2 runs as 4 chains, small or single-item batches as one
     assert [L.mg_gen_forward_slices(b, t) for b, t in ((64, 32), (40, 32), (16, 32), (1, 1000), (0, 5))] == [4, 2, 1, 1, 1]
     # the training-side entry points validate before touching the device too
@@ -268,3 +272,32 @@ def test_backward_restatement_matches_reference_gradients():
     loss_disc.backward()
     assert abs(loss_disc.item() / float(gg["loss_disc"]) - 1) < 1e-5
     check_grad_digest(gg, "dstep/D/", msd.named_parameters(), 2e-4)
+
+
+def test_mel_tables_match_the_oracle_filterbank():
+    """mg_mel_tables_build (host code of the library: window, twiddles, sparse Slaney filter bank) against oracle/mel_oracle.py."""
+    from oracle import mel_oracle as mo
+    L = engine.lib()
+    L.mg_mel_tables_bytes.restype = ctypes.c_size_t
+    n = L.mg_mel_tables_bytes()
+    for norm, onorm in ((1, 1), (0, None), (2, "l1")):
+        buf = np.zeros((n + 3) // 4, np.float32)
+        assert L.mg_mel_tables_build(22050, 80, ctypes.c_float(55), ctypes.c_float(9000), norm, buf.ctypes.data_as(ctypes.c_void_p)) == 0
+        ib = buf.view(np.int32)
+        win, tw = buf[:1024], buf[1024:2048].reshape(512, 2)
+        k = np.arange(1024)
+        assert np.abs(win - (0.5 - 0.5 * np.cos(2 * np.pi * k / 1024))).max() < 1e-7
+        assert np.abs(tw[:, 0] - np.cos(2 * np.pi * k[:512] / 1024)).max() < 1e-7 and np.abs(tw[:, 1] + np.sin(2 * np.pi * k[:512] / 1024)).max() < 1e-7
+        assert ib[2048] == 80
+        ks, kc, wo = ib[2049:2049 + 128], ib[2049 + 128:2049 + 256], ib[2049 + 256:2049 + 384]
+        wts = buf[2049 + 384:2049 + 384 + 1026]
+        dense = np.zeros((80, 513), np.float32)
+        for m in range(80):
+            dense[m, ks[m]:ks[m] + kc[m]] = wts[wo[m]:wo[m] + kc[m]]
+        ref = mo.mel_filterbank(22050, 1024, 80, 55, 9000, norm=onorm)
+        assert np.abs(dense - ref).max() <= 2e-7 * max(ref.max(), 1e-30) + 1e-9, (norm, np.abs(dense - ref).max())
+    assert L.mg_mel_tables_build(22050, 200, ctypes.c_float(55), ctypes.c_float(9000), 1, buf.ctypes.data_as(ctypes.c_void_p)) == -1
+    assert L.mg_mel_frames(8192) == 32 and L.mg_mel_frames(255) == 0 and L.mg_mel_frames(256) == 1 and L.mg_mel_frames(1000) == 3
+    from melgan_multi_b200 import meldataset
+    with pytest.raises(engine.EngineError):
+        meldataset.mel_spectrogram(torch.zeros(8192), 1024, 80, 22050, 256, 1024, 55, 9000)

@@ -121,3 +121,37 @@ def test_torch_cpu_port_matches_reference_at_config2():
         y = torch_port.generator_forward_reference(params, torch.from_numpy(synth.mel_input(64, 32, 0, realistic))).numpy()
         m, l2 = rel_errors(y, g["gen_B64_T32_s0_r%d" % int(realistic)])
         assert m < TOL and l2 < TOL, (realistic, m, l2)
+
+
+def test_mel_oracle_stft_matches_scipy_and_filterbank_properties():
+    """oracle/mel_oracle.py restates librosa (absent here; parity of this row is unpinned by any reference fixture): its STFT
+    magnitudes against scipy.signal.stft (an independent implementation), its filter bank against closed-form properties
+    of Slaney-normalised triangles on the Slaney mel scale."""
+    import scipy.signal
+    from oracle import mel_oracle as mo
+    rs = np.random.RandomState(5)
+    y = (rs.uniform(-1, 1, 8192) * 0.7).astype(np.float32)
+    yp = np.pad(y, (384, 384))
+    S = mo.stft_magnitude(yp, 1024, 256, 1024)
+    win = scipy.signal.get_window("hann", 1024, fftbins=True)
+    _, _, Z = scipy.signal.stft(yp, window=win, nperseg=1024, noverlap=768, boundary=None, padded=False, scaling="spectrum")
+    assert S.shape == (513, 32) and np.abs(S - np.abs(Z) * win.sum()).max() <= 1e-6 * S.max()
+    w = mo.mel_filterbank(22050, 1024, 80, 55, 9000, norm=1).astype(np.float64)
+    assert w.shape == (80, 513) and (w >= 0).all() and ((w > 0).sum(axis=0) <= 2).all()
+    freqs = np.linspace(0, 11025, 513)
+    edges = mo.mel_to_hz(np.linspace(mo.hz_to_mel(55), mo.hz_to_mel(9000), 82))
+    assert abs(mo.hz_to_mel(1000.0) - 15.0) < 1e-12 and abs(mo.mel_to_hz(mo.hz_to_mel(4321.0)) - 4321.0) < 1e-9
+    for m in (0, 17, 40, 79):
+        nz = np.nonzero(w[m])[0]
+        assert edges[m] < freqs[nz[0]] and freqs[nz[-1]] < edges[m + 2]           # support = (f_m, f_m+2)
+        assert abs(freqs[w[m].argmax()] - edges[m + 1]) <= 11025 / 512              # peak at the centre frequency
+        assert w[m].max() <= 2.0 / (edges[m + 2] - edges[m]) + 1e-12                # Slaney: triangle of unit AREA in Hz
+    wide = [m for m in range(80) if edges[m + 2] - edges[m] > 150]
+    area = (w[wide].sum(axis=1) * (11025 / 512))
+    assert np.abs(area - 1).max() < 0.05
+    un = mo.mel_filterbank(22050, 1024, 80, 55, 9000, norm=None)
+    inner = (freqs > edges[1]) & (freqs < edges[80])
+    assert np.abs(un[:, inner].sum(axis=0) - 1).max() < 1e-5                         # un-normalised triangles partition unity
+    out = mo.mel_spectrogram(y)
+    assert out.shape == (80, 32) and np.isfinite(out).all()
+    assert np.allclose(mo.mel_spectrogram(np.zeros(4096, np.float32)), np.log(1e-5))  # silence sits on the clip floor

@@ -76,6 +76,30 @@ def test_convt_tc_matches_oracle(state, dev, stage, B, L):
     assert m < TOL and l2 < TOL, (stage, B, L, m, l2)
 
 
+@pytest.mark.parametrize("stage,B,L", [(2, 2, 500), (2, 1, 1), (2, 1, 223), (2, 1, 224), (2, 3, 447), (2, 1, 4096),
+                                       (1, 2, 300), (1, 1, 2), (1, 1, 222), (1, 1, 223), (1, 2, 2048),
+                                       (0, 1, 3), (0, 2, 128), (0, 1, 129), (0, 3, 256), (0, 1, 223), (0, 2, 224), (0, 1, 600),
+                                       (0, 64, 256)])
+def test_resblock_with_tail_convt_matches_oracle(state, dev, stage, B, L):
+    """ResBlock `stage` + the NEXT stage's LeakyReLU -> ConvTranspose1d fused at its tail (what the default pipeline runs:
+    res0+up1, res1+up2, res2+up3) against the oracle's ResBlock followed by its conv_transpose1d.  Lengths straddle the tile
+    borders of the tail-fused tiling (one more halo row on the left, position L owned by the last tile) and, for stage 0, the
+    single-CTA / CTA-pair switch at 128."""
+    C = 256 >> stage
+    S, pad = (8, 4) if stage == 0 else (2, 1)
+    rs = np.random.RandomState(9000 + 100 * stage + L + B)
+    x = rs.standard_normal((B, C, L)).astype(np.float32)
+    h = oracle_resblock(state, stage, x)
+    name = "ups.%d" % (stage + 1)
+    w = cport.fold_weight_norm(state[name + ".weight_g"], state[name + ".weight_v"])
+    lr = np.where(h > 0, h, h * np.float32(0.01)).astype(np.float32)
+    ref = cport.conv_transpose1d(lr, w, state[name + ".bias"], S, pad)
+    y = dev.resup(stage, torch.from_numpy(x).cuda()).cpu().numpy()
+    assert y.shape == ref.shape
+    m, l2 = rel_errors(y, ref)
+    assert m < TOL and l2 < TOL, (stage, B, L, m, l2)
+
+
 @pytest.mark.parametrize("stage,B,Lin", [(2, 2, 500), (2, 1, 1), (2, 1, 64), (2, 3, 129), (2, 1, 2048), (3, 2, 1050), (3, 1, 1),
                                          (3, 1, 128), (3, 1, 255), (3, 2, 256), (3, 1, 4096)])
 def test_fused_convt_resblock_matches_oracle(state, dev, stage, B, Lin):
