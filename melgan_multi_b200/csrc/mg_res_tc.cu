@@ -20,7 +20,9 @@
 //
 // Warp roles: NEPI/32 epilogue warps (TMEM -> registers -> bias/LeakyReLU/mask/split -> X), one TMA producer
 // warp, NIW MMA issuer warps (each runs its loop warp-uniform and one elected lane issues tcgen05.mma for its blocks).
+#include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "mg_common.cuh"
 #include "mg_tc.cuh"
@@ -57,8 +59,14 @@ using namespace tc;
 // whole extra tile exactly where sequences are a multiple of the tile (stage 0 at T = 32: 256 positions = one CTA pair), so
 // those pad * C/2 outputs -- dot products of x[L-1] with the tap-1 weights -- are computed in fp32 by the CTA that owns
 // position L - 1 (fix-up at the end of the epilogue).
-template <int C_, int NBLK_, int NSTAGE_, int NWG_, int MINB_, bool POST_ = false, bool UPF_ = false, int CL_ = 1, int UPT_ = 0>
+// TMA = true: the input tile arrives by tensor-map TMA (cp.async.bulk.tensor.3d) instead of per-thread strided loads: the
+// producer streams [LCH channels][P positions] fp32 slabs of x through the (still idle) weight-ring slots, positions past
+// the end of the sequence zero-filled by the copy engine; the epilogue warps turn each slab into R (TMEM) and
+// X = split(lrelu(x)) as it lands.  Needs L % 4 == 0 (16-byte global strides); the launcher falls back otherwise.
+template <int C_, int NBLK_, int NSTAGE_, int NWG_, int MINB_, bool POST_ = false, bool UPF_ = false, int CL_ = 1, int UPT_ = 0,
+          bool TMA_ = false>
 struct RbCfg {
+    static constexpr bool TMA = TMA_;
     static constexpr int CL = CL_;
     static constexpr int UPT = UPT_;
     static constexpr bool UPF = UPF_;
@@ -70,7 +78,9 @@ struct RbCfg {
     // zero rows either side of X (dilation-9 taps reach 9 rows out); 12 lets two C = 128 single-block CTAs share an SM
     static constexpr int SLACK = (C_ == 128 && NBLK_ == 1) ? 12 : 16;
     static constexpr int HALO = 16 + (POST ? 3 : 0);  // 1+1+3+1+9+1 (+3 for the fused k7 conv_post)
-    static constexpr int HL = HALO + (UPT_ ? 1 : 0);  // left halo: a fused tail ConvT also reads x[s - 1]
+    // left halo: a fused tail ConvT also reads x[s - 1]; with tensor-map input the tile origin must stay a multiple of 4
+    // positions (the copy engine wants 16-byte aligned box starts: an origin of 223 is an illegal instruction), so 4 rows
+    static constexpr int HL = HALO + (UPT_ ? (TMA_ ? 4 : 1) : 0);
     static constexpr int PVALID = P - HALO - HL;
     static constexpr int ROWS = P + 2 * SLACK;
     static constexpr int XPITCH = ROWS * 16;  // bytes between k-panels
@@ -105,7 +115,11 @@ struct RbCfg {
     static constexpr int TSLOT = UPT == 8 ? 16384 : 128 * UPT * TNG, TNSLOT = UPT ? TNCG * (C / 16) * (UPT == 8 ? 2 : 1) : 0;
     static_assert(UPT == 0 || ((UPT == 2 || UPT == 8) && TN == C && TSLOT <= CHUNK && !POST_ && !UPF_), "tail ConvT shape");
     static_assert(UPT != 8 || (NBLK == 1 && TCOLS == 512), "stride-8 tail ConvT double-buffers its accumulators in the 512 columns");
-    static constexpr int SMEM_BYTES = 2 * XBYTES + NSTAGE * CHUNK + 2 * C * 4 + (2 * NSTAGE + 1 + NH + 4) * 8 + 16;
+    // TMA input slabs: LCH channels x P positions x 4 B = one ring slot; unit = (128-row block, 8-channel k-panel) of a slab
+    static constexpr int LCH = CHUNK / (P * 4), NSLAB = TMA ? C / (LCH > 0 ? LCH : 1) : 0, LUNITS = NBLK * (LCH / 8);
+    static_assert(!TMA || (LCH >= 8 && LCH % 8 == 0 && LCH * P * 4 == CHUNK && LUNITS % NWG == 0 && !UPF_ && P <= 256 &&
+                           (C / NH) % LCH == 0 && (CL == 1 || LUNITS == NWG)), "TMA input slabs");
+    static constexpr int SMEM_BYTES = 2 * XBYTES + NSTAGE * CHUNK + 2 * C * 4 + (2 * NSTAGE + 1 + NH + 4 + 2 * NSTAGE + 1) * 8 + 16;
     static_assert(KSL % NH == 0 && (CW / NH) % 32 == 0 && (NH == 1 || ITEMS == NWG), "hand-off split");
     // fused ConvT: input rows s = o/2 - 1 .. o/2 + P/2 of 2C channels (2 KP k-panels), NCB blocks of 128 output pairs
     static constexpr int UROWS = P / 2 + 2, UPITCH = UROWS * 16, NCB = NBLK / 2, UKSL = 2 * C / KC, NUPCH = UPF ? 4 * UKSL : 0;
@@ -160,7 +174,7 @@ __device__ __forceinline__ void store_x16_push(uint8_t *Xh, uint8_t *Xl, int xpi
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB)
 resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const float *__restrict__ packed, int stage, int L,
-                   int *__restrict__ status, long long *__restrict__ trace) {
+                   int *__restrict__ status, long long *__restrict__ trace, const __grid_constant__ CUtensorMap xmap) {
     constexpr int C = Cfg::C, NBLK = Cfg::NBLK, P = Cfg::P, SLACK = Cfg::SLACK, HALO = Cfg::HALO;
     constexpr int XPITCH = Cfg::XPITCH, XBYTES = Cfg::XBYTES, KC = Cfg::KC, CHUNK = Cfg::CHUNK, NSTAGE = Cfg::NSTAGE;
     constexpr int NEPI = Cfg::NEPI, NWG = Cfg::NWG, PARTS = Cfg::PARTS, CW = Cfg::CW, ITEMS = Cfg::ITEMS, NIW = Cfg::NIW;
@@ -174,7 +188,10 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
     uint64_t *xready = done + 1;  // [NH]: X channels [h*C/NH, (h+1)*C/NH) of the next conv are written (all epilogue threads arrive)
     uint64_t *dup = xready + Cfg::NH;  // [2] tail ConvT (stride 8): accumulator buffer complete;  tfree[2]: drained by the epilogue
     uint64_t *tfree = dup + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tfree + 2);
+    uint64_t *lfull = tfree + 2;        // [NSTAGE] TMA input slab landed in ring slot s;  lempty[NSTAGE]: converted by every epilogue warp
+    uint64_t *lempty = lfull + NSTAGE;
+    uint64_t *rfree = lempty + NSTAGE;  // pair: both CTAs' input slabs are consumed, the leader may multicast weights into both rings
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(rfree + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.y;
@@ -209,6 +226,8 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
         mbar_init(done, NIW * CL);
         for (int h = 0; h < Cfg::NH; ++h) mbar_init(&xready[h], Cfg::XARRIVE);
         for (int k = 0; k < 2; ++k) { mbar_init(&dup[k], NIW * CL); mbar_init(&tfree[k], NEPI); }
+        for (int k = 0; k < NSTAGE; ++k) { mbar_init(&lfull[k], 1); mbar_init(&lempty[k], NEPI / 32); }
+        mbar_init(rfree, CL);
         fence_mbar_init();
     }
     for (int h = 0; h < Cfg::NH; ++h) rxready[h] = CL > 1 ? mapa_shared(smem_u32(&xready[h]), peer) : 0u;
@@ -236,6 +255,24 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
         if (lane == 0) {
             int s = 0, ph = 0;
             bool ok = true;
+            if constexpr (Cfg::TMA) {
+                // ---- the input tile, LCH channels at a time, through the ring slots (weights follow once they are free again)
+                tma_prefetch_desc(&xmap);
+                pdl_wait();  // x is the previous kernel's output
+                for (int k = 0; k < Cfg::NSLAB && ok; ++k) {
+                    const int sl = k % NSTAGE;
+                    if (k >= NSTAGE && !mbar_wait(&lempty[sl], ((k / NSTAGE) - 1) & 1)) { ok = false; break; }
+                    mbar_arrive_expect_tx(&lfull[sl], CHUNK);
+                    tma_load_3d(ring + sl * CHUNK, &xmap, o, k * Cfg::LCH, b, &lfull[sl]);
+                }
+                for (int k = Cfg::NSLAB > NSTAGE ? Cfg::NSLAB - NSTAGE : 0; k < Cfg::NSLAB && ok; ++k)  // every slot consumed
+                    if (!mbar_wait(&lempty[k % NSTAGE], (k / NSTAGE) & 1)) ok = false;
+                if constexpr (CL > 1) {  // ... in BOTH CTAs, before the leader's multicast copies land in both rings
+                    mbar_arrive(rfree);
+                    mbar_arrive_cluster(mapa_shared(smem_u32(rfree), peer));
+                    if (ok && !mbar_wait_cluster(rfree, 0)) ok = false;
+                }
+            }
             if constexpr (Cfg::UPF) {  // the fused ConvT's 4 taps x 2 K-slices, in blob order
                 const uint8_t *src = tc_base + tc_upf_offset(stage);
                 for (int i = 0; i < Cfg::NUPCH && ok; ++i) {
@@ -585,6 +622,57 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
             fence_proxy_async();
             tc_fence_before();
             mbar_arrive(&xready[0]);  // phase 1: conv 0 may start
+        } else if constexpr (Cfg::TMA) {
+        // ---- the input tile arrives slab by slab (tensor-map TMA, see the producer): R <- x (fp32, exact), X <- split(lrelu(x)).
+        // A slab is [LCH channels][P positions] fp32; warpgroup g converts the units (block, 8-channel panel) g, g + NWG, ...;
+        // lane = position, so the eight reads of a unit are conflict-free and its two 16-byte X stores are the usual ones.
+        constexpr int LCH = Cfg::LCH, LUNITS = Cfg::LUNITS;
+        bool lok = true;
+#pragma unroll 1
+        for (int k = 0; k < Cfg::NSLAB; ++k) {
+            const int sl = k % NSTAGE;
+            if (lok && !mbar_wait(&lfull[sl], (k / NSTAGE) & 1)) { lok = false; if (lane == 0) atomicExch(status, 9); }
+            const float *slab = reinterpret_cast<const float *>(ring + sl * CHUNK);
+#pragma unroll
+            for (int u = wg; u < LUNITS; u += NWG) {
+                const int blk = u % NBLK, j = u / NBLK;
+                const int p = blk * 128 + row, c0 = k * LCH + 8 * j;
+                uint32_t w[8];
+                float f[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    w[e] = __float_as_uint(slab[(8 * j + e) * P + p]);
+                    f[e] = lrelu(__uint_as_float(w[e]));
+                }
+                tmem_st8(lane_addr + blk * 2 * C + c0, w);
+                uint32_t h[4], l[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) split2_bf16(f[2 * e], f[2 * e + 1], h[e], l[e]);
+                const int poff = (c0 >> 3) * XPITCH;
+                *reinterpret_cast<uint4 *>(Xh + poff + (p + SLACK) * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4 *>(Xl + poff + (p + SLACK) * 16) = make_uint4(l[0], l[1], l[2], l[3]);
+                if constexpr (CL > 1) {
+                    if (rank == 0 ? p >= P - Cfg::BND : p < Cfg::BND) {  // boundary row: mirror into the peer's slack rows
+                        const uint32_t po = (uint32_t)(poff + (rank == 0 ? p - (P - Cfg::BND) : SLACK + P + p) * 16);
+                        st_cluster_v4(rxh + po, make_uint4(h[0], h[1], h[2], h[3]));
+                        st_cluster_v4(rxl + po, make_uint4(l[0], l[1], l[2], l[3]));
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&lempty[sl]);  // this warp is done reading the slot
+            if ((k + 1) * LCH % (C / NH) == 0) {      // a channel half (or everything) of conv 0's input is in place
+                const int h = (k + 1) * LCH / (C / NH) - 1;
+                tmem_st_wait();
+                if constexpr (CL > 1) fence_proxy_async_all(); else fence_proxy_async();
+                tc_fence_before();
+                mbar_arrive(&xready[h]);
+                if constexpr (CL > 1) {  // (LUNITS == NWG: every thread converts exactly one unit per slab, so a boundary-row thread
+                                         //  accounts for one of the BND * PARTS remote arrivals its peer's barrier expects)
+                    if (rank == 0 ? row >= P - Cfg::BND : row < Cfg::BND) mbar_arrive_cluster(rxready[h]);
+                }
+            }
+        }
         } else {
         // ---- load the input tile: R <- x (fp32, exact), X <- split(lrelu(x))
         // an item (blk, part) owns, in every channel half h, the CH = CW/NH columns  h*C/NH + part*CH .. + CH
@@ -871,6 +959,40 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
     if constexpr (CL > 1) cluster_sync();  // nobody leaves while the peer may still multicast into its ring or arrive on its barriers
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+static bool tma_disabled() {
+    static const bool off = [] { const char *e = getenv("MG_RES_TMA"); return e && e[0] == '0'; }();
+    return off;
+}
+// can x [B][C][L] fp32 be described by a tensor map? (16-byte aligned base and row stride)
+static bool tma_input_ok(const float *x, int L) {
+    return !tma_disabled() && (L % 4) == 0 && ((uintptr_t)x % 16) == 0 && encode_tiled_fn() != nullptr;
+}
+// x as a 3-D tensor (L, C, B) with boxes of (P positions, LCH channels, 1 item); out-of-bounds positions read as zero
+static int make_input_map(CUtensorMap *m, const float *x, int B, int C, int L, int P, int LCH) {
+    const cuuint64_t dims[3] = {(cuuint64_t)L, (cuuint64_t)C, (cuuint64_t)B};
+    const cuuint64_t strides[2] = {(cuuint64_t)L * 4, (cuuint64_t)L * C * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)P, (cuuint32_t)LCH, 1}, estr[3] = {1, 1, 1};
+    const CUresult r = encode_tiled_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(x), dims, strides, box, estr,
+                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(MG_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for [%d][%d][%d]", (int)r, B, C, L);
+    return MG_OK;
+}
+
 template <class Cfg>
 static int launch_resblock(const float *x, float *y, const float *packed, int stage, int B, int L, int *status,
                            long long *trace, cudaStream_t s) {
@@ -882,14 +1004,21 @@ static int launch_resblock(const float *x, float *y, const float *packed, int st
     constexpr int PS = Cfg::CL * Cfg::P, PVS = PS - Cfg::HALO - Cfg::HL;  // edge-aware tiling in super-tiles of CL tiles, see the kernel
     const int Lc = L;
     const int ntiles = 1 + (Lc > PS ? (Lc - PS + PVS - 1) / PVS : 0);
+    CUtensorMap xmap;
+    memset(&xmap, 0, sizeof(xmap));
+    if constexpr (Cfg::TMA) {
+        int rc = make_input_map(&xmap, x, B, Cfg::C, L, Cfg::P, Cfg::LCH);
+        if (rc) return rc;
+    }
     MG_CUDA_TRY(launch_ex(resblock_tc_kernel<Cfg>, dim3(ntiles * Cfg::CL, B), dim3(Cfg::NT), Cfg::SMEM_BYTES, s, Cfg::CL, true, x, y,
-                          packed, stage, L, status, trace));
+                          packed, stage, L, status, trace, xmap));
     return MG_OK;
 }
 
 // x, y: [B][C][L] fp32 NCL with C = 256 >> stage; status: device int, set non-zero if a pipeline wait timed out.
 int launch_resblock_tc(const float *x, float *y, const float *packed, int stage, int B, int L, int *status, cudaStream_t s,
                        long long *trace) {
+    const bool tma = tma_input_ok(x, L);  // input tile by tensor-map TMA (needs 16-byte aligned rows), else per-thread loads
     switch (stage) {
         //                                       C  NBLK NSTAGE NWG MINB
         // (C = 256 is paced by its 4-slot weight ring -- 3 slots: 204 us, 4: 184 us -- but a fifth 16 KB slot only fits if the
@@ -898,14 +1027,21 @@ int launch_resblock_tc(const float *x, float *y, const float *packed, int stage,
         // L > 128: CTA pairs sharing a 256-position super-tile (no halo between the two; multicast weights).  MG_RES0_PAIR=0: A/B.
         case 0: {
             static const bool pair = [] { const char *e = getenv("MG_RES0_PAIR"); return !(e && e[0] == '0'); }();
-            if (pair && L > 128) return launch_resblock<RbCfg<256, 1, 4, 4, 1, false, false, 2>>(x, y, packed, stage, B, L, status, trace, s);
-            return launch_resblock<RbCfg<256, 1, 4, 4, 1>>(x, y, packed, stage, B, L, status, trace, s);
+            if (pair && L > 128)
+                return tma ? launch_resblock<RbCfg<256, 1, 4, 4, 1, false, false, 2, 0, true>>(x, y, packed, stage, B, L, status, trace, s)
+                           : launch_resblock<RbCfg<256, 1, 4, 4, 1, false, false, 2>>(x, y, packed, stage, B, L, status, trace, s);
+            return tma ? launch_resblock<RbCfg<256, 1, 4, 4, 1, false, false, 1, 0, true>>(x, y, packed, stage, B, L, status, trace, s)
+                       : launch_resblock<RbCfg<256, 1, 4, 4, 1>>(x, y, packed, stage, B, L, status, trace, s);
         }
         // (C = 128 as two single-block CTAs per SM, RbCfg<128, 1, 2, 2, 2>: measured 244 us vs 213 us at config 2 -- the
         //  25 % halo recompute and the two-slot weight rings cost more than the overlap buys)
-        case 1: return launch_resblock<RbCfg<128, 2, 4, 4, 1>>(x, y, packed, stage, B, L, status, trace, s);
+        case 1:
+            return tma ? launch_resblock<RbCfg<128, 2, 4, 4, 1, false, false, 1, 0, true>>(x, y, packed, stage, B, L, status, trace, s)
+                       : launch_resblock<RbCfg<128, 2, 4, 4, 1>>(x, y, packed, stage, B, L, status, trace, s);
         // (3 CTAs/SM with half-size tiles was measured slower for C = 64 / 32: the extra halo recompute outweighs the overlap)
-        case 2: return launch_resblock<RbCfg<64, 2, 2, 2, 2>>(x, y, packed, stage, B, L, status, trace, s);
+        case 2:
+            return tma ? launch_resblock<RbCfg<64, 2, 2, 2, 2, false, false, 1, 0, true>>(x, y, packed, stage, B, L, status, trace, s)
+                       : launch_resblock<RbCfg<64, 2, 2, 2, 2>>(x, y, packed, stage, B, L, status, trace, s);
         // (C = 32 with the two A = hi(x) passes merged into one N = 64 MMA against [w hi | w lo] -- 4C TMEM columns per
         //  block, so NBLK = 2: measured 184 us vs 142 us; this stage is bound by its epilogue, which then reads twice the
         //  accumulator columns, not by the A-operand re-reads the merge saves)
@@ -916,10 +1052,17 @@ int launch_resblock_tc(const float *x, float *y, const float *packed, int stage,
         // [B][2C][L/2] (L stays the output length)
         // 20 / 21 / 22 = ResBlock 0 / 1 / 2 with the NEXT stage's LeakyReLU -> ConvT at its tail: y is [B][C/2][S L]
         case 20:
-            if (L > 128) return launch_resblock<RbCfg<256, 1, 4, 4, 1, false, false, 2, 8>>(x, y, packed, 0, B, L, status, trace, s);
-            return launch_resblock<RbCfg<256, 1, 4, 4, 1, false, false, 1, 8>>(x, y, packed, 0, B, L, status, trace, s);
-        case 21: return launch_resblock<RbCfg<128, 2, 4, 4, 1, false, false, 1, 2>>(x, y, packed, 1, B, L, status, trace, s);
-        case 22: return launch_resblock<RbCfg<64, 2, 2, 2, 2, false, false, 1, 2>>(x, y, packed, 2, B, L, status, trace, s);
+            if (L > 128)
+                return tma ? launch_resblock<RbCfg<256, 1, 4, 4, 1, false, false, 2, 8, true>>(x, y, packed, 0, B, L, status, trace, s)
+                           : launch_resblock<RbCfg<256, 1, 4, 4, 1, false, false, 2, 8>>(x, y, packed, 0, B, L, status, trace, s);
+            return tma ? launch_resblock<RbCfg<256, 1, 4, 4, 1, false, false, 1, 8, true>>(x, y, packed, 0, B, L, status, trace, s)
+                       : launch_resblock<RbCfg<256, 1, 4, 4, 1, false, false, 1, 8>>(x, y, packed, 0, B, L, status, trace, s);
+        case 21:
+            return tma ? launch_resblock<RbCfg<128, 2, 4, 4, 1, false, false, 1, 2, true>>(x, y, packed, 1, B, L, status, trace, s)
+                       : launch_resblock<RbCfg<128, 2, 4, 4, 1, false, false, 1, 2>>(x, y, packed, 1, B, L, status, trace, s);
+        case 22:
+            return tma ? launch_resblock<RbCfg<64, 2, 2, 2, 2, false, false, 1, 2, true>>(x, y, packed, 2, B, L, status, trace, s)
+                       : launch_resblock<RbCfg<64, 2, 2, 2, 2, false, false, 1, 2>>(x, y, packed, 2, B, L, status, trace, s);
         case 12: return launch_resblock<RbCfg<64, 2, 2, 2, 2, false, true>>(x, y, packed, 2, B, L, status, trace, s);
         case 13: return launch_resblock<RbCfg<32, 4, 4, 2, 2, false, true>>(x, y, packed, 3, B, L, status, trace, s);
         case 14: return launch_resblock<RbCfg<32, 4, 4, 2, 2, true, true>>(x, y, packed, 3, B, L, status, trace, s);
