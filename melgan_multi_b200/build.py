@@ -63,6 +63,7 @@ def build(force=False, verbose=False, extra=()):
     if not force and not needs_build():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
+    extra = list(extra) + os.environ.get("MG_NVCC_EXTRA", "").split()
     _run([_nvcc()] + NVCC_FLAGS + list(extra) + ["-o", TEST_LIB] + test_sources(), False)
     cmd = [_nvcc()] + NVCC_FLAGS + list(extra) + ["-o", LIB] + sources()
     _run(cmd, verbose)

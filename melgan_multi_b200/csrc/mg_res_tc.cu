@@ -103,9 +103,16 @@ struct RbCfg {
     // X is handed to the MMA warps in NH channel halves: the next conv starts on input channels [0, C/NH) while the
     // epilogue is still writing the rest (K-slice order of the weight chunks follows).  Each epilogue thread owns CW/NH
     // columns of every half.
-    // (measured: -5 % per conv at C = 128; at C = 256 the early MMAs and the epilogue's stores fight for shared-memory
-    //  bandwidth and it is a wash, so that stage keeps the single hand-off)
-    static constexpr int NH = (C == 128) ? 2 : 1;
+    // (measured at config 2: C = 128 with 2 hand-offs -5 % per conv, with 4 another -2 % (209 -> 205 us); at C = 256 the early
+    //  MMAs and the epilogue's stores fight for shared-memory bandwidth: 2 hand-offs are a wash, 4 cost 4 %, so that stage
+    //  keeps the single hand-off.  -DMG_NH128 / -DMG_NH256 override for A/B builds, scripts/gpu_nh.sh)
+#ifndef MG_NH128
+#define MG_NH128 4
+#endif
+#ifndef MG_NH256
+#define MG_NH256 1
+#endif
+    static constexpr int NH = (C == 128) ? MG_NH128 : (C == 256) ? MG_NH256 : 1;
     static constexpr int BND = SLACK;  // boundary rows pushed to the peer CTA (CL = 2); the widest tap reaches 9
     static constexpr int XARRIVE = NEPI + (CL > 1 ? BND * PARTS : 0);  // xready arrivals: local epilogue threads + the peer's boundary threads
     static_assert(CL == 1 || (CL == 2 && !UPF_ && !POST_), "CTA pairs: plain ResBlock only");
@@ -120,7 +127,7 @@ struct RbCfg {
     static_assert(!TMA || (LCH >= 8 && LCH % 8 == 0 && LCH * P * 4 == CHUNK && LUNITS % NWG == 0 && !UPF_ && P <= 256 &&
                            (C / NH) % LCH == 0 && (CL == 1 || LUNITS == NWG)), "TMA input slabs");
     static constexpr int SMEM_BYTES = 2 * XBYTES + NSTAGE * CHUNK + 2 * C * 4 + (2 * NSTAGE + 1 + NH + 4 + 2 * NSTAGE + 1) * 8 + 16;
-    static_assert(KSL % NH == 0 && (CW / NH) % 32 == 0 && (NH == 1 || ITEMS == NWG), "hand-off split");
+    static_assert(KSL % NH == 0 && (CW / NH) % 16 == 0 && (NH == 1 || ITEMS == NWG), "hand-off split");
     // fused ConvT: input rows s = o/2 - 1 .. o/2 + P/2 of 2C channels (2 KP k-panels), NCB blocks of 128 output pairs
     static constexpr int UROWS = P / 2 + 2, UPITCH = UROWS * 16, NCB = NBLK / 2, UKSL = 2 * C / KC, NUPCH = UPF ? 4 * UKSL : 0;
     static constexpr int SPITCH = P + 4;  // floats between channels of the fp32 staging buffer [C][P]
@@ -756,29 +763,29 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
                     const bool push = CL > 1 && (rank == 0 ? p >= P - Cfg::BND : p < Cfg::BND);
                     const int prow = (rank == 0 ? p - (P - Cfg::BND) : SLACK + P + p) * 16;
                     nb += push;
+                    constexpr int EW = CH >= 32 ? 32 : 16;  // columns per TMEM read
 #pragma unroll 1
-                    for (int c0 = cbeg; c0 < cbeg + CH; c0 += 32) {
-                        uint32_t v[32];
-                        float f[32];
-                        tmem_ld32(lane_addr + blk * 2 * C + scol + c0, v);
+                    for (int c0 = cbeg; c0 < cbeg + CH; c0 += EW) {
+                        uint32_t v[EW];
+                        float f[EW];
+                        if constexpr (EW == 32) tmem_ld32(lane_addr + blk * 2 * C + scol + c0, v);
+                        else tmem_ld16(lane_addr + blk * 2 * C + scol + c0, v);
                         tmem_ld_wait();
                         if (interior) {  // whole tile inside [0, L): no zero-padding mask needed (CTA-uniform branch)
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) f[j] = lrelu(__uint_as_float(v[j]) + bsrc[c0 + j]);
+                            for (int j = 0; j < EW; ++j) f[j] = lrelu(__uint_as_float(v[j]) + bsrc[c0 + j]);
                         } else {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) f[j] = inr ? lrelu(__uint_as_float(v[j]) + bsrc[c0 + j]) : 0.f;
+                            for (int j = 0; j < EW; ++j) f[j] = inr ? lrelu(__uint_as_float(v[j]) + bsrc[c0 + j]) : 0.f;
                         }
                         if (Cfg::UPT != 0 && conv == 5 && t == L - 1) {  // lrelu(x[L-1]) in fp32 for the fix-up (b1s is free now)
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) b1s[c0 + j] = f[j];
+                            for (int j = 0; j < EW; ++j) b1s[c0 + j] = f[j];
                         }
-                        if constexpr (CL > 1) {
-                            store_x16_push(Xh, Xl, XPITCH, c0, (p + SLACK) * 16, f, push, rxh, rxl, prow);
-                            store_x16_push(Xh, Xl, XPITCH, c0 + 16, (p + SLACK) * 16, f + 16, push, rxh, rxl, prow);
-                        } else {
-                            store_x16(Xh, Xl, XPITCH, c0, (p + SLACK) * 16, f);
-                            store_x16(Xh, Xl, XPITCH, c0 + 16, (p + SLACK) * 16, f + 16);
+#pragma unroll
+                        for (int e0 = 0; e0 < EW; e0 += 16) {
+                            if constexpr (CL > 1) store_x16_push(Xh, Xl, XPITCH, c0 + e0, (p + SLACK) * 16, f + e0, push, rxh, rxl, prow);
+                            else store_x16(Xh, Xl, XPITCH, c0 + e0, (p + SLACK) * 16, f + e0);
                         }
                     }
                 }
