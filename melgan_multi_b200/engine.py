@@ -403,12 +403,17 @@ def loss_forward(a, b, modes):
     return out
 
 
-def loss_backward(a, b, modes, grad_out, need_b):
-    """Gradients of the row means w.r.t. a (and b where need_b[i] and the row is an L1 pair), scaled by grad_out [rows]."""
+def loss_backward(a, b, modes, grad_out, need_b, out_a=None, out_b=None):
+    """Gradients of the row means w.r.t. a (and b where need_b[i] and the row is an L1 pair), scaled by grad_out [rows].
+    out_a / out_b: optional preallocated contiguous tensors to write into (e.g. the two halves of one stacked buffer)."""
     import torch
     dev, keep_a, keep_b, n, md, pa, pb = _loss_tables(a, b, modes)
-    ga = [torch.empty_like(t) for t in keep_a]
-    gb = [torch.empty_like(u) if (u is not None and nb) else None for u, nb in zip(keep_b, need_b)]
+    ga = list(out_a) if out_a is not None else [torch.empty_like(t) for t in keep_a]
+    gb = (list(out_b) if out_b is not None else
+          [torch.empty_like(u) if (u is not None and nb) else None for u, nb in zip(keep_b, need_b)])
+    for t in ga + [u for u in gb if u is not None]:
+        if not t.is_contiguous():
+            raise EngineError("loss_backward: output gradients must be contiguous")
     pga = _ptr_array([t.data_ptr() for t in ga])
     pgb = _ptr_array([t.data_ptr() if t is not None else 0 for t in gb])
     grad_out = grad_out.to(device=dev, dtype=torch.float32).contiguous()

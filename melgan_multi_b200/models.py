@@ -70,27 +70,35 @@ def _layer_modules(gen):
 
 
 class _GeneratorFunction(torch.autograd.Function):
-    """Forward on the fused sm_100a kernels; backward by recomputation through stock PyTorch ops
-    (open row: native backward).  Inputs: mel, then 30 x (weight_v, weight_g, bias)."""
+    """Forward on the fused sm_100a kernels; backward by recomputation through stock PyTorch ops (open row: native
+    backward).  The recomputation -- 30 convs forward, their backward, weight-norm: ~600 launches that cost the host more
+    than the GPU -- is captured ONCE per input shape as a pair of CUDA graphs (torch.cuda.make_graphed_callables) and
+    replayed, so the step is no longer bound by eager launch overhead (MG_GEN_BWD_GRAPH=0: eager).
+    Inputs: mel, then 30 x (weight_v, weight_g, bias)."""
 
     @staticmethod
     def forward(ctx, gen, mel, *params):
         ctx.gen = gen
         ctx.save_for_backward(mel, *params)
+        ctx.graphed = gen._graphed_recompute(mel, params)  # built here (not inside backward): capture needs a quiet device
         return gen._engine_forward(mel)
 
     @staticmethod
     def backward(ctx, grad_out):
         gen = ctx.gen
         mel, *params = ctx.saved_tensors
+        need_mel = ctx.needs_input_grad[1]
         with torch.enable_grad():
-            mel_ = mel.detach().requires_grad_(ctx.needs_input_grad[1])
+            mel_ = mel.detach().requires_grad_(need_mel)
             leaves = [p.detach().requires_grad_(True) for p in params]
-            y = gen._torch_forward(mel_, leaves)
-            wanted = ([mel_] if ctx.needs_input_grad[1] else []) + leaves
-            grads = torch.autograd.grad(y, wanted, grad_out, allow_unused=True)
+            if ctx.graphed is not None and need_mel == ctx.graphed[1]:
+                y = ctx.graphed[0](mel_, *leaves)
+            else:
+                y = gen._torch_forward(mel_, leaves)
+            wanted = ([mel_] if need_mel else []) + leaves
+            grads = torch.autograd.grad(y, wanted, grad_out.contiguous(), allow_unused=True)
         grads = list(grads)
-        gmel = grads.pop(0) if ctx.needs_input_grad[1] else None
+        gmel = grads.pop(0) if need_mel else None
         return (None, gmel, *grads)
 
 
@@ -131,6 +139,27 @@ class Generator(nn.Module):
 
     def _engine_forward(self, mel):
         return self._ensure_packed().forward(mel)
+
+    def _graphed_recompute(self, mel, params):
+        """(graphed stock-op forward+backward, mel_requires_grad) for this input shape, or None.  Cached per shape / dtype
+        policy; the graphs own static copies of nothing but activations -- parameters are call arguments."""
+        import os
+        if os.environ.get("MG_GEN_BWD_GRAPH", "1") == "0" or torch.cuda.is_current_stream_capturing():
+            return None
+        need_mel = bool(mel.requires_grad)
+        key = (tuple(mel.shape), mel.device, need_mel, torch.backends.cudnn.conv.fp32_precision, torch.backends.cudnn.benchmark)
+        cache = self.__dict__.setdefault("_bwd_graphs", {})
+        if key not in cache:
+            if len(cache) >= 4:  # shapes keep changing (e.g. whole-utterance validation): stay eager for new ones
+                return None
+            sample = [mel.detach().clone().requires_grad_(need_mel)] + [p.detach().clone().requires_grad_(True) for p in params]
+            try:
+                with torch.enable_grad():  # (we are inside autograd.Function.forward, where grad mode is off)
+                    fn = torch.cuda.make_graphed_callables(lambda m, *leaves: self._torch_forward(m, list(leaves)), tuple(sample))
+            except Exception:  # capture refused (e.g. allocator / library state): the eager recompute still works
+                fn = None
+            cache[key] = fn
+        return (cache[key], need_mel) if cache[key] is not None else None
 
     # -- stock-PyTorch restatement, used ONLY to differentiate (backward) ---------------------
     def _torch_forward(self, x, leaves):
@@ -343,12 +372,22 @@ class MultiScaleDiscriminator(nn.Module):
                 fmaps.append(list(_MSDFunction.apply(self, s, cache, y2, *flat)))
         else:
             fmaps = self._engine_forward(y2)
+        # The reference's four lists.  Every element is an ordinary autograd slice of the stacked map (any use of it
+        # differentiates correctly), and is also tagged with the stacked tensor it is a half of: the package's own loss
+        # functions then work on the stacked tensors directly -- one gradient tensor per map instead of two zero-padded
+        # slice gradients and their sum (SliceBackward + add_: ~1000 launches and 3 ms per training step).
+        def half(f, h, flat=False):
+            t = f[h * B:(h + 1) * B]
+            if flat:
+                t = torch.flatten(t, 1, -1)
+            t._mg_half = (f, h)
+            return t
         y_d_rs, y_d_gs, fmap_rs, fmap_gs = [], [], [], []
         for s in range(3):
-            fmap_rs.append([f[:B] for f in fmaps[s]])
-            fmap_gs.append([f[B:] for f in fmaps[s]])
-            y_d_rs.append(torch.flatten(fmaps[s][6][:B], 1, -1))
-            y_d_gs.append(torch.flatten(fmaps[s][6][B:], 1, -1))
+            fmap_rs.append([half(f, 0) for f in fmaps[s]])
+            fmap_gs.append([half(f, 1) for f in fmaps[s]])
+            y_d_rs.append(half(fmaps[s][6], 0, True))
+            y_d_gs.append(half(fmaps[s][6], 1, True))
         return y_d_rs, y_d_gs, fmap_rs, fmap_gs
 
 
@@ -377,10 +416,70 @@ class _LossRows(torch.autograd.Function):
                 *[g.view_as(t) if g is not None else None for g, t in zip(gb, b)])
 
 
+class _StackedLossRows(torch.autograd.Function):
+    """The same row means, for rows that are halves (real / generated) of stacked discriminator outputs: forward reads the
+    halves in place, backward writes each row's gradient straight into its half of ONE gradient tensor per stacked map.
+    rows: tuple of (parent index, half of a, half of b or None, mode)."""
+
+    @staticmethod
+    def forward(ctx, rows, *parents):
+        ctx.rows = rows
+        ctx.save_for_backward(*parents)
+        a, b = _StackedLossRows._views(rows, [p.detach() for p in parents])
+        return _engine.loss_forward(a, [u if u is not None else t for t, u in zip(a, b)], [r[3] for r in rows])
+
+    @staticmethod
+    def _views(rows, tensors):
+        a, b = [], []
+        for pi, ha, hb, _mode in rows:
+            t = tensors[pi]
+            n = t.shape[0] // 2
+            a.append(t[ha * n:(ha + 1) * n])
+            b.append(t[hb * n:(hb + 1) * n] if hb is not None else None)
+        return a, b
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        rows, parents = ctx.rows, ctx.saved_tensors
+        covered = [set() for _ in parents]
+        for pi, ha, hb, _mode in rows:
+            covered[pi].add(ha)
+            if hb is not None:
+                covered[pi].add(hb)
+        grads = [(torch.empty_like(p) if len(c) == 2 else torch.zeros_like(p)) if ctx.needs_input_grad[1 + i] else None
+                 for i, (p, c) in enumerate(zip(parents, covered))]
+        scratch = [g if g is not None else torch.empty_like(p) for g, p in zip(grads, parents)]
+        a, b = _StackedLossRows._views(rows, [p.detach() for p in parents])
+        ga, gb = _StackedLossRows._views(rows, scratch)
+        modes = [r[3] for r in rows]
+        _engine.loss_backward(a, [u if u is not None else t for t, u in zip(a, b)], modes, grad_out,
+                              [u is not None for u in b], out_a=ga, out_b=gb)
+        return (None, *grads)
+
+
+def _stacked_rows(a, b, modes):
+    """If every row is a tagged half of a stacked discriminator output (MultiScaleDiscriminator.forward), the table in
+    (parent index, halves, mode) form plus the distinct parents; else None."""
+    parents, index, rows = [], {}, []
+    for t, u, m in zip(a, b, modes):
+        ti = getattr(t, "_mg_half", None)
+        ui = getattr(u, "_mg_half", None) if u is not None else None
+        if ti is None or (u is not None and (ui is None or ui[0] is not ti[0])) or not ti[0].requires_grad:
+            return None
+        if id(ti[0]) not in index:
+            index[id(ti[0])] = len(parents)
+            parents.append(ti[0])
+        rows.append((index[id(ti[0])], ti[1], ui[1] if ui is not None else None, m))
+    return tuple(rows), parents
+
+
 def _row_means(a, b, modes):
     """Row means of a loss table on the fused kernels.  CUDA tensors only, like the modules: there is no CPU path."""
     if not all(t.is_cuda for t in a):
         raise _engine.EngineError("melgan_multi_b200 loss functions need CUDA tensors (no CPU fallback)")
+    st = _stacked_rows(a, b, modes) if torch.is_grad_enabled() else None
+    if st is not None:
+        return _StackedLossRows.apply(st[0], *st[1])
     b = [u if u is not None else t for t, u in zip(a, b)]  # placeholder rows keep the argument list rectangular
     return _LossRows.apply(tuple(modes), *a, *b)
 
