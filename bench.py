@@ -20,6 +20,7 @@ audio frames.  Weights are seeded random-init (melgan_multi_b200.syn
              Python and /root/reference does not exist on the GPU box); value from the MEDIAN step.
 """
 import argparse
+import ctypes
 import json
 import os
 import statistics
@@ -466,19 +467,33 @@ def main():
     alg_bytes = ALG_BYTES_PER_FRAME * frames + ALG_WEIGHT_BYTES
     moved_bytes = (ALG_BYTES_PER_FRAME + extra) * frames + packed_bytes
     fwd_ms = total_ms / K
-    traffic = None  # dram bytes per launch of the dominant kernel, from the committed ncu --set full capture
-    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    # dram bytes per launch of the dominant kernel from the committed `ncu --set full` capture -- quoted only if that capture
+    # was taken with the kernel configuration this build runs (profiles/r02_ncu_traffic.json records mg_gen_kernel_config)
+    traffic, traffic_note = None, None
+    L_ = engine.lib()
+    L_.mg_gen_kernel_config.restype = ctypes.c_char_p
+    L_.mg_gen_kernel_config.argtypes = [ctypes.c_int, ctypes.c_int]
+    cfg_now = L_.mg_gen_kernel_config(dom, T).decode()
+    tpath = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
     if os.path.exists(tpath):
-        t = json.load(open(tpath)).get("res1")
-        if t:
+        t = json.load(open(tpath)).get(dom_name)
+        if t and t.get("kernel_config") == cfg_now:
             traffic = t["dram_read_bytes"] + t["dram_write_bytes"]
+            traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full of this kernel configuration "
+                            "(profiles/r02_ncu_traffic.json, %.1f us under ncu); algorithmic HBM bytes of this kernel: 2 * 64*128*2048*4 "
+                            "= 134.2 MB (the 126 MB L2 keeps part of the output)" % t["gpu_time_us"])
+        else:
+            traffic_note = ("STALE CAPTURE IGNORED: profiles/r02_ncu_traffic.json holds %r for %s, this build runs %r -- re-run "
+                            "scripts/gpu_profile_r02.sh" % (t.get("kernel_config") if t else None, dom_name, cfg_now))
+            print("bench.py: " + traffic_note, file=sys.stderr)
+    else:
+        traffic_note = "no ncu capture committed for this build"
     roofline = {
         "kernel": ("resblock_tc_kernel<C=128> (%s: stage-1 ResBlock, 6 k3 convs%s; %.0f%% of generator FLOPs)" % (
             dom_name, " + stage-2 ConvTranspose at its tail" if "+" in dom_name else "", 100.0 * k_flops[dom] / sum(k_flops))),
         "bound": "tensor", "achieved": dom_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
         "frac": dom_tflops / peaks["bf16_tflops"], "traffic": traffic,
-        "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r01_ncu_res1_key_metrics.txt); "
-                        "algorithmic HBM bytes of this kernel: 2 * 64*128*2048*4 = 134.2 MB (the 126 MB L2 keeps part of the output)",
+        "traffic_note": traffic_note, "kernel_config": cfg_now,
         "peak_source": "%s bf16 dense burst (MEASURED_PEAKS.json)" % peaks["source"],
         "algorithmic_flops_per_launch": k_flops[dom], "avg_launch_ms": float(kms[dom]),
         "math": ("split-bf16 tcgen05: 3 MMA passes per product, so tensor-pipe work is 3x the algorithmic FLOPs "

@@ -239,6 +239,10 @@ int mg_gen_forward_slices(int B, int T);
  * which = 1..3); -1 = the default (environment MG_GEN_TAIL, else all three).  For tests and A/B measurements. */
 int mg_gen_set_pipeline(int tail_mask);
 const char *mg_gen_kernel_name(int i);
+/* Template configuration of the i-th chain kernel at T mel frames per item (e.g. "resblock_tc_kernel<RbCfg<128,2,4,4,1,0,0,1,0,1>>/NH4"):
+ * profile evidence (profiles/ ncu captures) records it, and bench.py only quotes a capture taken with the configuration this
+ * build actually runs. */
+const char *mg_gen_kernel_config(int i, int T);
 
 #ifdef __cplusplus
 }

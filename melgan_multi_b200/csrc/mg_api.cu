@@ -118,6 +118,8 @@ int mg_gen_forward_timed(const void *packed, const float *mel, float *audio, int
 
 const char *mg_gen_kernel_name(int i) { return generator_tc_kernel_name(i); }
 
+const char *mg_gen_kernel_config(int i, int T) { return generator_tc_kernel_config(i, T); }
+
 int mg_gen_set_pipeline(int tail_mask) {
     if (tail_mask < -1 || tail_mask > 15) return set_error(MG_ERR_INVALID_ARGUMENT, "mg_gen_set_pipeline: mask %d", tail_mask);
     generator_tc_set_tail(tail_mask);

@@ -76,6 +76,8 @@ int generator_tc_fused_up();  // bit 0: stage 2, bit 1: stage 3 run their stride
 int generator_tc_tail();      // bit i: stage i's ConvT runs at the TAIL of ResBlock i-1's kernel
 void generator_tc_set_tail(int mask);
 const char *generator_tc_kernel_name(int i);
+const char *generator_tc_kernel_config(int i, int T);
+const char *resblock_config_name(int stage, int L);
 int generator_tc_slices(int B, int T);  // batch slices (concurrent kernel chains) one forward is cut into
 int launch_generator_tc(const float *packed, const float *mel, float *audio, int B, int T, float *ws, int *status,
                         cudaStream_t s, cudaEvent_t *ev = nullptr, const float *mel_host = nullptr, float *audio_host = nullptr);

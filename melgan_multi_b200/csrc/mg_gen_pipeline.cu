@@ -68,6 +68,24 @@ const char *generator_tc_kernel_name(int i) {
     return (i >= 0 && i < n) ? st[i].name : "";
 }
 
+// template configuration of chain kernel i at T mel frames (what evidence files record; "" for non-ResBlock kernels)
+const char *generator_tc_kernel_config(int i, int T) {
+    ChainStep st[12];
+    const int n = build_chain(st);
+    if (i < 0 || i >= n || T < 1) return "";
+    int len = T;
+    for (int k = 0; k <= i; ++k) {
+        if (st[k].kind == 1) len *= stage_stride(st[k].arg);
+        else if (st[k].kind == 2) {
+            const int a = st[k].arg;
+            const int Lk = (a >= 12 && a <= 14) ? 2 * len : len;
+            if (k == i) return resblock_config_name(a, Lk);
+            len = a >= 20 ? Lk * stage_stride(a - 20 + 1) : Lk;
+        }
+    }
+    return st[i].kind == 0 ? "conv_rows_tc_kernel<ConvCfg<80,512,7>>" : "convt_tc_kernel";
+}
+
 // Tensor-core pipeline of one contiguous slice of the batch.  a0: conv_pre output; a[0]: ResBlock-0 output (unfused chains);
 // a[1], a[2], u: three buffers of 8192 T floats per item that the stages rotate through (a kernel never writes its input).
 static int generator_tc_chain(const float *packed, const float *mel, float *audio, int B, int T, float *a0, float *const *a,

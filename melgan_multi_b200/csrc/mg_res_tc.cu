@@ -1022,6 +1022,14 @@ static int launch_resblock(const float *x, float *y, const float *packed, int st
     return MG_OK;
 }
 
+template <class Cfg>
+static const char *cfg_name() {
+    static char buf[96];
+    snprintf(buf, sizeof(buf), "resblock_tc_kernel<RbCfg<%d,%d,%d,%d,%d,%d,%d,%d,%d,%d>>/NH%d", Cfg::C, Cfg::NBLK, Cfg::NSTAGE, Cfg::NWG,
+             Cfg::MINB, (int)Cfg::POST, (int)Cfg::UPF, Cfg::CL, Cfg::UPT, (int)Cfg::TMA, Cfg::NH);
+    return buf;
+}
+
 // x, y: [B][C][L] fp32 NCL with C = 256 >> stage; status: device int, set non-zero if a pipeline wait timed out.
 int launch_resblock_tc(const float *x, float *y, const float *packed, int stage, int B, int L, int *status, cudaStream_t s,
                        long long *trace) {
@@ -1075,6 +1083,46 @@ int launch_resblock_tc(const float *x, float *y, const float *packed, int stage,
         case 14: return launch_resblock<RbCfg<32, 4, 4, 2, 2, true, true>>(x, y, packed, 3, B, L, status, trace, s);
     }
     return set_error(MG_ERR_INVALID_ARGUMENT, "launch_resblock_tc: stage %d", stage);
+}
+
+// the configuration launch_resblock_tc picks for (stage code, L) with a 16-byte aligned input: evidence files (ncu captures) record
+// it, bench.py refuses a capture whose configuration is not the one this build runs
+const char *resblock_config_name(int stage, int L) {
+    const bool tma = !tma_disabled() && (L % 4) == 0 && encode_tiled_fn() != nullptr;
+    switch (stage) {
+        case 0: {
+            static const bool pair = [] { const char *e = getenv("MG_RES0_PAIR"); return !(e && e[0] == '0'); }();
+            if (pair && L > 128)
+                return tma ? cfg_name<RbCfg<256, 1, 4, 4, 1, false, false, 2, 0, true>>()
+                           : cfg_name<RbCfg<256, 1, 4, 4, 1, false, false, 2>>();
+            return tma ? cfg_name<RbCfg<256, 1, 4, 4, 1, false, false, 1, 0, true>>()
+                       : cfg_name<RbCfg<256, 1, 4, 4, 1>>();
+        }
+        case 1:
+            return tma ? cfg_name<RbCfg<128, 2, 4, 4, 1, false, false, 1, 0, true>>()
+                       : cfg_name<RbCfg<128, 2, 4, 4, 1>>();
+        case 2:
+            return tma ? cfg_name<RbCfg<64, 2, 2, 2, 2, false, false, 1, 0, true>>()
+                       : cfg_name<RbCfg<64, 2, 2, 2, 2>>();
+        case 3: return cfg_name<RbCfg<32, 4, 4, 2, 2>>();
+        case 4: return cfg_name<RbCfg<32, 4, 4, 2, 2, true>>();
+        case 20:
+            if (L > 128)
+                return tma ? cfg_name<RbCfg<256, 1, 4, 4, 1, false, false, 2, 8, true>>()
+                           : cfg_name<RbCfg<256, 1, 4, 4, 1, false, false, 2, 8>>();
+            return tma ? cfg_name<RbCfg<256, 1, 4, 4, 1, false, false, 1, 8, true>>()
+                       : cfg_name<RbCfg<256, 1, 4, 4, 1, false, false, 1, 8>>();
+        case 21:
+            return tma ? cfg_name<RbCfg<128, 2, 4, 4, 1, false, false, 1, 2, true>>()
+                       : cfg_name<RbCfg<128, 2, 4, 4, 1, false, false, 1, 2>>();
+        case 22:
+            return tma ? cfg_name<RbCfg<64, 2, 2, 2, 2, false, false, 1, 2, true>>()
+                       : cfg_name<RbCfg<64, 2, 2, 2, 2, false, false, 1, 2>>();
+        case 12: return cfg_name<RbCfg<64, 2, 2, 2, 2, false, true>>();
+        case 13: return cfg_name<RbCfg<32, 4, 4, 2, 2, false, true>>();
+        case 14: return cfg_name<RbCfg<32, 4, 4, 2, 2, true, true>>();
+    }
+    return "";
 }
 
 }  // namespace mg
