@@ -280,7 +280,12 @@ def multi_gpu_blocks(dev, rank, world, barrier, max_over_ranks, steps=10, warmup
     mgd.apply_gradient_allreduce(msd1)
     g1, d1 = Adam(gen1.parameters(), 2e-4, betas=(0.5, 0.9)), Adam(msd1.parameters(), 2e-4, betas=(0.5, 0.9))
     ddp_ms = timed(lambda: train_step(gen1, msd1, g1, d1, True), steps, warmup)
-    sg, sd = gen1._grad_reducer.stats, msd1._grad_reducer.stats
+    sg, sd = dict(gen1._grad_reducer.stats), dict(msd1._grad_reducer.stats)
+    # the same wrapped step with the collectives themselves left out (hooks, bucket adoption, /world still run): what is left of
+    # ddp_ms - dry_ms is communication that backward did not hide
+    gen1._grad_reducer.dry = msd1._grad_reducer.dry = True
+    dry_ms = timed(lambda: train_step(gen1, msd1, g1, d1, False), steps, warmup)
+    gen1._grad_reducer.dry = msd1._grad_reducer.dry = False
     passes = max(1, sg["passes"])
     bytes_step = (sg["allreduce_bytes"] + sd["allreduce_bytes"]) / passes
     skipped_step = sd["skipped_bytes"] / passes
@@ -295,11 +300,18 @@ def multi_gpu_blocks(dev, rank, world, barrier, max_over_ranks, steps=10, warmup
             w_.wait()
     bare_ms = timed(bare, 20, 5)
     gbytes, dbytes = fg_.flat.numel() * 4, fd_.flat.numel() * 4
-    exposed = max(0.0, ddp_ms - nocomm_ms)
+    exposed = max(0.0, ddp_ms - dry_ms)
     out["ddp_train_step"] = {
         "config": "configs[3]: DDP train step batch=16/gpu, 8192-sample segments, %d x B200, NCCL all-reduce" % world,
-        "ms": ddp_ms, "ms_same_step_without_communication": nocomm_ms, "exposed_communication_ms": exposed,
-        "allreduce_ms": bare_ms, "overlap_frac": (max(0.0, min(1.0, 1.0 - exposed / bare_ms)) if bare_ms > 0 else None),
+        "ms": ddp_ms, "ms_same_step_unwrapped_single_gpu": nocomm_ms, "ms_wrapped_without_the_collectives": dry_ms,
+        "exposed_communication_ms": exposed,
+        "allreduce_ms": bare_ms,
+        "overlap_frac": (sg["bytes_launched_with_backward_left"] + sd["bytes_launched_with_backward_left"]) /
+                        max(1, sg["allreduce_bytes"] + sd["allreduce_bytes"]),
+        "overlap_frac_definition": "share of all-reduced gradient bytes whose collective was launched (from a gradient hook) "
+                                   "while autograd still had gradients to produce, i.e. with backward compute left to overlap; the "
+                                   "measured cost is exposed_communication_ms = ms - ms_wrapped_without_the_collectives (includes "
+                                   "the two synchronous logging all-reduces of train.py:113,124 and SM contention of the NCCL kernels)",
         "bytes": bytes_step, "bytes_reference_would_send": gbytes + 2 * dbytes, "bytes_skipped_per_step": skipped_step,
         "segments_per_s": 16 * world / (ddp_ms * 1e-3),
         "allreduce_busbw_gbs": 2 * (world - 1) / world * (gbytes + dbytes) / (bare_ms * 1e-3) / 1e9,

@@ -52,12 +52,14 @@ def init_distributed(rank, num_gpus, group_name, dist_backend, dist_url):
 # ---- process-wide bookkeeping of the wrapped modules -------------------------------------------------------------------
 _REDUCERS = []          # every _GradReducer of this process
 _FORWARD_SET = set()    # ids of the reducers whose module ran forward since the last backward pass ended
-_PASS = {"key": None}   # key of the backward pass in flight (frozenset of reducer ids), None between passes
+_PASS = {"key": None, "open": []}  # key of the backward pass in flight (frozenset of reducer ids), None between passes; "open":
+                                   # [reducer, bytes] of buckets launched in this pass after which no gradient has appeared yet
 _OPT_HOOK = {"handle": None}
 
 
 def _end_pass():
     _PASS["key"] = None
+    _PASS["open"] = []
     _FORWARD_SET.clear()
 
 
@@ -80,11 +82,13 @@ class _GradReducer:
         self.world = dist.get_world_size()
         self.params = [p for p in module.parameters() if p.requires_grad]
         self.dedup = os.environ.get("MG_DDP_DEDUP", "1") != "0"
-        self.stats = {"allreduce_calls": 0, "allreduce_bytes": 0, "skipped_bytes": 0, "lazy_flushes": 0, "passes": 0}
+        self.stats = {"allreduce_calls": 0, "allreduce_bytes": 0, "skipped_bytes": 0, "lazy_flushes": 0, "passes": 0,
+                      "bytes_launched_with_backward_left": 0}
         self.history = {}            # pass key -> "consumed" | "discarded"
         self.unconsumed_key = None   # key of the last backward whose gradients nobody has consumed or dropped yet
         self.pending = False         # ... and those gradients are still local (lazy mode): reduce them if consumed
         self.state = 0               # 0: no backward pass in flight, 1: eager pass, 2: lazy pass
+        self.dry = False             # measurement aid (bench.py): do everything except the collectives themselves
         self.skip_once = False
         if not self.params:
             self.flat = None
@@ -142,6 +146,10 @@ class _GradReducer:
         """post-accumulate-grad hook of parameter i (runs ~150 times per backward on a host-bound training step: keep it
         to a few bytecodes).  state 0: no pass in flight, 1: eager pass (count, launch full buckets), 2: lazy pass."""
         st = self.state
+        if _PASS["open"]:  # backward produced another gradient after those buckets were launched: their all-reduce had
+            for r, n in _PASS["open"]:  # compute to overlap with (statistics only)
+                r.stats["bytes_launched_with_backward_left"] += n
+            _PASS["open"] = []
         if st == 2:
             return
         if st == 0:
@@ -177,9 +185,12 @@ class _GradReducer:
         start, end, members = self.buckets[b]
         self._adopt(members)
         chunk = self.flat.narrow(0, start, end - start)
-        self.works.append(dist.all_reduce(chunk, async_op=True))
+        if not self.dry:
+            self.works.append(dist.all_reduce(chunk, async_op=True))
         self.stats["allreduce_calls"] += 1
         self.stats["allreduce_bytes"] += chunk.numel() * chunk.element_size()
+        if self.state == 1:
+            _PASS["open"].append((self, chunk.numel() * chunk.element_size()))
 
     def _finish_pass(self):
         """End-of-backward callback (the reference does ALL its work here, distributed.py:105-129): buckets whose
@@ -187,6 +198,7 @@ class _GradReducer:
         st, self.state = self.state, 0
         if st == 0:
             return
+        # (buckets launched from here on are launched by the end-of-backward callback: state is already 0)
         self.module.needs_reduction = False
         if st == 2:  # gradients stay where autograd put them, un-reduced
             if self.skip_once:  # skip_next_reduction(): the caller promised to throw these gradients away
@@ -209,7 +221,8 @@ class _GradReducer:
             return
         if self.pending:  # predicted "discarded", but they are wanted after all: reduce now (blocking, exact)
             self._adopt(range(len(self.params)))
-            dist.all_reduce(self.flat)
+            if not self.dry:
+                dist.all_reduce(self.flat)
             self.flat.div_(self.world)
             self.stats["lazy_flushes"] += 1
             self.stats["allreduce_calls"] += 1

@@ -23,6 +23,17 @@ with torch.no_grad():
     if os.environ.get("MG_GEN_SLICES"):  # two batch-slice chains on forked streams
         y2 = g(torch.from_numpy(synth.mel_input(2, 3, 6)).cuda())
         g._dev.check_status(2, 3)
+    # T = 40: stage 0 is 320 positions -> CTA pairs (DSMEM boundary exchange, multicast weights), tensor-map TMA input slabs
+    # (every stage length is a multiple of 4), tail ConvT with its fp32 fix-up, several tiles per item in the later stages
+    y3 = g(torch.from_numpy(synth.mel_input(1, 40, 9)).cuda())
+    g._dev.check_status(1, 40)
+    # the unfused chain (one kernel per ConvT / ResBlock) and the mel front end
+    from melgan_multi_b200 import engine, meldataset
+    engine.check(engine.lib().mg_gen_set_pipeline(0))
+    y4 = g(torch.from_numpy(synth.mel_input(1, 5, 10)).cuda())
+    g._dev.check_status(1, 5)
+    engine.check(engine.lib().mg_gen_set_pipeline(-1))
+    m = meldataset.mel_spectrogram(y3[0, 0].clamp(-1, 1), 1024, 80, 22050, 256, 1024, 55, 9000)
 # one train.py:108-129 step on a 512-sample segment
 g.train(); d.train()
 og, od = Adam(g.parameters(), 1e-4, betas=(0.5, 0.9)), Adam(d.parameters(), 1e-4, betas=(0.5, 0.9))
