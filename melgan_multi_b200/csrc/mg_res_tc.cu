@@ -63,9 +63,16 @@ using namespace tc;
 // producer streams [LCH channels][P positions] fp32 slabs of x through the (still idle) weight-ring slots, positions past
 // the end of the sequence zero-filled by the copy engine; the epilogue warps turn each slab into R (TMEM) and
 // X = split(lrelu(x)) as it lands.  Needs L % 4 == 0 (16-byte global strides); the launcher falls back otherwise.
+// G2 = true: two CTAs with INDEPENDENT tiles (own halo, own input) form a cluster and run every MMA as one cta_group::2
+// instruction of M = 256: each CTA keeps only HALF of every weight chunk in its ring (rows [rank*C/2, +C/2) of B), so an MMA
+// reads 4 KB of A + N*16 B of B per SM instead of 4 KB + N*32 B -- the shared-memory bandwidth that the overlapped epilogue
+// stores and the ring's writes compete for.  The leader CTA's issuer warps issue for both; the peer's epilogue warps arrive on
+// the leader's xready barriers through DSMEM, the peer's (otherwise idle) issuer warp relays its ring's full barriers.
 template <int C_, int NBLK_, int NSTAGE_, int NWG_, int MINB_, bool POST_ = false, bool UPF_ = false, int CL_ = 1, int UPT_ = 0,
-          bool TMA_ = false>
+          bool TMA_ = false, bool G2_ = false>
 struct RbCfg {
+    static constexpr bool G2 = G2_;
+    static constexpr int CLUSTER = (CL_ > 1 || G2_) ? 2 : 1;  // CTAs per cluster (launch attribute)
     static constexpr bool TMA = TMA_;
     static constexpr int CL = CL_;
     static constexpr int UPT = UPT_;
@@ -114,7 +121,9 @@ struct RbCfg {
 #endif
     static constexpr int NH = (C == 128) ? MG_NH128 : (C == 256) ? MG_NH256 : 1;
     static constexpr int BND = SLACK;  // boundary rows pushed to the peer CTA (CL = 2); the widest tap reaches 9
-    static constexpr int XARRIVE = NEPI + (CL > 1 ? BND * PARTS : 0);  // xready arrivals: local epilogue threads + the peer's boundary threads
+    // xready arrivals: local epilogue threads + (pair) the peer's boundary threads / (G2, leader) one per epilogue warp of the peer
+    static constexpr int XARRIVE = NEPI + (CL > 1 ? BND * PARTS : 0) + (G2_ ? NEPI / 32 : 0);
+    static_assert(!G2_ || (CL_ == 1 && UPT_ == 0 && !UPF_ && !POST_ && C_ % 32 == 0), "cta_group::2: plain ResBlock tiles");
     static_assert(CL == 1 || (CL == 2 && !UPF_ && !POST_), "CTA pairs: plain ResBlock only");
     // tail ConvT: TNG output channels per group (mg_layout.h up_ng of the next stage), TN = MMA N, TNCG groups, ring slots of
     // TSLOT bytes (stride 8: one tap of a 16-channel chunk; stride 2: both taps), TNSLOT of them
@@ -126,7 +135,7 @@ struct RbCfg {
     static constexpr int LCH = CHUNK / (P * 4), NSLAB = TMA ? C / (LCH > 0 ? LCH : 1) : 0, LUNITS = NBLK * (LCH / 8);
     static_assert(!TMA || (LCH >= 8 && LCH % 8 == 0 && LCH * P * 4 == CHUNK && LUNITS % NWG == 0 && !UPF_ && P <= 256 &&
                            (C / NH) % LCH == 0 && (CL == 1 || LUNITS == NWG)), "TMA input slabs");
-    static constexpr int SMEM_BYTES = 2 * XBYTES + NSTAGE * CHUNK + 2 * C * 4 + (2 * NSTAGE + 1 + NH + 4 + 2 * NSTAGE + 1) * 8 + 16;
+    static constexpr int SMEM_BYTES = 2 * XBYTES + NSTAGE * CHUNK + 2 * C * 4 + (2 * NSTAGE + 1 + NH + 4 + 2 * NSTAGE + 1 + NSTAGE) * 8 + 16;
     static_assert(KSL % NH == 0 && (CW / NH) % 16 == 0 && (NH == 1 || ITEMS == NWG), "hand-off split");
     // fused ConvT: input rows s = o/2 - 1 .. o/2 + P/2 of 2C channels (2 KP k-panels), NCB blocks of 128 output pairs
     static constexpr int UROWS = P / 2 + 2, UPITCH = UROWS * 16, NCB = NBLK / 2, UKSL = 2 * C / KC, NUPCH = UPF ? 4 * UKSL : 0;
@@ -180,7 +189,7 @@ __device__ __forceinline__ void store_x16_push(uint8_t *Xh, uint8_t *Xl, int xpi
 
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB)
-resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const float *__restrict__ packed, int stage, int L,
+resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const float *__restrict__ packed, int stage, int L, int nB,
                    int *__restrict__ status, long long *__restrict__ trace, const __grid_constant__ CUtensorMap xmap) {
     constexpr int C = Cfg::C, NBLK = Cfg::NBLK, P = Cfg::P, SLACK = Cfg::SLACK, HALO = Cfg::HALO;
     constexpr int XPITCH = Cfg::XPITCH, XBYTES = Cfg::XBYTES, KC = Cfg::KC, CHUNK = Cfg::CHUNK, NSTAGE = Cfg::NSTAGE;
@@ -198,37 +207,52 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
     uint64_t *lfull = tfree + 2;        // [NSTAGE] TMA input slab landed in ring slot s;  lempty[NSTAGE]: converted by every epilogue warp
     uint64_t *lempty = lfull + NSTAGE;
     uint64_t *rfree = lempty + NSTAGE;  // pair: both CTAs' input slabs are consumed, the leader may multicast weights into both rings
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(rfree + 1);
+    uint64_t *pfull = rfree + 1;        // [NSTAGE] G2, leader: the PEER's half of ring slot s has landed (relayed by its issuer warp)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(pfull + NSTAGE);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int b = blockIdx.y;
+    int b = blockIdx.y;
     // Edge-aware tiling: a halo is only needed where the tile borders MORE sequence.  Tile 0 starts at position 0 (its
     // left edge is the real zero padding) and keeps P - HALO outputs; later tiles keep P - 2*HALO, and a tile that reaches
     // the end of the sequence keeps its right HALO rows too.  (L = 2048, P = 256: 9 tiles instead of 10.)
     // CL > 1: all of this at super-tile granularity (PS = CL * P rows), CTA `rank` of the cluster owning rows [rank * P, + P).
     constexpr int CL = Cfg::CL, PS = CL * P, HL = Cfg::HL, PVS = PS - HALO - HL;
-    const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
-    const int stile = (int)blockIdx.x / CL;
+    constexpr bool G2 = Cfg::G2;
+    const int crank = Cfg::CLUSTER > 1 ? (int)cluster_ctarank() : 0;  // rank in the cluster (pair or G2)
+    const int rank = CL > 1 ? crank : 0;                              // position inside a super-tile (pair only)
+    int stile = (int)blockIdx.x / CL;
+    bool phantom = false;
+    if constexpr (G2) {
+        // cta_group::2 pairs are formed over the linearised (item, tile) list (grid.y = 1), so that only an odd TOTAL leaves one
+        // phantom tile: it sits past the last tile of the last item, reads zeros (or rows it ignores) and stores nothing
+        const int nt = 1 + (L > PS ? (L - PS + PVS - 1) / PVS : 0), id = (int)blockIdx.x;
+        b = id / nt;
+        stile = id - b * nt;
+        if (b >= nB) { b = nB - 1; stile = nt; phantom = true; }
+    }
     const int os = stile == 0 ? 0 : (PS - HALO) + (stile - 1) * PVS - HL;  // position of super-tile row 0
     const int o = os + rank * P;                                            // position of tile-local p = 0
     const int Lc = L;  // (tail ConvT: position L would own the last `pad` outputs; they are x[L-1]-only and fixed up below)
     const int s_lo = stile == 0 ? 0 : HL;
     const int s_hi = (os + PS >= Lc) ? PS : PS - HALO;  // first super-tile row that is NOT a valid output
-    const int p_lo = min(max(s_lo - rank * P, 0), P), p_hi = min(max(s_hi - rank * P, 0), P);
+    const int p_lo = phantom ? 0 : min(max(s_lo - rank * P, 0), P), p_hi = phantom ? 0 : min(max(s_hi - rank * P, 0), P);
     const bool interior = (o >= 0 && o + P <= L);  // every row of the tile is a real position
     // CTA pair: my boundary rows (rank 0: the last BND rows, rank 1: the first BND) mirror into the peer's slack rows
-    const uint32_t peer = (uint32_t)(rank ^ 1);
+    const uint32_t peer = (uint32_t)(crank ^ 1);
     const uint32_t rxh = CL > 1 ? mapa_shared(smem_u32(smem), peer) : 0u, rxl = rxh + XBYTES;
     uint32_t rxready[Cfg::NH];
     // consumption order of the six convs of ResBlock `stage`: c1[0], c2[0], c1[1], c2[1], c1[2], c2[2]
     const int l0 = 5 + 6 * stage;
     const uint8_t *tc_base = reinterpret_cast<const uint8_t *>(packed) + tc_region_start();
 
-    if (warp == 0) tmem_alloc(tmem_slot, Cfg::TCOLS);
+    if (warp == 0) {
+        if constexpr (G2) tmem_alloc2(tmem_slot, Cfg::TCOLS); else tmem_alloc(tmem_slot, Cfg::TCOLS);
+    }
     if (tid == 32) {
         for (int s = 0; s < NSTAGE; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], NIW * CL);  // every issuer warp (of every CTA of the pair) commits its own arrival
+            mbar_init(&pfull[s], 1);
         }
         mbar_init(done, NIW * CL);
         for (int h = 0; h < Cfg::NH; ++h) mbar_init(&xready[h], Cfg::XARRIVE);
@@ -237,7 +261,7 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
         mbar_init(rfree, CL);
         fence_mbar_init();
     }
-    for (int h = 0; h < Cfg::NH; ++h) rxready[h] = CL > 1 ? mapa_shared(smem_u32(&xready[h]), peer) : 0u;
+    for (int h = 0; h < Cfg::NH; ++h) rxready[h] = Cfg::CLUSTER > 1 ? mapa_shared(smem_u32(&xready[h]), peer) : 0u;
     // (fused ConvT: the X region first holds the ConvT operand and the staging buffer; its slack rows are zeroed later)
     for (int i = Cfg::UPF ? 1 << 30 : tid; i < 2 * Cfg::KP * 2 * SLACK; i += Cfg::NT) {  // zero the slack rows of Xh and Xl
         const int r = i % (2 * SLACK), kp = (i / (2 * SLACK)) % Cfg::KP, hl = i / (2 * SLACK * Cfg::KP);
@@ -250,12 +274,23 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
-    if constexpr (CL > 1) cluster_sync();  // the peer's barriers exist before a copy, commit or arrival of mine can land on them
+    if constexpr (Cfg::CLUSTER > 1) cluster_sync();  // the peer's barriers exist before a copy, commit or arrival of mine can land on them
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     // optional timeline of one interior CTA (clock64 stamps; see mg_gen_resblock_trace)
-    const bool tr = trace && blockIdx.y == 0 && blockIdx.x == (gridDim.x > 1 ? 1u : 0u) && lane == 0 && (warp == 0 || warp == NEPI / 32 + 1);  // epilogue warp 0 and issuer 0
+    const bool tr = trace && blockIdx.y == 0 && blockIdx.x == (G2 ? 0u : gridDim.x > 1 ? 1u : 0u) && lane == 0 && (warp == 0 || warp == NEPI / 32 + 1);  // epilogue warp 0 and issuer 0
 #define MG_TR(slot) do { if (tr) trace[slot] = clock64(); } while (0)
+    // "channels h of the next conv's input are written": every epilogue thread arrives on its CTA's barrier -- except in the peer
+    // CTA of a cta_group::2 pair, whose MMAs the LEADER issues: there one lane per warp arrives on the leader's barrier (DSMEM)
+#define MG_XREADY_ARRIVE(h)                                              \
+    do {                                                                 \
+        if (G2 && crank == 1) {                                          \
+            __syncwarp();                                                \
+            if (lane == 0) mbar_arrive_cluster(rxready[h]);              \
+        } else {                                                         \
+            mbar_arrive(&xready[h]);                                     \
+        }                                                                \
+    } while (0)
 
     if (warp == NEPI / 32) {
         // ================= TMA producer: streams the 6 * NCHUNK weight chunks through the ring =================
@@ -299,6 +334,17 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
                     const int h = i / (3 * KH), tap = (i / KH) % 3, ks = h * KH + i % KH;
                     const int ch = tap * Cfg::KSL + ks;
                     if (!mbar_wait(&empty[s], ph ^ 1)) { ok = false; break; }  // (pair: free in BOTH CTAs, see the commits)
+                    if constexpr (G2) {
+                        // my half of the chunk: rows [crank*C/2, +C/2) of every (hi|lo, k-panel) piece, packed contiguously in the slot
+                        constexpr int PIECE = (C / 2) * 16, NP = 2 * (KC / 8);
+                        mbar_arrive_expect_tx(&full[s], CHUNK / 2);
+#pragma unroll
+                        for (int pc = 0; pc < NP; ++pc)
+                            bulk_g2s(ring + s * CHUNK + pc * PIECE, src + (size_t)ch * CHUNK + (size_t)pc * C * 16 + (size_t)crank * PIECE,
+                                     PIECE, &full[s]);
+                        if (++s == NSTAGE) { s = 0; ph ^= 1; }
+                        continue;
+                    }
                     mbar_arrive_expect_tx(&full[s], CHUNK);
                     if constexpr (CL > 1) {  // every CTA arms its own barrier; the leader's copy lands in both rings
                         if (rank == 0)
@@ -330,11 +376,35 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
         // (each warp runs the loop warp-uniform and one elected lane issues; a single issuing thread sustains only
         //  one tcgen05.mma per ~50 cycles, which starves the pipe when N = C <= 64)
         const int iw = warp - (NEPI / 32 + 1);
-        const uint32_t idesc = make_idesc_bf16(128, C);
-        const uint64_t adesc_t = desc_template(XPITCH, 128), bdesc_t = desc_template(C * 16, 128);
+        // cta_group::2: M = 256 (this CTA's 128 rows + the peer's), B rows per ring slot = C / 2 (the other half is the peer's)
+        constexpr int BROWS = G2 ? C / 2 : C, BHALF = G2 ? Cfg::HALF / 2 : Cfg::HALF;
+        const uint32_t idesc = make_idesc_bf16(G2 ? 256 : 128, C);
+        const uint64_t adesc_t = desc_template(XPITCH, 128), bdesc_t = desc_template(BROWS * 16, 128);
         const uint32_t xh_addr = smem_u32(Xh), xl_addr = smem_u32(Xl), ring_addr = smem_u32(ring);
         int s = 0, ph = 0;
         bool ok = true;  // a timed-out wait only raises the status word: control flow stays warp-uniform
+        if (G2 && crank == 1) {
+            // ---- peer CTA of a cta_group::2 pair: the leader issues every MMA.  This warp only tells it when MY half of a ring slot
+            // has landed (the leader cannot wait on another CTA's barrier): wait locally, arrive on the leader's pfull[s].
+            if (iw == 0) {
+                uint32_t rpfull[NSTAGE];
+#pragma unroll
+                for (int k = 0; k < NSTAGE; ++k) rpfull[k] = mapa_shared(smem_u32(&pfull[k]), 0);
+#pragma unroll 1
+                for (int i = 0; i < 6 * Cfg::NCHUNK; ++i) {
+                    ok &= mbar_wait(&full[s], ph);
+                    if (lane == 0) {
+                        uint32_t a = rpfull[0];
+#pragma unroll
+                        for (int k = 1; k < NSTAGE; ++k) a = (s == k) ? rpfull[k] : a;
+                        mbar_arrive_cluster(a);
+                    }
+                    __syncwarp();
+                    if (++s == NSTAGE) { s = 0; ph ^= 1; }
+                }
+                if (!ok && lane == 0) atomicExch(status, 10);
+            }
+        } else {
         if constexpr (Cfg::UPF) {
             // ---- fused ConvT: chunk (tap k, K-slice ks); odd taps feed the even outputs (D1 of block 2cb), even taps the odd ones
             constexpr int UPITCH = Cfg::UPITCH, UKSL = Cfg::UKSL, NCB = Cfg::NCB;
@@ -384,11 +454,12 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
                 constexpr int KH = Cfg::KSL / Cfg::NH;
                 const int h = ch / (3 * KH), tap = (ch / KH) % 3, ks = h * KH + ch % KH;
                 if (ch % (3 * KH) == 0) {  // first chunk of channel half h: wait until the epilogue has written those channels of X
-                    ok &= CL > 1 ? mbar_wait_cluster(&xready[h], (conv + PH0) & 1) : mbar_wait(&xready[h], (conv + PH0) & 1);
+                    ok &= Cfg::CLUSTER > 1 ? mbar_wait_cluster(&xready[h], (conv + PH0) & 1) : mbar_wait(&xready[h], (conv + PH0) & 1);
                     tc_fence_after();
                     if (ch == 0 && iw == 0) MG_TR(64 + 3 * conv);
                 }
                 ok &= mbar_wait(&full[s], ph);
+                if constexpr (G2) ok &= mbar_wait_cluster(&pfull[s], ph);  // the peer's half of the slot
                 tc_fence_after();
                 if (ch == 0 && iw == 0) MG_TR(65 + 3 * conv);
                 // per-chunk base descriptors; every MMA below adds a compile-time constant to the address field
@@ -399,24 +470,29 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
                 for (int pass = 0; pass < 3; ++pass) {
 #pragma unroll
                     for (int k16 = 0; k16 < KC / 16; ++k16) {
-                        const uint64_t bdesc = bbase + (uint64_t)(((pass == 2 ? Cfg::HALF : 0) + 2 * k16 * (C * 16)) >> 4);
+                        const uint64_t bdesc = bbase + (uint64_t)(((pass == 2 ? BHALF : 0) + 2 * k16 * (BROWS * 16)) >> 4);
 #pragma unroll
                         for (int bi = 0; bi < NBLK / NIW; ++bi) {
                             const int blk = iw + bi * NIW;
                             const uint64_t adesc = (pass == 1 ? al : ah) + (uint64_t)((2 * k16 * XPITCH) >> 4) + (uint64_t)(blk * 128);
                             const bool acc = !(fresh && ch == 0 && pass == 0 && k16 == 0);
-                            if (elect_one()) mma_bf16(tmem + blk * 2 * C + dcol, adesc, bdesc, idesc, acc);
+                            if (elect_one()) {
+                                if constexpr (G2) mma2_bf16(tmem + blk * 2 * C + dcol, adesc, bdesc, idesc, acc);
+                                else mma_bf16(tmem + blk * 2 * C + dcol, adesc, bdesc, idesc, acc);
+                            }
                         }
                     }
                 }
                 if (elect_one()) {  // ring slot free once these MMAs have read it
-                    if constexpr (CL > 1) mma_commit_multicast(&empty[s], (uint16_t)((1u << CL) - 1));
+                    if constexpr (G2) mma2_commit(&empty[s], 3);  // ... in both CTAs
+                    else if constexpr (CL > 1) mma_commit_multicast(&empty[s], (uint16_t)((1u << CL) - 1));
                     else mma_commit(&empty[s]);
                 }
                 if (++s == NSTAGE) { s = 0; ph ^= 1; }
             }
             if (elect_one()) {
-                if constexpr (CL > 1) mma_commit_multicast(done, (uint16_t)((1u << CL) - 1));  // the peer's epilogue may write my slack rows
+                if constexpr (G2) mma2_commit(done, 3);  // both CTAs' epilogues
+                else if constexpr (CL > 1) mma_commit_multicast(done, (uint16_t)((1u << CL) - 1));  // the peer's epilogue may write my slack rows
                 else mma_commit(done);
             }
             if (iw == 0) MG_TR(66 + 3 * conv);
@@ -477,6 +553,7 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
             if (!ok && lane == 0) atomicExch(status, 7);
             __syncwarp();
         }
+        }  // (leader / single-CTA issuer)
     } else {
         // ================= epilogue warps (16): lane = position, 4 warpgroups split blocks / column ranges =========
         const int wg = warp >> 2, q = warp & 3;
@@ -671,9 +748,9 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
             if ((k + 1) * LCH % (C / NH) == 0) {      // a channel half (or everything) of conv 0's input is in place
                 const int h = (k + 1) * LCH / (C / NH) - 1;
                 tmem_st_wait();
-                if constexpr (CL > 1) fence_proxy_async_all(); else fence_proxy_async();
+                if constexpr (Cfg::CLUSTER > 1) fence_proxy_async_all(); else fence_proxy_async();
                 tc_fence_before();
-                mbar_arrive(&xready[h]);
+                MG_XREADY_ARRIVE(h);
                 if constexpr (CL > 1) {  // (LUNITS == NWG: every thread converts exactly one unit per slab, so a boundary-row thread
                                          //  accounts for one of the BND * PARTS remote arrivals its peer's barrier expects)
                     if (rank == 0 ? row >= P - Cfg::BND : row < Cfg::BND) mbar_arrive_cluster(rxready[h]);
@@ -716,10 +793,10 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
             }
         }
         tmem_st_wait();
-        if constexpr (CL > 1) fence_proxy_async_all(); else fence_proxy_async();
+        if constexpr (Cfg::CLUSTER > 1) fence_proxy_async_all(); else fence_proxy_async();
         tc_fence_before();
         for (int h = 0; h < NH; ++h) {  // conv 0 may start (phase 0 of both halves)
-            mbar_arrive(&xready[h]);
+            MG_XREADY_ARRIVE(h);
             for (int k = 0; k < nb0; ++k) mbar_arrive_cluster(rxready[h]);
         }
         }
@@ -790,9 +867,9 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
                     }
                 }
                 // channels [h*C/NH, (h+1)*C/NH) of the next conv's input are in place: let its MMAs start on them
-                if constexpr (CL > 1) fence_proxy_async_all(); else fence_proxy_async();
+                if constexpr (Cfg::CLUSTER > 1) fence_proxy_async_all(); else fence_proxy_async();
                 tc_fence_before();
-                mbar_arrive(&xready[h]);
+                MG_XREADY_ARRIVE(h);
                 for (int k = 0; k < nb; ++k) mbar_arrive_cluster(rxready[h]);  // my boundary rows are in the peer's slack rows
             }
             if (warp == 0) MG_TR(4 + 3 * conv);
@@ -960,9 +1037,13 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
         if (warp == 0) MG_TR(20);
     }
 #undef MG_TR
+#undef MG_XREADY_ARRIVE
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, Cfg::TCOLS);
+    if constexpr (G2) cluster_sync();  // both CTAs are done with the pair's tensor memory
+    if (warp == 0) {
+        if constexpr (G2) tmem_dealloc2(tmem, Cfg::TCOLS); else tmem_dealloc(tmem, Cfg::TCOLS);
+    }
     if constexpr (CL > 1) cluster_sync();  // nobody leaves while the peer may still multicast into its ring or arrive on its barriers
 }
 
@@ -1017,16 +1098,18 @@ static int launch_resblock(const float *x, float *y, const float *packed, int st
         int rc = make_input_map(&xmap, x, B, Cfg::C, L, Cfg::P, Cfg::LCH);
         if (rc) return rc;
     }
-    MG_CUDA_TRY(launch_ex(resblock_tc_kernel<Cfg>, dim3(ntiles * Cfg::CL, B), dim3(Cfg::NT), Cfg::SMEM_BYTES, s, Cfg::CL, true, x, y,
-                          packed, stage, L, status, trace, xmap));
+    // (G2: the (item, tile) list pairs up along x; an odd total gets one phantom tile, see the kernel)
+    const dim3 grid = Cfg::G2 ? dim3((unsigned)(((long long)ntiles * B + 1) / 2 * 2), 1) : dim3(ntiles * Cfg::CL, B);
+    MG_CUDA_TRY(launch_ex(resblock_tc_kernel<Cfg>, grid, dim3(Cfg::NT), Cfg::SMEM_BYTES, s, Cfg::CLUSTER, true, x, y,
+                          packed, stage, L, B, status, trace, xmap));
     return MG_OK;
 }
 
 template <class Cfg>
 static const char *cfg_name() {
     static char buf[96];
-    snprintf(buf, sizeof(buf), "resblock_tc_kernel<RbCfg<%d,%d,%d,%d,%d,%d,%d,%d,%d,%d>>/NH%d", Cfg::C, Cfg::NBLK, Cfg::NSTAGE, Cfg::NWG,
-             Cfg::MINB, (int)Cfg::POST, (int)Cfg::UPF, Cfg::CL, Cfg::UPT, (int)Cfg::TMA, Cfg::NH);
+    snprintf(buf, sizeof(buf), "resblock_tc_kernel<RbCfg<%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d>>/NH%d", Cfg::C, Cfg::NBLK, Cfg::NSTAGE, Cfg::NWG,
+             Cfg::MINB, (int)Cfg::POST, (int)Cfg::UPF, Cfg::CL, Cfg::UPT, (int)Cfg::TMA, (int)Cfg::G2, Cfg::NH);
     return buf;
 }
 
@@ -1050,9 +1133,16 @@ int launch_resblock_tc(const float *x, float *y, const float *packed, int stage,
         }
         // (C = 128 as two single-block CTAs per SM, RbCfg<128, 1, 2, 2, 2>: measured 244 us vs 213 us at config 2 -- the
         //  25 % halo recompute and the two-slot weight rings cost more than the overlap buys)
-        case 1:
+        case 1: {
+            // cta_group::2 pairs of tiles (RbCfg<..., G2>): built, parity-green, and SLOWER at config 2 -- 257 us vs 197 us: the
+            // M = 256 MMAs issue at ~78 cycles instead of 64-69 and the epilogue that overlaps them takes 6.5 k cycles instead of
+            // 3.8 k (phase trace in DESIGN.md section 5) -- so it is opt-in: MG_RES1_G2=1
+            static const bool g2 = [] { const char *e = getenv("MG_RES1_G2"); return e && e[0] == '1'; }();
+            if (g2 && tma && (long long)B * (1 + (L > 256 ? (L - 256 + 223) / 224 : 0)) >= 2)
+                return launch_resblock<RbCfg<128, 2, 4, 4, 1, false, false, 1, 0, true, true>>(x, y, packed, stage, B, L, status, trace, s);
             return tma ? launch_resblock<RbCfg<128, 2, 4, 4, 1, false, false, 1, 0, true>>(x, y, packed, stage, B, L, status, trace, s)
                        : launch_resblock<RbCfg<128, 2, 4, 4, 1>>(x, y, packed, stage, B, L, status, trace, s);
+        }
         // (3 CTAs/SM with half-size tiles was measured slower for C = 64 / 32: the extra halo recompute outweighs the overlap)
         case 2:
             return tma ? launch_resblock<RbCfg<64, 2, 2, 2, 2, false, false, 1, 0, true>>(x, y, packed, stage, B, L, status, trace, s)
@@ -1098,9 +1188,12 @@ const char *resblock_config_name(int stage, int L) {
             return tma ? cfg_name<RbCfg<256, 1, 4, 4, 1, false, false, 1, 0, true>>()
                        : cfg_name<RbCfg<256, 1, 4, 4, 1>>();
         }
-        case 1:
+        case 1: {
+            const char *e = getenv("MG_RES1_G2");
+            if (e && e[0] == '1' && tma) return cfg_name<RbCfg<128, 2, 4, 4, 1, false, false, 1, 0, true, true>>();
             return tma ? cfg_name<RbCfg<128, 2, 4, 4, 1, false, false, 1, 0, true>>()
                        : cfg_name<RbCfg<128, 2, 4, 4, 1>>();
+        }
         case 2:
             return tma ? cfg_name<RbCfg<64, 2, 2, 2, 2, false, false, 1, 0, true>>()
                        : cfg_name<RbCfg<64, 2, 2, 2, 2>>();

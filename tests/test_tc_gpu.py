@@ -59,6 +59,35 @@ def test_resblock_tc_matches_oracle(state, dev, stage, B, L):
     assert m < TOL and l2 < TOL, (stage, B, L, m, l2)
 
 
+def test_resblock_cta_group2_variant_matches_oracle(state):
+    """The opt-in cta_group::2 form of the stage-1 ResBlock (pairs of tiles run every MMA as one M = 256 instruction, each CTA
+    holding half of every weight chunk; MG_RES1_G2=1 -- off by default because it measured slower): same results.  Runs in a
+    subprocess because the switch is read once per process."""
+    import subprocess
+    import sys
+    code = (
+        "import os, sys, numpy as np, torch\n"
+        "sys.path.insert(0, '.'); sys.path.insert(0, 'tests')\n"
+        "from melgan_multi_b200 import engine, synth\n"
+        "import test_tc_gpu as t\n"
+        "state = synth.generator_state(1234)\n"
+        "gd = engine.GeneratorDevice('cuda:0')\n"
+        "order = [n for n, *_ in synth.GENERATOR_LAYERS]\n"
+        "to = lambda a: torch.from_numpy(a).cuda()\n"
+        "gd.pack([to(state[n + '.weight_v']) for n in order], [to(state[n + '.weight_g']) for n in order], [to(state[n + '.bias']) for n in order])\n"
+        "for B, L in ((2, 500), (1, 224), (3, 2048), (1, 4)):\n"
+        "    x = np.random.RandomState(L).standard_normal((B, 128, L)).astype(np.float32)\n"
+        "    ref = t.oracle_resblock(state, 1, x)\n"
+        "    y = gd.resblock(1, torch.from_numpy(x).cuda()).cpu().numpy()\n"
+        "    m, l2 = t.rel_errors(y, ref)\n"
+        "    assert m < 1e-4 and l2 < 1e-4, (B, L, m, l2)\n"
+        "print('G2_OK')\n")
+    env = dict(os.environ, MG_RES1_G2="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                         cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), timeout=300)
+    assert "G2_OK" in out.stdout, out.stdout[-2000:]
+
+
 @pytest.mark.parametrize("stage,B,L", [(0, 2, 32), (0, 64, 32), (0, 1, 1), (0, 3, 130), (1, 2, 256), (1, 1, 5),
                                        (2, 2, 700), (2, 1, 1), (3, 2, 1500), (3, 1, 511), (3, 1, 512), (3, 1, 513)])
 def test_convt_tc_matches_oracle(state, dev, stage, B, L):
