@@ -197,6 +197,10 @@ void mg_gen_engine_destroy(mg_gen_engine *e);
  *   weight; mg_msd_wn_backward turns the 21 layers' dw into (d weight_v, d weight_g) in one launch (dw[i] NULL: skip). */
 /* dz = (g1 + g2) * LeakyReLU'(out) over n elements (g2 may be NULL): the gradient entering a layer's pre-activation from the
  * next layer and from the feature-map loss, in one launch (F.leaky_relu backward of models.py:91,94,97 + the add). */
+/* Data gradient of conv_post1 (Conv1d 1024 -> 1024, k5, pad 2; models.py:84,96) of discriminator `scale`: dz [Bt][1024][L] (already
+ * multiplied by LeakyReLU') -> dx [Bt][1024][L], on the same tcgen05 kernel as the forward, streaming the transposed, tap-flipped
+ * copy of the weights that mg_msd_pack / mg_disc_pack keep for it. */
+int mg_msd_post1_dgrad(const void *packed, int scale, const float *dz, float *dx, int Bt, int L, void *status_word, void *stream);
 int mg_lrelu_backward(const float *g1, const float *g2, const float *out, float *dz, long long n, void *stream);
 size_t mg_msd_grouped_backward_workspace_bytes(int layer, int Bt, int Lout);
 int mg_msd_grouped_backward(const void *packed, int scale, int layer, const float *dz, const float *x, float *dx, float *dw,

@@ -159,6 +159,14 @@ int mg_msd_grouped_backward(const void *packed, int scale, int layer, const floa
     return launch_disc_grouped_backward(blob, layer, dz, x, dx, dw, db, (float *)workspace, Bt, Lin, Lout, (cudaStream_t)stream);
 }
 
+int mg_msd_post1_dgrad(const void *packed, int scale, const float *dz, float *dx, int Bt, int L, void *status_word, void *stream) {
+    if (!packed || !dz || !dx || dz == dx || !status_word || scale < 0 || scale > 2 || Bt < 1 || L < 1)
+        return set_error(MG_ERR_INVALID_ARGUMENT, "mg_msd_post1_dgrad: bad argument");
+    const uint8_t *blob = reinterpret_cast<const uint8_t *>(packed) + (size_t)scale * d_blob_bytes();
+    return launch_disc_post1_dgrad_tc(dz, dx, blob + d_tcT_start(), reinterpret_cast<const float *>(blob + d_zero_start()), Bt, L,
+                                      (int *)status_word, (cudaStream_t)stream);
+}
+
 int mg_lrelu_backward(const float *g1, const float *g2, const float *out, float *dz, long long n, void *stream) {
     return launch_lrelu_grad(g1, g2, out, dz, n, (cudaStream_t)stream);
 }

@@ -252,6 +252,7 @@ using PreCfg = ConvCfg<80, 512, 7, 80, false>;          // generator conv_pre
 //  reads 8 KB of operands per 64 cycles = the whole 128 B/cycle, and the ring's bulk-copy writes (42 B/cycle) and the
 //  converter's stores come on top.  The lever is cta_group::2, where each CTA of a pair holds half of B.)
 using Post1Cfg = ConvCfg<1024, 1024, 5, 32, true, 2, kPost1NG, 1>;
+using Post1DgradCfg = ConvCfg<1024, 1024, 5, 32, false, 2, kPost1NG, 1>;  // the same contraction on the transposed blob, no activation
 
 // mel [B][80][T] -> y [B][512][T]   (Generator.conv_pre)
 int launch_gen_pre_tc(const float *mel, float *y, const float *packed, int B, int T, int *status, cudaStream_t s) {
@@ -263,6 +264,12 @@ int launch_gen_pre_tc(const float *mel, float *y, const float *packed, int B, in
 int launch_disc_post1_tc(const float *x, float *y, const uint8_t *wtc, const float *bias, int Bt, int L, int *status,
                          cudaStream_t s) {
     return launch_conv_rows<Post1Cfg>(x, y, wtc, bias, Bt, L, status, s);
+}
+
+// dz [Bt][1024][L] -> dx [Bt][1024][L]: data gradient of conv_post1 (autograd of models.py:96), wtcT = blob + d_tcT_start()
+int launch_disc_post1_dgrad_tc(const float *dz, float *dx, const uint8_t *wtcT, const float *zero_bias, int Bt, int L, int *status,
+                               cudaStream_t s) {
+    return launch_conv_rows<Post1DgradCfg>(dz, dx, wtcT, zero_bias, Bt, L, status, s);
 }
 
 }  // namespace mg

@@ -82,6 +82,9 @@ __global__ void __launch_bounds__(128) disc_pack_kernel(DiscPackArgs a, uint8_t 
             tc::split_bf16(scale * vr[j], hi, lo);
             tcw[conv_tc_weight_index(1024, 5, kPost1NG, row, ci, tap, 0)] = hi;
             tcw[conv_tc_weight_index(1024, 5, kPost1NG, row, ci, tap, 1)] = lo;
+            __nv_bfloat16 *tct = reinterpret_cast<__nv_bfloat16 *>(blob + d_tcT_start());  // dgrad copy: [ci][co][4 - tap]
+            tct[conv_tc_weight_index(1024, 5, kPost1NG, ci, row, 4 - tap, 0)] = hi;
+            tct[conv_tc_weight_index(1024, 5, kPost1NG, ci, row, 4 - tap, 1)] = lo;
         }
     } else {
         for (int j = threadIdx.x; j < inner; j += blockDim.x) fw[j] = scale * vr[j];  // [ci][tap]
@@ -96,6 +99,8 @@ int launch_disc_pack(const float *const *v, const float *const *g, const float *
         if (!v[i] || !g[i] || !bias[i]) return set_error(MG_ERR_INVALID_ARGUMENT, "discriminator pack: null tensor %d", i);
         a.v[i] = v[i]; a.g[i] = g[i]; a.bias[i] = bias[i];
     }
+    for (int d = 0; d < ndisc; ++d)  // the dgrad launch's zero "bias"
+        MG_CUDA_TRY(cudaMemsetAsync(reinterpret_cast<uint8_t *>(packed) + (size_t)d * d_blob_bytes() + d_zero_start(), 0, 4096, s));
     disc_pack_kernel<<<ndisc * kDiscRows, 128, 0, s>>>(a, reinterpret_cast<uint8_t *>(packed));
     MG_CUDA_TRY(cudaGetLastError());
     return MG_OK;

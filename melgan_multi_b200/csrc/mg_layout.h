@@ -205,7 +205,12 @@ MG_HD constexpr size_t d_g4tc_index(int kp, int ci, int n, int i) {  // bf16 ele
 }
 MG_HD constexpr size_t d_g4tc_start() { return d_gtc_start() + d_gtc_bytes(); }
 MG_HD constexpr size_t d_g4tc_bytes() { return (size_t)d_layer(4).groups * d_g4tc_group_bytes(); }
-MG_HD constexpr size_t d_blob_bytes() { return d_g4tc_start() + d_g4tc_bytes(); }
+// conv_post1 once more, TRANSPOSED and tap-flipped, for its data gradient: dx = conv1d(dz, W'), W'[ci][co][k] = W[co][ci][4 - k] (a
+// stride-1 "same" conv's dgrad is the same conv on flipped, transposed weights), same conv_tc_weight_index layout (mg_conv_tc.cu
+// streams it unchanged); then 1024 zero floats: the dgrad launch's "bias"
+MG_HD constexpr size_t d_tcT_start() { return d_g4tc_start() + d_g4tc_bytes(); }
+MG_HD constexpr size_t d_zero_start() { return d_tcT_start() + d_tc_bytes(); }
+MG_HD constexpr size_t d_blob_bytes() { return d_zero_start() + 4096; }
 MG_HD constexpr size_t msd_packed_bytes() { return 3 * d_blob_bytes(); }
 
 // Activation workspace (floats per batch item per mel frame): conv_pre out, stage 0..2 outs.

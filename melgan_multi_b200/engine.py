@@ -91,6 +91,9 @@ def lib():
         L.mg_msd_grouped_backward.restype = ctypes.c_int
         L.mg_msd_grouped_backward.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 6 + [
             ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        L.mg_msd_post1_dgrad.restype = ctypes.c_int
+        L.mg_msd_post1_dgrad.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_void_p, ctypes.c_void_p]
         L.mg_lrelu_backward.restype = ctypes.c_int
         L.mg_lrelu_backward.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_longlong, ctypes.c_void_p]
         L.mg_msd_wn_backward.restype = ctypes.c_int
@@ -504,6 +507,20 @@ class DiscriminatorDevice:
                                                 dx.data_ptr() if need_dx else None, dw.data_ptr(), db.data_ptr(),
                                                 ws.data_ptr(), nbytes, Bt, Lin, Lout, stream))
         return dx, dw, db
+
+    def post1_dgrad(self, scale, dz):
+        """dx of conv_post1 of discriminator `scale` from dz [Bt, 1024, L] (tcgen05, transposed weight copy of the blob)."""
+        torch = self.torch
+        dz = dz.contiguous()
+        Bt, C, L = dz.shape
+        if C != 1024:
+            raise EngineError("post1_dgrad expects 1024 channels")
+        dx = torch.empty_like(dz)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            check(lib().mg_msd_post1_dgrad(self.packed.data_ptr(), scale, dz.data_ptr(), dx.data_ptr(), Bt, L,
+                                           self.status.data_ptr(), stream))
+        return dx
 
     def lrelu_backward(self, g1, g2, out):
         """(g1 + g2) * LeakyReLU'(out) in one launch; g1 or g2 may be None (not both)."""
