@@ -201,6 +201,10 @@ void mg_gen_engine_destroy(mg_gen_engine *e);
  * multiplied by LeakyReLU') -> dx [Bt][1024][L], on the same tcgen05 kernel as the forward, streaming the transposed, tap-flipped
  * copy of the weights that mg_msd_pack / mg_disc_pack keep for it. */
 int mg_msd_post1_dgrad(const void *packed, int scale, const float *dz, float *dx, int Bt, int L, void *status_word, void *stream);
+/* Weight and bias gradient of conv_post1 (autograd of models.py:96; no weights needed): x [Bt][1024][L] (the layer input),
+ * dz [Bt][1024][L] -> dw [1024][1024][5] (gradient of the FOLDED weight, torch layout), db [1024]; one tcgen05 launch, split-bf16
+ * (fp32-grade) with fp32 accumulation over all Bt * L positions. */
+int mg_msd_post1_wgrad(const float *x, const float *dz, float *dw, float *db, int Bt, int L, void *status_word, void *stream);
 int mg_lrelu_backward(const float *g1, const float *g2, const float *out, float *dz, long long n, void *stream);
 size_t mg_msd_grouped_backward_workspace_bytes(int layer, int Bt, int Lout);
 int mg_msd_grouped_backward(const void *packed, int scale, int layer, const float *dz, const float *x, float *dx, float *dw,

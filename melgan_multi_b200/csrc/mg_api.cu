@@ -167,6 +167,12 @@ int mg_msd_post1_dgrad(const void *packed, int scale, const float *dz, float *dx
                                       (int *)status_word, (cudaStream_t)stream);
 }
 
+int mg_msd_post1_wgrad(const float *x, const float *dz, float *dw, float *db, int Bt, int L, void *status_word, void *stream) {
+    if (!x || !dz || !dw || !db || !status_word || Bt < 1 || L < 1)
+        return set_error(MG_ERR_INVALID_ARGUMENT, "mg_msd_post1_wgrad: bad argument");
+    return launch_disc_post1_wgrad_tc(x, dz, dw, db, Bt, L, (int *)status_word, (cudaStream_t)stream);
+}
+
 int mg_lrelu_backward(const float *g1, const float *g2, const float *out, float *dz, long long n, void *stream) {
     return launch_lrelu_grad(g1, g2, out, dz, n, (cudaStream_t)stream);
 }

@@ -94,6 +94,8 @@ def lib():
         L.mg_msd_post1_dgrad.restype = ctypes.c_int
         L.mg_msd_post1_dgrad.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                          ctypes.c_void_p, ctypes.c_void_p]
+        L.mg_msd_post1_wgrad.restype = ctypes.c_int
+        L.mg_msd_post1_wgrad.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         L.mg_lrelu_backward.restype = ctypes.c_int
         L.mg_lrelu_backward.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_longlong, ctypes.c_void_p]
         L.mg_msd_wn_backward.restype = ctypes.c_int
@@ -521,6 +523,21 @@ class DiscriminatorDevice:
             check(lib().mg_msd_post1_dgrad(self.packed.data_ptr(), scale, dz.data_ptr(), dx.data_ptr(), Bt, L,
                                            self.status.data_ptr(), stream))
         return dx
+
+    def post1_wgrad(self, x, dz):
+        """(dW [1024, 1024, 5], db [1024]) of conv_post1 from its input x and dz, both [Bt, 1024, L] (tcgen05, split-bf16)."""
+        torch = self.torch
+        x, dz = x.contiguous(), dz.contiguous()
+        Bt, C, L = dz.shape
+        if C != 1024 or tuple(x.shape) != (Bt, C, L):
+            raise EngineError("post1_wgrad expects x and dz of shape [Bt, 1024, L]")
+        dw = torch.empty((1024, 1024, 5), dtype=torch.float32, device=dz.device)
+        db = torch.empty((1024,), dtype=torch.float32, device=dz.device)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            check(lib().mg_msd_post1_wgrad(x.data_ptr(), dz.data_ptr(), dw.data_ptr(), db.data_ptr(), Bt, L,
+                                           self.status.data_ptr(), stream))
+        return dw, db
 
     def lrelu_backward(self, g1, g2, out):
         """(g1 + g2) * LeakyReLU'(out) in one launch; g1 or g2 may be None (not both)."""

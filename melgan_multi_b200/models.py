@@ -163,21 +163,20 @@ class Generator(nn.Module):
 
     # -- stock-PyTorch restatement, used ONLY to differentiate (backward) ---------------------
     def _torch_forward(self, x, leaves):
-        """models.py:61-71 of the reference on 4-D [N, C, 1, L] channels_last tensors (conv2d with (1, k) kernels): cuDNN's
-        NHWC tensor-op kernels then run without an nchw<->nhwc conversion around every call (scripts/gen_bwd_layout_ab.py:
-        5.66 -> 4.95 ms per recompute+backward at B=16)."""
-        ws = [torch._weight_norm(leaves[3 * i], leaves[3 * i + 1], 0).unsqueeze(2) for i in range(30)]
+        # (the same graph on channels_last 4-D tensors through conv2d saves cuDNN's nchw<->nhwc conversions -- 0.7 ms eager,
+        #  ~0.2 ms under the CUDA graph, scripts/gen_bwd_layout_ab.py -- but picks TF32 kernels whose rounding puts the deepest
+        #  layers' weight_g gradients AT the 5e-3 digest tolerance of tests/test_train_gpu.py on the small case: not taken)
+        ws = [torch._weight_norm(leaves[3 * i], leaves[3 * i + 1], 0) for i in range(30)]
         bs = [leaves[3 * i + 2] for i in range(30)]
-        x = x.unsqueeze(2).contiguous(memory_format=torch.channels_last)
-        x = F.conv2d(x, ws[0], bs[0], padding=(0, 3))
+        x = F.conv1d(x, ws[0], bs[0], padding=3)
         for i in range(4):
-            k = ws[1 + i].shape[3]
-            x = F.conv_transpose2d(F.leaky_relu(x), ws[1 + i], bs[1 + i], stride=(1, k // 2), padding=(0, k // 4))
+            k = ws[1 + i].shape[2]
+            x = F.conv_transpose1d(F.leaky_relu(x), ws[1 + i], bs[1 + i], stride=k // 2, padding=k // 4)
             for j, d in enumerate(_RES_DILATIONS):
                 a, b = 5 + 6 * i + j, 5 + 6 * i + 3 + j
-                h = F.conv2d(F.leaky_relu(x), ws[a], bs[a], padding=(0, d), dilation=(1, d))
-                x = F.conv2d(F.leaky_relu(h), ws[b], bs[b], padding=(0, 1)) + x
-        return torch.tanh(F.conv2d(F.leaky_relu(x), ws[29], bs[29], padding=(0, 3))).squeeze(2)
+                h = F.conv1d(F.leaky_relu(x), ws[a], bs[a], padding=d, dilation=d)
+                x = F.conv1d(F.leaky_relu(h), ws[b], bs[b], padding=1) + x
+        return torch.tanh(F.conv1d(F.leaky_relu(x), ws[29], bs[29], padding=3))
 
     def forward(self, x):
         if not x.is_cuda:
@@ -295,11 +294,9 @@ class _MSDFunction(torch.autograd.Function):
             _n, _cin, cout, _k, stride, groups, pad = DISCRIMINATOR_LAYERS[l]
             if groups > 1:
                 g, dws[l], dbs[l] = dev.grouped_backward(s, l, dz, inputs[l], need_dx)
-            elif l == 5:  # conv_post1: dgrad on the tcgen05 conv kernel (transposed weight copy); wgrad / bias grad still aten
+            elif l == 5:  # conv_post1 (88 % of a discriminator's FLOPs): data and weight gradients on the tcgen05 kernels
                 g = dev.post1_dgrad(s, dz)
-                w = torch._weight_norm(params[3 * l], params[3 * l + 1], 0)
-                _, dws[l], dbs[l] = torch.ops.aten.convolution_backward(
-                    dz, inputs[l], w, [cout], [stride], [pad], [1], False, [0], 1, [False, True, True])
+                dws[l], dbs[l] = dev.post1_wgrad(inputs[l], dz)
             else:
                 w = torch._weight_norm(params[3 * l], params[3 * l + 1], 0)
                 g, dws[l], dbs[l] = torch.ops.aten.convolution_backward(

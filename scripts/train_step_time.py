@@ -23,6 +23,23 @@ def build():
     return g.cuda().train(), d.cuda().train()
 
 
+def generator_stock_forward(x, leaves):
+    """The reference's own formulation (nn.Conv1d / nn.ConvTranspose1d on NCL tensors, models.py:61-71 of the reference) --
+    the drop-in's recompute (models.Generator._torch_forward) runs the same graph on channels_last 4-D tensors instead."""
+    import torch.nn.functional as F
+    ws = [torch._weight_norm(leaves[3 * i], leaves[3 * i + 1], 0) for i in range(30)]
+    bs = [leaves[3 * i + 2] for i in range(30)]
+    x = F.conv1d(x, ws[0], bs[0], padding=3)
+    for i in range(4):
+        k = ws[1 + i].shape[2]
+        x = F.conv_transpose1d(F.leaky_relu(x), ws[1 + i], bs[1 + i], stride=k // 2, padding=k // 4)
+        for j, d in enumerate((1, 3, 9)):
+            a, b = 5 + 6 * i + j, 5 + 6 * i + 3 + j
+            h = F.conv1d(F.leaky_relu(x), ws[a], bs[a], padding=d, dilation=d)
+            x = F.conv1d(F.leaky_relu(h), ws[b], bs[b], padding=1) + x
+    return torch.tanh(F.conv1d(F.leaky_relu(x), ws[29], bs[29], padding=3))
+
+
 class Stock(torch.nn.Module):
     """Routes forward() through the module's stock-PyTorch restatement (autograd records the usual cuDNN graph)."""
 
@@ -34,7 +51,7 @@ class Stock(torch.nn.Module):
         vs, gs, bs = self.m._param_triplets()
         leaves = [t for trip in zip(vs, gs, bs) for t in trip]
         if not self.msd:
-            return self.m._torch_forward(a[0], leaves)
+            return generator_stock_forward(a[0], leaves)
         y, y_hat = a
         B = y.shape[0]
         flat = self.m._torch_forward(torch.cat([y, y_hat]), leaves)

@@ -179,6 +179,33 @@ def test_grouped_conv_backward_matches_torch(msd_module, layer, Bt, Lin):
         torch.backends.cudnn.conv.fp32_precision = old
 
 
+@pytest.mark.parametrize("Bt,L", [(32, 32), (32, 16), (32, 8), (3, 17), (2, 20), (5, 7), (1, 3), (2, 130)])
+def test_conv_post1_gradients_match_fp64(msd_module, Bt, L):
+    """csrc/mg_wgrad_tc.cu (dW, db) and the transposed-blob dgrad of conv_post1 (models.py:84,96) against autograd of F.conv1d
+    in float64: the three training lengths (32 / 16 / 8 positions, 2 x 16 items) and ragged ones (L % 4 != 0: scalar loads;
+    L % 8 != 0: padded k-panels; L < 5: every tap touches the zero padding; K extent not a multiple of 32)."""
+    import torch.nn.functional as F
+    with torch.no_grad():
+        msd_module(torch.zeros(1, 1, 64).cuda(), torch.zeros(1, 1, 64).cuda())  # makes sure the weights are packed
+    scale = 2
+    conv = msd_module.discriminators[scale].layers()[5]
+    w = torch._weight_norm(conv.weight_v, conv.weight_g, 0).detach().double().requires_grad_(True)
+    gen = torch.Generator(device="cpu").manual_seed(1000 * Bt + L)
+    x = torch.randn(Bt, 1024, L, generator=gen).cuda()
+    dz = torch.randn(Bt, 1024, L, generator=gen).cuda()
+    xd = x.double().requires_grad_(True)
+    rdx, rdw = torch.autograd.grad(F.conv1d(xd, w, None, 1, 2), (xd, w), dz.double())
+    dev = msd_module._dev
+    dw, db = dev.post1_wgrad(x, dz)
+    dx = dev.post1_dgrad(scale, dz)
+    torch.cuda.synchronize()
+    assert int(dev.status[0].item()) == 0
+    for name, got, ref in (("dw", dw, rdw), ("db", db, dz.double().sum(dim=(0, 2))), ("dx", dx, rdx)):
+        m, l2 = rel_errors(got.cpu().numpy(), ref.float().cpu().numpy())
+        # (the sums run over 5120 products: the dropped lo*lo term of the 3-pass split leaves ~2e-5 of the maximum on dx)
+        assert m < 5e-5 and l2 < 3e-5, (name, m, l2)
+
+
 def test_standalone_discriminator_forward_and_backward(golden, dstate, msd_module):
     """Discriminator.forward on its own (reference models.py:87-103: returns (flattened logits, 7 feature maps)): scale 0 of
     the reference golden is exactly discriminators[0] applied to y, so the stand-alone module must reproduce it; its
