@@ -205,6 +205,13 @@ int mg_msd_post1_dgrad(const void *packed, int scale, const float *dz, float *dx
  * dz [Bt][1024][L] -> dw [1024][1024][5] (gradient of the FOLDED weight, torch layout), db [1024]; one tcgen05 launch, split-bf16
  * (fp32-grade) with fp32 accumulation over all Bt * L positions. */
 int mg_msd_post1_wgrad(const float *x, const float *dz, float *dw, float *db, int Bt, int L, void *status_word, void *stream);
+/* Backward of conv_pre (layer 0: Conv1d 1 -> 16, k15; x [Bt][1][L], dz [Bt][16][L], dw [16][1][15]) or conv_post2 (layer 6:
+ * Conv1d 1024 -> 1, k3; x [Bt][1024][L], dz [Bt][1][L], dw [1][1024][3]) of discriminator `scale` (autograd of models.py:90,99):
+ * dx (same shape as x; NULL: skip -- conv_pre's is only needed when the audio requires a gradient), dw (gradient of the FOLDED
+ * weight, torch layout), db.  fp32, fixed summation order.  Layer 0 needs a workspace (bytes from the helper), layer 6 none. */
+size_t mg_msd_edge_backward_workspace_bytes(int layer, int Bt, int L);
+int mg_msd_edge_backward(const void *packed, int scale, int layer, const float *dz, const float *x, float *dx, float *dw, float *db,
+                         void *workspace, size_t workspace_bytes, int Bt, int L, void *stream);
 int mg_lrelu_backward(const float *g1, const float *g2, const float *out, float *dz, long long n, void *stream);
 size_t mg_msd_grouped_backward_workspace_bytes(int layer, int Bt, int Lout);
 int mg_msd_grouped_backward(const void *packed, int scale, int layer, const float *dz, const float *x, float *dx, float *dw,

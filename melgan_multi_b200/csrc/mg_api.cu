@@ -173,6 +173,21 @@ int mg_msd_post1_wgrad(const float *x, const float *dz, float *dw, float *db, in
     return launch_disc_post1_wgrad_tc(x, dz, dw, db, Bt, L, (int *)status_word, (cudaStream_t)stream);
 }
 
+size_t mg_msd_edge_backward_workspace_bytes(int layer, int Bt, int L) {
+    return (layer == 0 && Bt > 0 && L > 0) ? edge_bwd_workspace_bytes(layer, Bt, L) : 0;
+}
+
+int mg_msd_edge_backward(const void *packed, int scale, int layer, const float *dz, const float *x, float *dx, float *dw, float *db,
+                         void *workspace, size_t workspace_bytes, int Bt, int L, void *stream) {
+    if (!packed || !dz || !x || !dw || !db || scale < 0 || scale > 2 || (layer != 0 && layer != 6) || Bt < 1 || L < 1)
+        return set_error(MG_ERR_INVALID_ARGUMENT, "mg_msd_edge_backward: bad argument (layer is 0 = conv_pre or 6 = conv_post2)");
+    if (layer == 0 && (!workspace || workspace_bytes < edge_bwd_workspace_bytes(0, Bt, L)))
+        return set_error(MG_ERR_WORKSPACE_TOO_SMALL, "mg_msd_edge_backward: conv_pre needs a workspace of %zu bytes",
+                         edge_bwd_workspace_bytes(0, Bt, L));
+    const uint8_t *blob = reinterpret_cast<const uint8_t *>(packed) + (size_t)scale * d_blob_bytes();
+    return launch_disc_edge_backward(blob, layer, dz, x, dx, dw, db, (float *)workspace, Bt, L, (cudaStream_t)stream);
+}
+
 int mg_lrelu_backward(const float *g1, const float *g2, const float *out, float *dz, long long n, void *stream) {
     return launch_lrelu_grad(g1, g2, out, dz, n, (cudaStream_t)stream);
 }

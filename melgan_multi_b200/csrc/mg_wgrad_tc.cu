@@ -9,8 +9,11 @@
 // A tap shifts x along K, i.e. by one bf16 INSIDE a 16-byte operand row -- not expressible as a descriptor offset -- so the
 // converter warps write five shifted copies of the (smaller) x tile next to one copy of the dz tile; the zero padding of the
 // reference at the two ends of every item is produced there, which is also what lets items follow each other along K.
-//   stage (32 positions = 2 K16 steps): A = split(dz) [hi|lo][4 k-panels][128 rows][16 B] = 16 KB
-//                                       B = split(x)  [tap][hi|lo][4 k-panels][64 rows][16 B] = 40 KB       x 3 stages
+//   stage (32 positions = 2 K16 steps): A = split(dz) [hi|lo][4 k-panels][128 rows][16 B] = 16 KB   (+ 32 B per panel, below)
+//                                       B = split(x)  [hi|lo][4 k-panels][tap 5][64 rows][16 B] = 40 KB     x 3 stages
+// The five copies are stacked along N, so one K16 step is an N = 256 MMA (taps 0..3) plus an N = 64 one (tap 4) instead of five
+// N = 64 ones: an MMA's cost is dominated by fetching its 128 x 16 A operand from shared memory (measured ~80 cycles at N = 64,
+// ~96 at N = 128 in the ResBlock kernels), so wide N is what amortises it.
 // Positions are padded per item to a multiple of 8 (one k-panel never straddles two items), the K extent to a multiple of 32.
 #include "mg_common.cuh"
 #include "mg_tc.cuh"
@@ -22,39 +25,39 @@ namespace wg {
 constexpr int C = 1024, NTAP = 5, PAD = 2;
 constexpr int MT = 128, NTILE = 64;            // co rows / ci rows of a CTA
 constexpr int NPANEL = 4;                      // k-panels (8 positions) per stage
-constexpr int APANEL = MT * 16, BPANEL = NTILE * 16;
+constexpr int NB = NTAP * NTILE;                // B rows of a stage: the five shifted copies stacked along N (row = tap * 64 + ci)
+// k-panel pitches: + 32 bytes, so the four panels of a stage start 8 banks apart and a half-warp's 8-byte stores (2 rows x 4
+// panels x 2 halves of a 16-byte operand row) hit 16 different bank pairs
+constexpr int APANEL = MT * 16 + 32, BPANEL = NB * 16 + 32;
 constexpr int AHALF = NPANEL * APANEL, BHALF = NPANEL * BPANEL;
-constexpr int ASTAGE = 2 * AHALF, BSTAGE = NTAP * 2 * BHALF, STAGE = ASTAGE + BSTAGE;
+constexpr int ASTAGE = 2 * AHALF, BSTAGE = 2 * BHALF, STAGE = ASTAGE + BSTAGE;
 constexpr int NSTAGE = 3;
-constexpr int NCONV = 256;                     // converter threads: 512 A units (row, panel) + 256 B units per stage
+constexpr int NCONV = 512;                     // converter threads: 1024 dz units + 512 x units (row, half k-panel) per stage
 constexpr int NT = NCONV + 32;
 constexpr int TMEM_COLS = 512;                 // 5 x 64 accumulator columns (power-of-two allocation)
-constexpr int SMEM_BYTES = NSTAGE * STAGE + (2 * NSTAGE + 1) * 8 + 16 + NCONV * 4;
+constexpr int SMEM_BYTES = NSTAGE * STAGE + (2 * NSTAGE + 1) * 8 + 16 + 2 * NCONV * 4;
 static_assert(SMEM_BYTES + 1024 <= 227 * 1024, "shared memory budget");
 }  // namespace wg
 
-// 8 consecutive positions [p0, p0 + 8) of one channel row (length L, base `row`), zero outside [0, L)
-__device__ __forceinline__ void load8(const float *__restrict__ row, int p0, int L, bool vec, bool live, float (&f)[8]) {
-    if (vec) {  // L % 4 == 0 and the row base is 16-byte aligned: each float4 is wholly inside or wholly outside
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const int p = p0 + 4 * q;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (live && p >= 0 && p < L) v = __ldg(reinterpret_cast<const float4 *>(row + p));
-            f[4 * q] = v.x; f[4 * q + 1] = v.y; f[4 * q + 2] = v.z; f[4 * q + 3] = v.w;
-        }
+// 4 consecutive positions [p0, p0 + 4) of one channel row (length L, base `row`), zero outside [0, L)
+__device__ __forceinline__ void load4(const float *__restrict__ row, int p0, int L, bool vec, bool live, float *f) {
+    if (vec) {  // L % 4 == 0, p0 % 4 == 0 and the row base is 16-byte aligned: the float4 is wholly inside or wholly outside
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live && p0 >= 0 && p0 < L) v = __ldg(reinterpret_cast<const float4 *>(row + p0));
+        f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
     } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = (live && p0 + j >= 0 && p0 + j < L) ? __ldg(row + p0 + j) : 0.f;
+        for (int j = 0; j < 4; ++j) f[j] = (live && p0 + j >= 0 && p0 + j < L) ? __ldg(row + p0 + j) : 0.f;
     }
 }
 
-__device__ __forceinline__ void store_split8(uint8_t *hi_dst, uint8_t *lo_dst, const float *f) {
-    uint32_t h[4], l[4];
+// half of a 16-byte operand row: 4 consecutive K elements, hi and lo parts
+__device__ __forceinline__ void store_split4(uint8_t *hi_dst, uint8_t *lo_dst, const float *f) {
+    uint32_t h[2], l[2];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) split2_bf16(f[2 * e], f[2 * e + 1], h[e], l[e]);
-    *reinterpret_cast<uint4 *>(hi_dst) = make_uint4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<uint4 *>(lo_dst) = make_uint4(l[0], l[1], l[2], l[3]);
+    for (int e = 0; e < 2; ++e) split2_bf16(f[2 * e], f[2 * e + 1], h[e], l[e]);
+    *reinterpret_cast<uint2 *>(hi_dst) = make_uint2(h[0], h[1]);
+    *reinterpret_cast<uint2 *>(lo_dst) = make_uint2(l[0], l[1]);
 }
 
 __global__ void __launch_bounds__(wg::NT, 1)
@@ -86,7 +89,7 @@ post1_wgrad_tc_kernel(const float *__restrict__ x, const float *__restrict__ dz,
 
     if (warp == NCONV / 32) {
         // ================= MMA issuer =================
-        const uint32_t idesc = make_idesc_bf16(MT, NTILE);
+        const uint32_t idesc4 = make_idesc_bf16(MT, 4 * NTILE), idesc1 = make_idesc_bf16(MT, NTILE);
         const uint64_t adesc_t = desc_template(APANEL, 128), bdesc_t = desc_template(BPANEL, 128);
         const uint32_t base = smem_u32(smem);
         int s = 0, ph = 0;
@@ -98,14 +101,14 @@ post1_wgrad_tc_kernel(const float *__restrict__ x, const float *__restrict__ dz,
             const uint32_t a0 = base + s * STAGE, b0 = a0 + ASTAGE;
 #pragma unroll 1
             for (int j = 0; j < NPANEL / 2; ++j) {
-#pragma unroll 1
-                for (int tap = 0; tap < NTAP; ++tap) {
 #pragma unroll
-                    for (int pass = 0; pass < 3; ++pass) {
-                        const uint64_t adesc = desc_at(adesc_t, a0 + (pass == 1) * AHALF + 2 * j * APANEL);
-                        const uint64_t bdesc = desc_at(bdesc_t, b0 + (2 * tap + (pass == 2)) * BHALF + 2 * j * BPANEL);
-                        const bool acc = !(st == 0 && j == 0 && pass == 0);
-                        if (elect_one()) mma_bf16(tmem + tap * NTILE, adesc, bdesc, idesc, acc);
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint64_t adesc = desc_at(adesc_t, a0 + (pass == 1) * AHALF + 2 * j * APANEL);
+                    const uint32_t baddr = b0 + (pass == 2) * BHALF + 2 * j * BPANEL;
+                    const bool acc = !(st == 0 && j == 0 && pass == 0);
+                    if (elect_one()) {
+                        mma_bf16(tmem, adesc, desc_at(bdesc_t, baddr), idesc4, acc);                                      // taps 0..3
+                        mma_bf16(tmem + 4 * NTILE, adesc, desc_at(bdesc_t, baddr + 4 * NTILE * 16), idesc1, acc);        // tap 4
                     }
                 }
             }
@@ -116,65 +119,70 @@ post1_wgrad_tc_kernel(const float *__restrict__ x, const float *__restrict__ dz,
         if (!ok && lane == 0) atomicExch(status, 26);
     } else {
         // ================= converter warps =================
-        // A units: (row r = tid % 128, panel tid / 128) and the same row two panels further; B unit: (row tid % 64, panel tid / 64).
-        // Lanes of a warp are consecutive rows of one panel: conflict-free 16-byte stores, and one (item, chunk) per warp.
+        // Unit = (channel row, HALF a k-panel: 4 positions = one float4).  The 8 lanes of an octet are the 8 float4 of one
+        // row's 32 positions of the stage, a warp is 4 rows: every load instruction reads 4 x 128 contiguous bytes (4 cache
+        // lines, all sectors used).  (With lanes along rows a request touched 32 sectors in 8-32 lines and the L1 data stage
+        // -- 95 % busy in ncu -- set the pace at 2.2x the MMA time.)  Thread: rows rq and rq + 64 of dz, row rq of x.  16 warps:
+        // the split is a chain of fixed-latency conversions, and 8 warps left the schedulers waiting on it (IPC 1.9).
         const bool vec = (L & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dz)) & 15) == 0;
-        const int ar = tid & (MT - 1), ap = tid >> 7;       // panels ap, ap + 2
-        const int br = tid & (NTILE - 1), bp = tid >> 6;
-        float acc_db = 0.f;
+        const int l8 = tid & 7, rq = tid >> 3, pm = l8 >> 1, hf = l8 & 1;
+        float acc_db[2] = {0.f, 0.f};
         int s = 0, ph = 0;
         bool ok = true;
-#pragma unroll 1
-        for (int st = 0; st < nstages; ++st) {
-            // loads first (they do not depend on the ring), then wait for the slot
-            float fa[2][8], fb[16];
+        // fa[u]: positions p0 .. p0+3 of dz row rq + 64u; fb: positions p0-4 .. p0+7 of x row rq (p0 = 8c + 4 hf)
+        auto load_stage = [&](int st, float (&fa)[2][4], float (&fb)[12]) {
+            const int q = st * NPANEL + pm;
+            const bool live = q < npanels;
+            const int b = live ? q / ppi : 0, c = q - b * ppi, p0 = 8 * c + 4 * hf;
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int q = st * NPANEL + ap + 2 * u;
-                const bool live = q < npanels;
-                const int b = live ? q / ppi : 0, c = q - b * ppi;
-                load8(dz + ((size_t)b * C + co0 + ar) * L, 8 * c, L, vec, live, fa[u]);
-            }
-            {
-                const int q = st * NPANEL + bp;
-                const bool live = q < npanels;
-                const int b = live ? q / ppi : 0, c = q - b * ppi;
-                const float *row = x + ((size_t)b * C + ci0 + br) * L;
-                float lo4[8], hi4[8];
-                load8(row, 8 * c - 4, L, vec, live, lo4);   // positions 8c-4 .. 8c+3
-                load8(row, 8 * c + 4, L, vec, live, hi4);   // positions 8c+4 .. 8c+11
+            for (int u = 0; u < 2; ++u) load4(dz + ((size_t)b * C + co0 + rq + 64 * u) * L, p0, L, vec, live, fa[u]);
+            const float *row = x + ((size_t)b * C + ci0 + rq) * L;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { fb[j] = lo4[j]; fb[8 + j] = hi4[j]; }
-            }
+            for (int k = 0; k < 3; ++k) load4(row, p0 - 4 + 4 * k, L, vec, live, &fb[4 * k]);
+        };
+        auto store_stage = [&](const float (&fa)[2][4], const float (&fb)[12]) {
             if (ok && !mbar_wait(&empty[s], ph ^ 1)) { ok = false; if (lane == 0) atomicExch(status, 27); }
-            uint8_t *a = smem + s * STAGE, *bb = a + ASTAGE;
+            uint8_t *a = smem + s * STAGE + pm * APANEL + hf * 8, *bb = smem + s * STAGE + ASTAGE + pm * BPANEL + hf * 8;
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-                uint8_t *dst = a + (ap + 2 * u) * APANEL + ar * 16;
-                store_split8(dst, dst + AHALF, fa[u]);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc_db += fa[u][j];
+                uint8_t *dst = a + (rq + 64 * u) * 16;
+                store_split4(dst, dst + AHALF, fa[u]);
+                acc_db[u] += (fa[u][0] + fa[u][1]) + (fa[u][2] + fa[u][3]);
             }
 #pragma unroll
             for (int tap = 0; tap < NTAP; ++tap) {
-                // X_tap[ci][l] = x[ci][l + tap - PAD]; fb[j] holds position 8c - 4 + j
-                uint8_t *dst = bb + (2 * tap) * BHALF + bp * BPANEL + br * 16;
-                store_split8(dst, dst + BHALF, &fb[4 + tap - PAD]);
+                // X_tap[ci][l] = x[ci][l + tap - PAD]; fb[j] holds position p0 - 4 + j
+                uint8_t *dst = bb + (tap * NTILE + rq) * 16;
+                store_split4(dst, dst + BHALF, &fb[4 + tap - PAD]);
             }
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&full[s]);
             if (++s == NSTAGE) { s = 0; ph ^= 1; }
+        };
+        // software pipeline: the NEXT stage's global loads are in flight while this one is split and stored (a stage is
+        // consumed in ~1.4k cycles of MMAs; an exposed L2 round trip per stage would double that)
+        float fa0[2][4], fb0[12], fa1[2][4], fb1[12];
+        load_stage(0, fa0, fb0);
+#pragma unroll 1
+        for (int st = 0; st < nstages; st += 2) {
+            if (st + 1 < nstages) load_stage(st + 1, fa1, fb1);
+            store_stage(fa0, fb0);
+            if (st + 1 < nstages) {
+                if (st + 2 < nstages) load_stage(st + 2, fa0, fb0);
+                store_stage(fa1, fb1);
+            }
         }
-        dbsum[tid] = acc_db;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) dbsum[u * NCONV + tid] = acc_db[u];
         // ================= epilogue: TMEM [co][tap][ci] -> dW [co][ci][tap] =================
         if (ok && !mbar_wait(done, 0)) { ok = false; if (lane == 0) atomicExch(status, 28); }
         tc_fence_after();
-        const int q = warp & 3, half = warp >> 2;             // TMEM lane quadrant, half of the ci columns
+        const int q = warp & 3, half = warp >> 2;             // TMEM lane quadrant, quarter of the ci columns
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
         float *out = dw + ((size_t)(co0 + q * 32 + lane) * C + ci0) * NTAP;
 #pragma unroll 1
-        for (int g = half * (NTILE / 16); g < (half + 1) * (NTILE / 16); ++g) {
+        for (int g = half * (NTILE / 32); g < (half + 1) * (NTILE / 32); ++g) {
             uint32_t w[NTAP][8];
 #pragma unroll
             for (int tap = 0; tap < NTAP; ++tap) tmem_ld8(lane_addr + tap * NTILE + g * 8, w[tap]);
@@ -191,7 +199,10 @@ post1_wgrad_tc_kernel(const float *__restrict__ x, const float *__restrict__ dz,
     }
     tc_fence_before();
     __syncthreads();
-    if (blockIdx.y == 0 && tid < MT) db[co0 + tid] = dbsum[tid] + dbsum[tid + MT];
+    if (blockIdx.y == 0 && tid < MT) {  // row tid = 64 u + rq: the eight float4 lanes of that row, in position order
+        const float *p = dbsum + (tid >> 6) * NCONV + (tid & 63) * 8;
+        db[co0 + tid] = ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
+    }
     if (warp == NCONV / 32) tmem_dealloc(tmem, TMEM_COLS);
 }
 

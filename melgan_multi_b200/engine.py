@@ -96,6 +96,11 @@ def lib():
                                          ctypes.c_void_p, ctypes.c_void_p]
         L.mg_msd_post1_wgrad.restype = ctypes.c_int
         L.mg_msd_post1_wgrad.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        L.mg_msd_edge_backward_workspace_bytes.restype = ctypes.c_size_t
+        L.mg_msd_edge_backward_workspace_bytes.argtypes = [ctypes.c_int] * 3
+        L.mg_msd_edge_backward.restype = ctypes.c_int
+        L.mg_msd_edge_backward.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 6 + [
+            ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
         L.mg_lrelu_backward.restype = ctypes.c_int
         L.mg_lrelu_backward.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_longlong, ctypes.c_void_p]
         L.mg_msd_wn_backward.restype = ctypes.c_int
@@ -523,6 +528,26 @@ class DiscriminatorDevice:
             check(lib().mg_msd_post1_dgrad(self.packed.data_ptr(), scale, dz.data_ptr(), dx.data_ptr(), Bt, L,
                                            self.status.data_ptr(), stream))
         return dx
+
+    def edge_backward(self, scale, layer, dz, x, need_dx=True):
+        """(dx | None, dw, db) of conv_pre (layer 0) or conv_post2 (layer 6) of discriminator `scale`; dw in the torch layout."""
+        torch = self.torch
+        x, dz = x.contiguous(), dz.contiguous()
+        Bt, L = x.shape[0], x.shape[2]
+        cin, cout, k = (1, 16, 15) if layer == 0 else (1024, 1, 3)
+        if tuple(x.shape) != (Bt, cin, L) or tuple(dz.shape) != (Bt, cout, L):
+            raise EngineError(f"edge_backward(layer {layer}) expects x [Bt, {cin}, L] and dz [Bt, {cout}, L]")
+        dx = torch.empty_like(x) if need_dx else None
+        dw = torch.empty((cout, cin, k), dtype=torch.float32, device=x.device)
+        db = torch.empty((cout,), dtype=torch.float32, device=x.device)
+        nbytes = lib().mg_msd_edge_backward_workspace_bytes(layer, Bt, L)
+        ws = torch.empty(max(nbytes // 4, 1), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            check(lib().mg_msd_edge_backward(self.packed.data_ptr(), scale, layer, dz.data_ptr(), x.data_ptr(),
+                                             dx.data_ptr() if need_dx else None, dw.data_ptr(), db.data_ptr(),
+                                             ws.data_ptr(), nbytes, Bt, L, stream))
+        return dx, dw, db
 
     def post1_wgrad(self, x, dz):
         """(dW [1024, 1024, 5], db [1024]) of conv_post1 from its input x and dz, both [Bt, 1024, L] (tcgen05, split-bf16)."""

@@ -19,8 +19,8 @@ What runs where
   * ``feature_loss`` / ``generator_loss`` / ``discriminator_loss`` (models.py:138-167) on CUDA tensors: every term of a
     loss is a row of one fused reduction launch (forward) and one gradient launch (backward).
   * Backward: the generator's runs as recomputation through stock PyTorch ops; the discriminators' walks the saved
-    feature maps layer by layer with hand-written kernels for the grouped convs and weight-norm and
-    aten::convolution_backward for the three dense layers.  Open row in DESIGN.md (native tcgen05 dgrad / wgrad).
+    feature maps layer by layer on hand-written kernels only (grouped convs, conv_post1 dgrad / wgrad on tcgen05,
+    conv_pre / conv_post2, LeakyReLU, weight-norm): no cuDNN call in a discriminator's backward.
 """
 import torch
 import torch.nn as nn
@@ -250,8 +250,9 @@ class Discriminator(nn.Module):
 class _MSDFunction(torch.autograd.Function):
     """ONE discriminator of the stack as an autograd node: forward on the fused sm_100a kernels, backward layer by layer on
     the saved feature maps without recomputing the forward -- the grouped k41 convs (layers 1..4) and weight-norm on the
-    hand-written kernels of csrc/mg_disc_bwd.cu (cuDNN launches one kernel per group for them), the dense layers
-    (conv_pre, conv_post1, conv_post2) through aten::convolution_backward (open row: native tcgen05 dgrad/wgrad).
+    hand-written kernels of csrc/mg_disc_bwd.cu (cuDNN launches one kernel per group for them), conv_post1 (88 % of the
+    FLOPs) on the tcgen05 kernels of csrc/mg_conv_tc.cu (dgrad, transposed weight copy) and csrc/mg_wgrad_tc.cu (wgrad),
+    conv_pre / conv_post2 on the bandwidth-bound kernels of csrc/mg_disc_edge_bwd.cu.  No aten / cuDNN call is left.
 
     The three scales of a MultiScaleDiscriminator are three nodes that share one forward: the first node to run launches the
     whole fused stack (real and generated stacked as one batch, the scales on forked streams) and parks the feature maps
@@ -297,10 +298,8 @@ class _MSDFunction(torch.autograd.Function):
             elif l == 5:  # conv_post1 (88 % of a discriminator's FLOPs): data and weight gradients on the tcgen05 kernels
                 g = dev.post1_dgrad(s, dz)
                 dws[l], dbs[l] = dev.post1_wgrad(inputs[l], dz)
-            else:
-                w = torch._weight_norm(params[3 * l], params[3 * l + 1], 0)
-                g, dws[l], dbs[l] = torch.ops.aten.convolution_backward(
-                    dz, inputs[l], w, [cout], [stride], [pad], [1], False, [0], 1, [need_dx, True, True])
+            else:  # conv_pre / conv_post2: bandwidth-bound SIMT kernels (csrc/mg_disc_edge_bwd.cu)
+                g, dws[l], dbs[l] = dev.edge_backward(s, l, dz, inputs[l], need_dx)
         gy = None
         if need_y and g is not None:  # back through the (linear) AvgPool chain: differentiate it on zeros
             gy = g

@@ -1,4 +1,4 @@
-"""conv_post1 (Conv1d 1024 -> 1024, k5) backward at the three training shapes (2 x 16 items, 32 / 16 / 8 positions): the tcgen05
+"""conv_post1 (Conv1d 1024 -> 1024, k5) backward at the three training shapes (2 x 16 items of 8192 samples: 128 / 65 / 33 positions): the tcgen05
 data- and weight-gradient kernels (split-bf16, fp32-grade) against aten.convolution_backward (cuDNN, TF32 default)."""
 import json
 import sys
@@ -30,7 +30,7 @@ def timed(fn, n=50):
 
 
 out = {}
-for s, L in enumerate((32, 16, 8)):
+for s, L in enumerate((128, 65, 33)):
     conv = d.discriminators[s].layers()[5]
     w = torch._weight_norm(conv.weight_v, conv.weight_g, 0).detach()
     x = torch.randn(32, 1024, L, device="cuda")

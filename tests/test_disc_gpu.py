@@ -206,6 +206,31 @@ def test_conv_post1_gradients_match_fp64(msd_module, Bt, L):
         assert m < 5e-5 and l2 < 3e-5, (name, m, l2)
 
 
+@pytest.mark.parametrize("layer,Bt,L", [(0, 3, 1300), (0, 2, 8192), (0, 2, 5), (0, 1, 512), (6, 3, 33), (6, 32, 128), (6, 2, 1), (6, 5, 65)])
+def test_edge_layer_backward_matches_fp64(msd_module, layer, Bt, L):
+    """csrc/mg_disc_edge_bwd.cu (dx, dw, db of conv_pre and conv_post2, models.py:77,85) against autograd of F.conv1d in float64:
+    tile boundaries (512 positions), sequences shorter than the kernel, single positions."""
+    import torch.nn.functional as F
+    from melgan_multi_b200.synth import DISCRIMINATOR_LAYERS
+    with torch.no_grad():
+        msd_module(torch.zeros(1, 1, 64).cuda(), torch.zeros(1, 1, 64).cuda())  # makes sure the weights are packed
+    scale = 1
+    _n, cin, cout, k, stride, groups, pad = DISCRIMINATOR_LAYERS[layer]
+    conv = msd_module.discriminators[scale].layers()[layer]
+    w = torch._weight_norm(conv.weight_v, conv.weight_g, 0).detach().double().requires_grad_(True)
+    gen = torch.Generator(device="cpu").manual_seed(77 * layer + 13 * Bt + L)
+    x = torch.randn(Bt, cin, L, generator=gen).cuda()
+    dz = torch.randn(Bt, cout, L, generator=gen).cuda()
+    xd = x.double().requires_grad_(True)
+    rdx, rdw = torch.autograd.grad(F.conv1d(xd, w, None, stride, pad), (xd, w), dz.double())
+    dx, dw, db = msd_module._dev.edge_backward(scale, layer, dz, x)
+    for name, got, ref in (("dx", dx, rdx), ("dw", dw, rdw), ("db", db, dz.double().sum(dim=(0, 2)))):
+        assert got.shape == ref.shape, (name, got.shape, ref.shape)
+        m, l2 = rel_errors(got.cpu().numpy(), ref.float().cpu().numpy())
+        assert m < 1e-5 and l2 < 1e-5, (name, m, l2)
+    assert msd_module._dev.edge_backward(scale, layer, dz, x, need_dx=False)[0] is None
+
+
 def test_standalone_discriminator_forward_and_backward(golden, dstate, msd_module):
     """Discriminator.forward on its own (reference models.py:87-103: returns (flattened logits, 7 feature maps)): scale 0 of
     the reference golden is exactly discriminators[0] applied to y, so the stand-alone module must reproduce it; its
