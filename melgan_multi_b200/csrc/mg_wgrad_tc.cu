@@ -12,8 +12,8 @@
 //   stage (32 positions = 2 K16 steps): A = split(dz) [hi|lo][4 k-panels][128 rows][16 B] = 16 KB   (+ 32 B per panel, below)
 //                                       B = split(x)  [hi|lo][4 k-panels][tap 5][64 rows][16 B] = 40 KB     x 3 stages
 // The five copies are stacked along N, so one K16 step is an N = 256 MMA (taps 0..3) plus an N = 64 one (tap 4) instead of five
-// N = 64 ones: an MMA's cost is dominated by fetching its 128 x 16 A operand from shared memory (measured ~80 cycles at N = 64,
-// ~96 at N = 128 in the ResBlock kernels), so wide N is what amortises it.
+// N = 64 ones: every MMA re-reads its 128 x 16 A operand from shared memory, so five narrow MMAs read 30 KB of operands per
+// (K16 step, pass) for 160 cycles of math -- shared-memory bound -- and the two stacked ones 18 KB: math bound.
 // Positions are padded per item to a multiple of 8 (one k-panel never straddles two items), the K extent to a multiple of 32.
 #include "mg_common.cuh"
 #include "mg_tc.cuh"
