@@ -204,7 +204,7 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
     uint64_t *xready = done + 1;  // [NH]: X channels [h*C/NH, (h+1)*C/NH) of the next conv are written (all epilogue threads arrive)
     uint64_t *dup = xready + Cfg::NH;  // [2] tail ConvT (stride 8): accumulator buffer complete;  tfree[2]: drained by the epilogue
     uint64_t *tfree = dup + 2;
-    uint64_t *lfull = tfree + 2;        // [NSTAGE] TMA input slab landed in ring slot s;  lempty[NSTAGE]: converted by every epilogue warp
+    uint64_t *lfull = tfree + 2;        // [NSTAGE] TMA input slab landed in ring slot s;  lempty[NSTAGE]: converted by every epilogue thread
     uint64_t *lempty = lfull + NSTAGE;
     uint64_t *rfree = lempty + NSTAGE;  // pair: both CTAs' input slabs are consumed, the leader may multicast weights into both rings
     uint64_t *pfull = rfree + 1;        // [NSTAGE] G2, leader: the PEER's half of ring slot s has landed (relayed by its issuer warp)
@@ -257,7 +257,7 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
         mbar_init(done, NIW * CL);
         for (int h = 0; h < Cfg::NH; ++h) mbar_init(&xready[h], Cfg::XARRIVE);
         for (int k = 0; k < 2; ++k) { mbar_init(&dup[k], NIW * CL); mbar_init(&tfree[k], NEPI); }
-        for (int k = 0; k < NSTAGE; ++k) { mbar_init(&lfull[k], 1); mbar_init(&lempty[k], NEPI / 32); }
+        for (int k = 0; k < NSTAGE; ++k) { mbar_init(&lfull[k], 1); mbar_init(&lempty[k], NEPI); }
         mbar_init(rfree, CL);
         fence_mbar_init();
     }
@@ -743,8 +743,8 @@ resblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y, const flo
                     }
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&lempty[sl]);  // this warp is done reading the slot
+            mbar_arrive(&lempty[sl]);  // this thread is done reading the slot (every thread arrives for itself: its release covers
+                                       // its own reads, which is also the form compute-sanitizer's racecheck can follow)
             if ((k + 1) * LCH % (C / NH) == 0) {      // a channel half (or everything) of conv 0's input is in place
                 const int h = (k + 1) * LCH / (C / NH) - 1;
                 tmem_st_wait();

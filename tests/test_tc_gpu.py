@@ -67,7 +67,7 @@ def test_resblock_cta_group2_variant_matches_oracle(state):
     import sys
     code = (
         "import os, sys, numpy as np, torch\n"
-        "sys.path.insert(0, '.'); sys.path.insert(0, 'tests')\n"
+        "sys.path.insert(0, '.'); sys.path.insert(0, 'tests'); sys.path.insert(0, 'tests/golden')\n"
         "from melgan_multi_b200 import engine, synth\n"
         "import test_tc_gpu as t\n"
         "state = synth.generator_state(1234)\n"
