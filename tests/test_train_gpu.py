@@ -67,6 +67,53 @@ def test_train_step_losses_and_gradients_match_reference(strict_fp32, which):
     print("worst relative gradient-norm error (%s):" % which, max(w1, w2, w3))
 
 
+def test_backward_arithmetic_matches_float64_autograd_under_a_smooth_loss(strict_fp32):
+    """The digest test above is bounded by the L1 feature loss (sign flips of r - g), not by arithmetic.  Here the loss is
+    smooth -- the mean square of every feature map and logit, real and generated -- so the whole backward chain (the
+    discriminators' native kernels: grouped convs, conv_post1 dgrad / wgrad on tcgen05, conv_pre / conv_post2, LeakyReLU,
+    weight-norm; the AvgPool chain; the generator's recompute) is compared ELEMENT-WISE with float64 autograd of the stock-op
+    graph (models.py:61-71,87-135 of the reference restated in _torch_forward), on EVERY element.
+    Discriminator parameters (native backward end to end): 1e-4 of each gradient's maximum (measured 3.8e-5).
+    Generator parameters: 2e-3 (measured 9.5e-4).  Their gradients pass through the generator's own LeakyReLU kinks: a
+    forward that differs by 1e-5 flips the derivative of the ~1e-5 of the activations that sit that close to zero, which
+    moves a cancelling sum over N positions (a bias or weight_g gradient) by ~sqrt(N) * 1e-5 of its size."""
+    from melgan_multi_b200 import models
+    B, T = 2, 8
+    gen = models.Generator()
+    gen.load_state_dict({k: torch.from_numpy(v) for k, v in synth.generator_state(1234).items()})
+    msd = models.MultiScaleDiscriminator()
+    msd.load_state_dict({k: torch.from_numpy(v) for k, v in synth.discriminator_state(4321).items()})
+    gen, msd = gen.cuda().train(), msd.cuda().train()
+    x = torch.from_numpy(synth.mel_input(B, T, 31)).cuda()
+    y = torch.from_numpy(synth.audio_input(B, 256 * T, 32)).cuda()
+
+    _dr, _dg, fr, fg = msd(y, gen(x))
+    loss = sum((m ** 2).mean() for maps in fr + fg for m in maps)
+    loss.backward()
+
+    def leaves64(mod):
+        vs, gs, bs = mod._param_triplets()
+        return [t.detach().double().requires_grad_(True) for trip in zip(vs, gs, bs) for t in trip]
+    gl, dl = leaves64(gen), leaves64(msd)
+    outs = msd._torch_forward(torch.cat([y.double(), gen._torch_forward(x.double(), gl)]), dl)
+    loss64 = sum((o[:B] ** 2).mean() + (o[B:] ** 2).mean() for o in outs)
+    assert abs(loss.item() / loss64.item() - 1) < 1e-5
+    ref = torch.autograd.grad(loss64, gl + dl)
+
+    def params(mod):
+        vs, gs, bs = mod._param_triplets()
+        return [t for trip in zip(vs, gs, bs) for t in trip]
+    worst = {"G": (0.0, 0.0), "D": (0.0, 0.0)}
+    for i, (p, r) in enumerate(zip(params(gen) + params(msd), ref)):
+        m, l2 = rel_errors(p.grad.cpu().numpy(), r.float().cpu().numpy())
+        which = "G" if i < 90 else "D"
+        worst[which] = (max(worst[which][0], m), max(worst[which][1], l2))
+        tol = 2e-3 if which == "G" else 1e-4
+        assert m < tol and l2 < tol, (which, i, tuple(p.shape), m, l2)
+    msd._dev.check_status()
+    print("worst element-wise gradient error (max-rel, l2-rel) under a smooth loss, vs float64:", worst)
+
+
 def test_training_with_multi_tensor_adam_tracks_torch_adam():
     """melgan_multi_b200.optim.Adam writes parameters through raw pointers; the modules re-fold their
     packed weights only when a parameter's (data_ptr, _version) changes, so the optimizer must bump the versions or every
