@@ -110,7 +110,9 @@ __global__ void __launch_bounds__(128) grouped_dx4_kernel(const float *__restric
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// dw, db partial sums.  CTA = (chunk of (item, 128-output tile) pairs, group); thread (ci, k) owns the COG outputs
+// dw, db partial sums, generic form (the model's four grouped layers all take the specialisations below -- grouped_dw4_kernel,
+// grouped_dw1_kernel -- this is the readable statement of the same sums for any COG / stride).
+// CTA = (chunk of (item, 128-output tile) pairs, group); thread (ci, k) owns the COG outputs
 // dw[.][ci][k]; threads 164 .. 164 + COG - 1 own db.  partial: [chunk][group][164 * COG + COG].
 template <int COG, int S>
 __global__ void __launch_bounds__(192) grouped_dw_kernel(const float *__restrict__ dz, const float *__restrict__ x,
@@ -164,6 +166,88 @@ __global__ void __launch_bounds__(192) grouped_dw_kernel(const float *__restrict
         for (int c = 0; c < COG; ++c) out[tid * COG + c] = acc[c];
     } else if (tid < 164 + COG) {
         out[164 * COG + (tid - 164)] = bacc;
+    }
+}
+
+// Stride-4 specialisation of dw (layers 1..3: 16 output channels per group).  With k = 4 j + r the input index of output t is
+// 4 (t + j) + r - 20: the 11 taps of one residue r read ONE phase signal x[4 u + r] at u = t + j, so a thread that owns
+// (ci, r, six consecutive j, eight output channels) keeps a six-value sliding window of that signal in registers and does
+// 48 FMAs per output position for 3 shared-memory loads (two float4 of dz, one new x value); the generic kernel: 16 per 5,
+// i.e. bound by shared-memory loads.  64 threads = 4 ci x 4 r x 2 tap halves x 2 channel halves; partial layout as above.
+__global__ void __launch_bounds__(64) grouped_dw4_kernel(const float *__restrict__ dz, const float *__restrict__ x,
+                                                        float *__restrict__ partial, int Bt, int Cin, int Cout, int Lin, int Lout,
+                                                        int tiles_per_item, int tiles_per_chunk) {
+    constexpr int COG = 16, TT = 128, XW = 4 * TT + 44;  // (XW % 32 = 12: the two ci of a warp read different banks)
+    __shared__ __align__(16) float zs[TT * COG];         // [t][co]
+    __shared__ float xs[4 * XW];                          // [ci][position - (4 t0 - 20)]
+    const int g = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+    const int ch = tid & 1, jh = (tid >> 1) & 1, r = (tid >> 2) & 3, ci = tid >> 4;
+    const int j0 = 6 * jh;
+    float acc[6][8];
+#pragma unroll
+    for (int jj = 0; jj < 6; ++jj)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[jj][c] = 0.f;
+    float bacc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) bacc[c] = 0.f;
+    const int total = Bt * tiles_per_item;
+    const int first = chunk * tiles_per_chunk, last = min(total, first + tiles_per_chunk);
+    const float *xr = xs + ci * XW + 4 * j0 + r;  // window element (t, jj) = xr[4 (t + jj)]
+#pragma unroll 1
+    for (int tile = first; tile < last; ++tile) {
+        const int b = tile / tiles_per_item, t0 = (tile - b * tiles_per_item) * TT;
+        __syncthreads();
+        // (staging loops unrolled: with 64 threads a tile is ~70 loads per thread, and one exposed L2 round trip per load would
+        //  cost more than the tile's FMAs)
+#pragma unroll 8
+        for (int i = tid; i < TT * COG; i += 64) {
+            const int co = i / TT, t = i - co * TT;  // coalesced along t
+            zs[t * COG + co] = (t0 + t < Lout) ? dz[((size_t)b * Cout + g * COG + co) * Lout + t0 + t] : 0.f;
+        }
+#pragma unroll 7
+        for (int i = tid; i < 4 * XW; i += 64) {
+            const int c = i / XW, p = 4 * t0 - 20 + (i - c * XW);
+            xs[i] = (p >= 0 && p < Lin && i - c * XW < 4 * TT + 40) ? x[((size_t)b * Cin + g * 4 + c) * Lin + p] : 0.f;
+        }
+        __syncthreads();
+        float w[6];  // slot (t + jj) % 6 holds the window element (t, jj)
+#pragma unroll
+        for (int jj = 0; jj < 5; ++jj) w[jj] = xr[4 * jj];
+        const int nt = min(TT, Lout - t0);  // (a short sequence's last tile is mostly padding: 33 of 128 positions at scale 2)
+#pragma unroll 1
+        for (int t = 0; t < nt; t += 6) {
+#pragma unroll
+            for (int tt = 0; tt < 6; ++tt) {
+                if (t + tt < nt) {
+                    w[(tt + 5) % 6] = xr[4 * (t + tt + 5)];
+                    const float4 za = *reinterpret_cast<const float4 *>(zs + (t + tt) * COG + 8 * ch);
+                    const float4 zb = *reinterpret_cast<const float4 *>(zs + (t + tt) * COG + 8 * ch + 4);
+                    const float z[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
+#pragma unroll
+                    for (int jj = 0; jj < 6; ++jj)
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) acc[jj][c] = fmaf(z[c], w[(tt + jj) % 6], acc[jj][c]);
+                    if (tid < 2) {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) bacc[c] += z[c];
+                    }
+                }
+            }
+        }
+    }
+    float *out = partial + ((size_t)chunk * gridDim.y + g) * (165 * COG);
+#pragma unroll
+    for (int jj = 0; jj < 6; ++jj) {
+        const int k = 4 * (j0 + jj) + r;
+        if (k <= 40) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) out[(ci * 41 + k) * COG + 8 * ch + c] = acc[jj][c];
+        }
+    }
+    if (tid < 2) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) out[164 * COG + 8 * tid + c] = bacc[c];
     }
 }
 
@@ -350,14 +434,15 @@ int launch_lrelu_grad(const float *g1, const float *g2, const float *out, float 
     return MG_OK;
 }
 
+constexpr int kDw4Ctas = 1184;  // grouped_dw4_kernel: 64 threads and 17 KB of shared memory per CTA -> 8 per SM
 struct GroupedBwdPlan {
     int tiles_per_item, tiles_per_chunk, chunks;
 };
-static GroupedBwdPlan grouped_plan(int groups, int Bt, int Lout) {
+static GroupedBwdPlan grouped_plan(int groups, int Bt, int Lout, int ctas = 592) {
     GroupedBwdPlan p;
     p.tiles_per_item = (Lout + 127) / 128;
     const int total = Bt * p.tiles_per_item;
-    int want = (592 + groups - 1) / groups;  // ~4 CTAs per SM over all groups
+    int want = (ctas + groups - 1) / groups;  // ~4 CTAs per SM over all groups (192-thread kernels), ~8 for the 64-thread one
     if (want > total) want = total;
     if (want < 1) want = 1;
     p.tiles_per_chunk = (total + want - 1) / want;
@@ -371,7 +456,8 @@ static int group_blocks(int groups, int cog, int stride) { return (stride == 1 &
 size_t grouped_bwd_workspace_bytes(int l, int Bt, int Lout) {
     const DLayer d = d_layer(l);
     const int cog = d.cout / d.groups;
-    return (size_t)grouped_plan(group_blocks(d.groups, cog, d.stride), Bt, Lout).chunks * d.groups * 165 * cog * sizeof(float);
+    return (size_t)grouped_plan(group_blocks(d.groups, cog, d.stride), Bt, Lout, d.stride == 4 ? kDw4Ctas : 592).chunks * d.groups * 165 * cog *
+           sizeof(float);
 }
 
 template <int COG, int S>
@@ -392,8 +478,11 @@ static int grouped_backward(const float *w, const float *dz, const float *x, flo
         MG_CUDA_TRY(cudaGetLastError());
     }
     if (dw) {
-        const GroupedBwdPlan p = grouped_plan(group_blocks(groups, COG, S), Bt, Lout);
-        if (S == 1 && COG == 4 && Cin == 1024) {
+        const GroupedBwdPlan p = grouped_plan(group_blocks(groups, COG, S), Bt, Lout, S == 4 ? kDw4Ctas : 592);
+        if (S == 4 && COG == 16) {
+            dim3 grid(p.chunks, groups);
+            grouped_dw4_kernel<<<grid, 64, 0, s>>>(dz, x, ws, Bt, Cin, Cout, Lin, Lout, p.tiles_per_item, p.tiles_per_chunk);
+        } else if (S == 1 && COG == 4 && Cin == 1024) {
             dim3 grid(p.chunks, groups / kG1Groups);
             grouped_dw1_kernel<<<grid, 192, 0, s>>>(dz, x, ws, Bt, Lin, p.tiles_per_item, p.tiles_per_chunk);
         } else {
