@@ -62,11 +62,20 @@ __global__ void __launch_bounds__(128) grouped_dx4_kernel(const float *__restric
     __shared__ __align__(16) float ws[COG * 4 * KP];               // [co][ci][k]
     __shared__ float zs[COG * NT_];
     const int p0 = blockIdx.x * TP, g = blockIdx.y, b = blockIdx.z;
-    for (int i = threadIdx.x; i < COG * 4 * KP; i += 128) {
-        const int co = i / (4 * KP), ci = (i / KP) & 3, k = i % KP;
-        ws[i] = k < 41 ? w[(size_t)g * 4 * 41 * COG + (ci * 41 + k) * COG + co] : 0.f;
+    // staging: loads in global order (coalesced), loops unrolled so that a thread's ~40 loads are in flight together -- a CTA's
+    // 2.8 k FMAs per thread are cheaper than 40 exposed L2 round trips
+    if (threadIdx.x < COG * 4) {  // zero padding of taps 41..43
+        float *pz = ws + threadIdx.x * KP + 41;
+        pz[0] = 0.f; pz[1] = 0.f; pz[2] = 0.f;
+    }
+    const float *wg = w + (size_t)g * 4 * 41 * COG;
+#pragma unroll 7
+    for (int i = threadIdx.x; i < COG * 4 * 41; i += 128) {
+        const int cik = i / COG, co = i - cik * COG, ci = cik / 41, k = cik - ci * 41;
+        ws[(co * 4 + ci) * KP + k] = wg[i];
     }
     const int tb = p0 / 4 - 5;  // dz position of zs column 0: t = j + 5 - q >= p0/4 - 5
+#pragma unroll 6
     for (int i = threadIdx.x; i < COG * NT_; i += 128) {
         const int co = i / NT_, t = tb + i % NT_;
         zs[i] = (t >= 0 && t < Lout) ? dz[((size_t)b * Cout + g * COG + co) * Lout + t] : 0.f;
