@@ -275,16 +275,25 @@ __global__ void __launch_bounds__(128) grouped_dx1_kernel(const float *__restric
     __shared__ __align__(16) float zs[NG * 4 * ZW];   // [group, co][position - (p0 - 20)]
     __shared__ float ws[NG * 16 * KP];                 // [group][co][ci][k]
     const int p0 = blockIdx.x * TP, g0 = blockIdx.y * NG, b = blockIdx.z;
-    for (int i = threadIdx.x; i < NG * 16 * KP; i += 128) {
-        const int g = i / (16 * KP), co = (i / (4 * KP)) & 3, ci = (i / KP) & 3, k = i % KP;
-        ws[i] = k < 41 ? w[(size_t)(g0 + g) * 656 + (ci * 41 + k) * 4 + co] : 0.f;  // packed [group][ci][k][co]
+    // staging (see grouped_dx4_kernel): the CTA's 8 groups are one contiguous run of the packed [group][ci][k][co] weights
+    {
+        float *pz = ws + threadIdx.x * KP + 41;  // 128 (group, co, ci) rows: zero padding of taps 41..43
+        pz[0] = 0.f; pz[1] = 0.f; pz[2] = 0.f;
     }
+    const float *wg = w + (size_t)g0 * 656;
+#pragma unroll 8
+    for (int i = threadIdx.x; i < NG * 656; i += 128) {
+        const int g = i / 656, rem = i - g * 656, cik = rem >> 2, co = rem & 3, ci = cik / 41, k = cik - ci * 41;
+        ws[((g * 4 + co) * 4 + ci) * KP + k] = wg[i];
+    }
+#pragma unroll 7
     for (int i = threadIdx.x; i < NG * 4 * ZW; i += 128) {
         const int c = i / ZW, t = p0 - 20 + i % ZW;  // stride 1: Lout == Lin
         zs[i] = (t >= 0 && t < Lin) ? dz[((size_t)b * C + g0 * 4 + c) * Lin + t] : 0.f;
     }
     __syncthreads();
     const int g = threadIdx.x >> 4, pb = threadIdx.x & 15, p = p0 + 8 * pb;
+    if (p >= Lin) return;  // (a 65- or 33-position sequence fills half / a quarter of its last tile)
     float acc[4][8];
 #pragma unroll
     for (int ci = 0; ci < 4; ++ci)
@@ -345,21 +354,24 @@ __global__ void __launch_bounds__(192) grouped_dw1_kernel(const float *__restric
     for (int tile = first; tile < last; ++tile) {
         const int b = tile / tiles_per_item, t0 = (tile - b * tiles_per_item) * TT;
         __syncthreads();
+#pragma unroll 6
         for (int i = tid; i < NG * 4 * TT; i += 192) {
             const int c = i / TT, t = t0 + i % TT;
             zs[i] = t < L ? dz[((size_t)b * C + g0 * 4 + c) * L + t] : 0.f;
         }
+#pragma unroll 6
         for (int i = tid; i < NG * 4 * XW; i += 192) {
             const int c = i / XW, p = t0 - 20 + i % XW;
             xs[i] = (p >= 0 && p < L) ? x[((size_t)b * C + g0 * 4 + c) * L + p] : 0.f;
         }
         __syncthreads();
+        const int nt = min(TT, L - t0);  // positions of this tile that exist
         const float *zr = zs + g * 4 * TT, *xr = xs + (g * 4 + ci) * XW + 8 * tb;
         float xw[8];  // x[ci][t + 8 tb + j - 20], slid along t
 #pragma unroll
         for (int j = 0; j < 8; ++j) xw[j] = xr[j];
 #pragma unroll 8
-        for (int t = 0; t < TT; ++t) {
+        for (int t = 0; t < nt; ++t) {
             const float z0 = zr[t], z1 = zr[TT + t], z2 = zr[2 * TT + t], z3 = zr[3 * TT + t];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
