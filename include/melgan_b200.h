@@ -212,6 +212,16 @@ int mg_msd_post1_wgrad(const float *x, const float *dz, float *dw, float *db, in
 size_t mg_msd_edge_backward_workspace_bytes(int layer, int Bt, int L);
 int mg_msd_edge_backward(const void *packed, int scale, int layer, const float *dz, const float *x, float *dx, float *dw, float *db,
                          void *workspace, size_t workspace_bytes, int Bt, int L, void *stream);
+/* The whole backward of discriminator `scale` in ONE call (autograd of Discriminator.forward, models.py:87-103): the host side
+ * walks the seven layers from the logits down and enqueues the kernels of the entry points above itself.
+ *   x0 [Bt][1][L0]: the discriminator's input (the pooled audio for scale > 0); fmap[7]: the maps the forward returned;
+ *   gfmap[7]: gradient w.r.t. each returned map (NULL entries: none); gx0 [Bt][1][L0] or NULL (input gradient not needed);
+ *   dw[7] / db[7]: outputs, gradient of each layer's FOLDED weight (torch layout) and bias -- layers the gradient does not
+ *   reach are left untouched and reported in reached[7] (host ints, may be NULL); workspace: bytes from the helper. */
+size_t mg_msd_scale_backward_workspace_bytes(int Bt, int L0);
+int mg_msd_scale_backward(const void *packed, int scale, const float *x0, const float *const *fmap, const float *const *gfmap,
+                          float *gx0, float *const *dw, float *const *db, int *reached, void *workspace, size_t workspace_bytes,
+                          int Bt, int L0, void *status_word, void *stream);
 int mg_lrelu_backward(const float *g1, const float *g2, const float *out, float *dz, long long n, void *stream);
 size_t mg_msd_grouped_backward_workspace_bytes(int layer, int Bt, int Lout);
 int mg_msd_grouped_backward(const void *packed, int scale, int layer, const float *dz, const float *x, float *dx, float *dw,

@@ -188,6 +188,23 @@ int mg_msd_edge_backward(const void *packed, int scale, int layer, const float *
     return launch_disc_edge_backward(blob, layer, dz, x, dx, dw, db, (float *)workspace, Bt, L, (cudaStream_t)stream);
 }
 
+size_t mg_msd_scale_backward_workspace_bytes(int Bt, int L0) {
+    return (Bt > 0 && L0 > 0) ? disc_scale_backward_workspace_bytes(Bt, L0) : 0;
+}
+
+int mg_msd_scale_backward(const void *packed, int scale, const float *x0, const float *const *fmap, const float *const *gfmap,
+                          float *gx0, float *const *dw, float *const *db, int *reached, void *workspace, size_t workspace_bytes,
+                          int Bt, int L0, void *status_word, void *stream) {
+    if (!packed || !x0 || !fmap || !gfmap || !dw || !db || !workspace || !status_word || scale < 0 || scale > 2 || Bt < 1 || L0 < 1)
+        return set_error(MG_ERR_INVALID_ARGUMENT, "mg_msd_scale_backward: bad argument");
+    for (int l = 0; l < kDiscLayers; ++l)
+        if (!fmap[l]) return set_error(MG_ERR_INVALID_ARGUMENT, "mg_msd_scale_backward: fmap[%d] is NULL", l);
+    if (Bt > 65535) return set_error(MG_ERR_INVALID_ARGUMENT, "discriminator batch %d exceeds 65535", Bt);
+    const uint8_t *blob = reinterpret_cast<const uint8_t *>(packed) + (size_t)scale * d_blob_bytes();
+    return launch_disc_scale_backward(blob, x0, fmap, gfmap, gx0, dw, db, reached, workspace, workspace_bytes, Bt, L0,
+                                      (int *)status_word, (cudaStream_t)stream);
+}
+
 int mg_lrelu_backward(const float *g1, const float *g2, const float *out, float *dz, long long n, void *stream) {
     return launch_lrelu_grad(g1, g2, out, dz, n, (cudaStream_t)stream);
 }

@@ -87,6 +87,10 @@ int launch_disc_post1_tc(const float *x, float *y, const uint8_t *wtc, const flo
 int launch_disc_post1_dgrad_tc(const float *dz, float *dx, const uint8_t *wtcT, const float *zero_bias, int Bt, int L, int *status,
                                cudaStream_t s);
 int launch_disc_post1_wgrad_tc(const float *x, const float *dz, float *dw, float *db, int Bt, int L, int *status, cudaStream_t s);
+size_t disc_scale_backward_workspace_bytes(int Bt, int L0);
+int launch_disc_scale_backward(const void *blob, const float *x0, const float *const *fmap, const float *const *gfmap, float *gx0,
+                               float *const *dw, float *const *db, int *reached, void *workspace, size_t workspace_bytes, int Bt,
+                               int L0, int *status, cudaStream_t st);
 size_t edge_bwd_workspace_bytes(int l, int Bt, int L);
 int launch_disc_edge_backward(const void *blob, int l, const float *dz, const float *x, float *dx, float *dw, float *db, float *ws,
                               int Bt, int L, cudaStream_t s);

@@ -101,6 +101,11 @@ def lib():
         L.mg_msd_edge_backward.restype = ctypes.c_int
         L.mg_msd_edge_backward.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 6 + [
             ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        L.mg_msd_scale_backward_workspace_bytes.restype = ctypes.c_size_t
+        L.mg_msd_scale_backward_workspace_bytes.argtypes = [ctypes.c_int, ctypes.c_int]
+        L.mg_msd_scale_backward.restype = ctypes.c_int
+        L.mg_msd_scale_backward.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 8 + [
+            ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         L.mg_lrelu_backward.restype = ctypes.c_int
         L.mg_lrelu_backward.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_longlong, ctypes.c_void_p]
         L.mg_msd_wn_backward.restype = ctypes.c_int
@@ -495,6 +500,37 @@ class DiscriminatorDevice:
             check(fn(self.packed.data_ptr(), y.data_ptr(), Bt, L, ptrs, self.status.data_ptr(), stream))
             self._watch.arm(self.status[:1])
         return fmaps
+
+    def scale_backward(self, scale, x0, fmaps, grads, need_gx0):
+        """The whole backward of discriminator `scale` in one host call (mg_msd_scale_backward): x0 [Bt, 1, L0] its input,
+        fmaps the 7 maps its forward returned, grads the gradient w.r.t. each (None: none).  Returns (gx0 | None, dws[7],
+        dbs[7]) -- gradients of the FOLDED weights in torch layout; entries of layers the gradient does not reach are None.
+        The intermediate gradients live in a workspace that is reused by every call on this device (the calls are ordered
+        by the stream they are enqueued on)."""
+        torch = self.torch
+        from .synth import DISCRIMINATOR_LAYERS
+        x0 = x0.contiguous()
+        Bt, _, L0 = x0.shape
+        gs = [g.contiguous() if g is not None else None for g in grads]
+        keep = [f.contiguous() for f in fmaps]
+        dws = [torch.empty((cout, cin // groups, k), dtype=torch.float32, device=self.device)
+               for _n, cin, cout, k, _s, groups, _p in DISCRIMINATOR_LAYERS]
+        dbs = [torch.empty((cout,), dtype=torch.float32, device=self.device) for _n, _cin, cout, *_ in DISCRIMINATOR_LAYERS]
+        gx0 = torch.empty_like(x0) if need_gx0 else None
+        nbytes = lib().mg_msd_scale_backward_workspace_bytes(Bt, L0)
+        ws = self.__dict__.get("_bwd_ws")
+        if ws is None or ws.numel() * 4 < nbytes:
+            ws = self._bwd_ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=self.device)
+        reached = (ctypes.c_int * 7)()
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            check(lib().mg_msd_scale_backward(
+                self.packed.data_ptr(), scale, x0.data_ptr(), _ptr_array([f.data_ptr() for f in keep]),
+                _ptr_array([g.data_ptr() if g is not None else None for g in gs]), gx0.data_ptr() if need_gx0 else None,
+                _ptr_array([t.data_ptr() for t in dws]), _ptr_array([t.data_ptr() for t in dbs]), reached, ws.data_ptr(),
+                ws.numel() * 4, Bt, L0, self.status.data_ptr(), stream))
+        hit = [bool(r) for r in reached]
+        return (gx0 if hit[0] else None), [w if h else None for w, h in zip(dws, hit)], [b if h else None for b, h in zip(dbs, hit)]
 
     def grouped_backward(self, scale, layer, dz, x, need_dx=True):
         """Gradients of grouped conv `layer` (1..4) of discriminator `scale`: dz [Bt, Cout, Lout] (already multiplied by

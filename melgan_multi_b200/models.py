@@ -280,26 +280,9 @@ class _MSDFunction(torch.autograd.Function):
         x0 = y2
         for k in range(s):  # the scale's input: the AvgPool chain of models.py:114-117,125-127
             x0 = host.meanpools[k](x0)
-        inputs = [x0] + list(fm[:6])
-        dws, dbs = [None] * 7, [None] * 7
-        g = None
-        for l in range(6, -1, -1):
-            go = grads[l]
-            if g is None and go is None:
-                continue
-            if l < 6:  # (g + go) * LeakyReLU'(layer output), one launch
-                dz = dev.lrelu_backward(g, go, fm[l])
-            else:
-                dz = (go if g is None else g if go is None else g + go).contiguous()
-            need_dx = l > 0 or need_y
-            _n, _cin, cout, _k, stride, groups, pad = DISCRIMINATOR_LAYERS[l]
-            if groups > 1:
-                g, dws[l], dbs[l] = dev.grouped_backward(s, l, dz, inputs[l], need_dx)
-            elif l == 5:  # conv_post1 (88 % of a discriminator's FLOPs): data and weight gradients on the tcgen05 kernels
-                g = dev.post1_dgrad(s, dz)
-                dws[l], dbs[l] = dev.post1_wgrad(inputs[l], dz)
-            else:  # conv_pre / conv_post2: bandwidth-bound SIMT kernels (csrc/mg_disc_edge_bwd.cu)
-                g, dws[l], dbs[l] = dev.edge_backward(s, l, dz, inputs[l], need_dx)
+        # one host call walks the seven layers and enqueues every kernel (csrc/mg_disc_bwd_chain.cu): LeakyReLU', grouped convs,
+        # conv_post1 dgrad / wgrad on tcgen05, conv_pre / conv_post2 -- the step was bound by per-kernel Python launches
+        g, dws, dbs = dev.scale_backward(s, x0, fm, grads, need_y)
         gy = None
         if need_y and g is not None:  # back through the (linear) AvgPool chain: differentiate it on zeros
             gy = g
