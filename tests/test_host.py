@@ -206,6 +206,21 @@ def test_cabi_argument_errors_are_reported_not_thrown():
     assert L.mg_disc_packed_bytes() * 3 == L.mg_msd_packed_bytes()
     assert L.mg_disc_pack(None, None, None, None, None) == -1 and L.mg_disc_forward(p, p, 1, 0, p, p, None) == -1
     assert L.mg_adam_chunk() == 4096 and L.mg_adam_step(None, None, None, None, None, None, 1, 1, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1, None) == -1
+    # round-2 backward entry points of the discriminators: conv_post1 dgrad / wgrad, conv_pre / conv_post2, the one-call chain
+    assert L.mg_msd_post1_dgrad(p, 3, p, ctypes.c_void_p(512), 2, 8, p, None) == -1  # scale 0..2
+    assert L.mg_msd_post1_dgrad(p, 0, p, p, 2, 8, p, None) == -1                     # dz and dx must differ
+    assert L.mg_msd_post1_wgrad(p, p, None, p, 2, 8, p, None) == -1
+    assert L.mg_msd_edge_backward_workspace_bytes(0, 2, 1024) == 2 * 2 * 256 * 4 and L.mg_msd_edge_backward_workspace_bytes(6, 2, 64) == 0
+    assert L.mg_msd_edge_backward(p, 0, 3, p, p, p, p, p, p, 1 << 20, 2, 64, None) == -1 and b"layer is 0" in L.mg_last_error_string()
+    assert L.mg_msd_edge_backward(p, 0, 0, p, p, p, p, p, p, 16, 2, 1024, None) == -4  # conv_pre needs its workspace
+    big, small = L.mg_msd_scale_backward_workspace_bytes(32, 8192), L.mg_msd_scale_backward_workspace_bytes(2, 1024)
+    assert big > small > 0 and L.mg_msd_scale_backward_workspace_bytes(0, 64) == 0
+    assert big >= 3 * 32 * 16 * 8192 * 4  # dz + two alternating dx buffers of the largest activation
+    seven = (ctypes.c_void_p * 7)(*([256] * 7))
+    none7 = (ctypes.c_void_p * 7)()
+    assert L.mg_msd_scale_backward(p, 0, p, none7, seven, None, seven, seven, None, p, big, 2, 1024, p, None) == -1
+    assert b"fmap[0]" in L.mg_last_error_string()
+    assert L.mg_msd_scale_backward(p, 0, p, seven, seven, None, seven, seven, None, p, 16, 2, 1024, p, None) == -4
 
 
 def _train_case():
