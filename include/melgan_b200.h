@@ -189,43 +189,51 @@ int mg_gen_engine_forward(mg_gen_engine *e, const float *mel_host, float *audio_
 int mg_gen_engine_last_kernel_ms(mg_gen_engine *e, float *ms);
 void mg_gen_engine_destroy(mg_gen_engine *e);
 
-/* ---- discriminator backward pieces (autograd of Discriminator.forward, models.py:87-103) ------------------------
- * Gradients of ONE grouped conv (layer 1..4: k41, pad 20, 4 input channels per group, stride 4/4/4/1) of discriminator
- * `scale` of the packed MSD blob, each a single launch (cuDNN runs one kernel per group):
- *   dz [Bt][Cout][Lout]: upstream gradient already multiplied by LeakyReLU'(layer output);  x [Bt][Cin][Lin]: layer input
- *   dx [Bt][Cin][Lin] (NULL: skip), dw [Cout][4][41] + db [Cout] (dw NULL: skip both) -- dw is the gradient of the FOLDED
- *   weight; mg_msd_wn_backward turns the 21 layers' dw into (d weight_v, d weight_g) in one launch (dw[i] NULL: skip). */
-/* dz = (g1 + g2) * LeakyReLU'(out) over n elements (g2 may be NULL): the gradient entering a layer's pre-activation from the
- * next layer and from the feature-map loss, in one launch (F.leaky_relu backward of models.py:91,94,97 + the add). */
-/* Data gradient of conv_post1 (Conv1d 1024 -> 1024, k5, pad 2; models.py:84,96) of discriminator `scale`: dz [Bt][1024][L] (already
- * multiplied by LeakyReLU') -> dx [Bt][1024][L], on the same tcgen05 kernel as the forward, streaming the transposed, tap-flipped
- * copy of the weights that mg_msd_pack / mg_disc_pack keep for it. */
-int mg_msd_post1_dgrad(const void *packed, int scale, const float *dz, float *dx, int Bt, int L, void *status_word, void *stream);
-/* Weight and bias gradient of conv_post1 (autograd of models.py:96; no weights needed): x [Bt][1024][L] (the layer input),
- * dz [Bt][1024][L] -> dw [1024][1024][5] (gradient of the FOLDED weight, torch layout), db [1024]; one tcgen05 launch, split-bf16
- * (fp32-grade) with fp32 accumulation over all Bt * L positions. */
-int mg_msd_post1_wgrad(const float *x, const float *dz, float *dw, float *db, int Bt, int L, void *status_word, void *stream);
-/* Backward of conv_pre (layer 0: Conv1d 1 -> 16, k15; x [Bt][1][L], dz [Bt][16][L], dw [16][1][15]) or conv_post2 (layer 6:
- * Conv1d 1024 -> 1, k3; x [Bt][1024][L], dz [Bt][1][L], dw [1][1024][3]) of discriminator `scale` (autograd of models.py:90,99):
- * dx (same shape as x; NULL: skip -- conv_pre's is only needed when the audio requires a gradient), dw (gradient of the FOLDED
- * weight, torch layout), db.  fp32, fixed summation order.  Layer 0 needs a workspace (bytes from the helper), layer 6 none. */
-size_t mg_msd_edge_backward_workspace_bytes(int layer, int Bt, int L);
-int mg_msd_edge_backward(const void *packed, int scale, int layer, const float *dz, const float *x, float *dx, float *dw, float *db,
-                         void *workspace, size_t workspace_bytes, int Bt, int L, void *stream);
-/* The whole backward of discriminator `scale` in ONE call (autograd of Discriminator.forward, models.py:87-103): the host side
- * walks the seven layers from the logits down and enqueues the kernels of the entry points above itself.
+/* ---- discriminator backward (autograd of Discriminator.forward, models.py:87-103): no aten / cuDNN call is left --------
+ * Conventions: dz = gradient w.r.t. a layer's PRE-activation output (i.e. already multiplied by LeakyReLU'), x = the layer's
+ * input, dw = gradient of the layer's FOLDED weight in torch layout, db = bias gradient; mg_msd_wn_backward turns the layers'
+ * dw into (d weight_v, d weight_g). */
+
+/* The whole backward of discriminator `scale` in ONE call: the host side walks the seven layers from the logits down and
+ * enqueues the kernels of the per-layer entry points below itself (what models._MSDFunction.backward uses).
  *   x0 [Bt][1][L0]: the discriminator's input (the pooled audio for scale > 0); fmap[7]: the maps the forward returned;
  *   gfmap[7]: gradient w.r.t. each returned map (NULL entries: none); gx0 [Bt][1][L0] or NULL (input gradient not needed);
- *   dw[7] / db[7]: outputs, gradient of each layer's FOLDED weight (torch layout) and bias -- layers the gradient does not
- *   reach are left untouched and reported in reached[7] (host ints, may be NULL); workspace: bytes from the helper. */
+ *   dw[7] / db[7]: outputs -- layers the gradient does not reach are left untouched and reported in reached[7] (host ints,
+ *   may be NULL); workspace: bytes from the helper. */
 size_t mg_msd_scale_backward_workspace_bytes(int Bt, int L0);
 int mg_msd_scale_backward(const void *packed, int scale, const float *x0, const float *const *fmap, const float *const *gfmap,
                           float *gx0, float *const *dw, float *const *db, int *reached, void *workspace, size_t workspace_bytes,
                           int Bt, int L0, void *status_word, void *stream);
+
+/* dz = (g1 + g2) * LeakyReLU'(out) over n elements (g2 may be NULL): the gradient entering a layer's pre-activation from the
+ * next layer and from the feature-map loss, in one launch (F.leaky_relu backward of models.py:91,94,97 + the add). */
 int mg_lrelu_backward(const float *g1, const float *g2, const float *out, float *dz, long long n, void *stream);
+
+/* Gradients of ONE grouped conv (layer 1..4: k41, pad 20, 4 input channels per group, stride 4/4/4/1) of discriminator
+ * `scale` of the packed MSD blob, each a single launch (cuDNN runs one kernel per group):
+ *   dz [Bt][Cout][Lout], x [Bt][Cin][Lin]; dx [Bt][Cin][Lin] (NULL: skip), dw [Cout][4][41] + db [Cout] (dw NULL: skip both). */
 size_t mg_msd_grouped_backward_workspace_bytes(int layer, int Bt, int Lout);
 int mg_msd_grouped_backward(const void *packed, int scale, int layer, const float *dz, const float *x, float *dx, float *dw,
                             float *db, void *workspace, size_t workspace_bytes, int Bt, int Lin, int Lout, void *stream);
+
+/* Data gradient of conv_post1 (Conv1d 1024 -> 1024, k5, pad 2; models.py:84,96) of discriminator `scale`: dz [Bt][1024][L]
+ * -> dx [Bt][1024][L], on the same tcgen05 kernel as the forward, streaming the transposed, tap-flipped copy of the weights
+ * that mg_msd_pack / mg_disc_pack keep for it. */
+int mg_msd_post1_dgrad(const void *packed, int scale, const float *dz, float *dx, int Bt, int L, void *status_word, void *stream);
+/* Weight and bias gradient of conv_post1 (no weights needed): x [Bt][1024][L], dz [Bt][1024][L] -> dw [1024][1024][5],
+ * db [1024]; one tcgen05 launch, split-bf16 (fp32-grade) with fp32 accumulation over all Bt * L positions. */
+int mg_msd_post1_wgrad(const float *x, const float *dz, float *dw, float *db, int Bt, int L, void *status_word, void *stream);
+
+/* Backward of conv_pre (layer 0: Conv1d 1 -> 16, k15; x [Bt][1][L], dz [Bt][16][L], dw [16][1][15]) or conv_post2 (layer 6:
+ * Conv1d 1024 -> 1, k3; x [Bt][1024][L], dz [Bt][1][L], dw [1][1024][3]) of discriminator `scale` (autograd of models.py:90,99):
+ * dx (same shape as x; NULL: skip -- conv_pre's is only needed when the audio requires a gradient), dw, db.  fp32, fixed
+ * summation order.  Layer 0 needs a workspace (bytes from the helper), layer 6 none. */
+size_t mg_msd_edge_backward_workspace_bytes(int layer, int Bt, int L);
+int mg_msd_edge_backward(const void *packed, int scale, int layer, const float *dz, const float *x, float *dx, float *dw, float *db,
+                         void *workspace, size_t workspace_bytes, int Bt, int L, void *stream);
+
+/* weight-norm backward of the 21 layers of an MSD blob in one launch: v, g, dw, dv, dg are HOST arrays of 21 device pointers
+ * (dw[i] NULL: layer skipped):  dg = <dw, v> / |v|,  dv = (g / |v|) (dw - <dw, v> v / |v|^2) per norm row. */
 int mg_msd_wn_backward(const float *const *v, const float *const *g, const float *const *dw, float *const *dv,
                        float *const *dg, void *stream);
 
